@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — embed+detect FPS of the watermark hot path on B200 (BASELINE.json metric), one JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload image1080p|video4k|image4k|image8k|batch256|image512]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      # the reference path on the host CPU cores (oracle port, all threads)
+
+A "step" is one pass of the hot path over one batch of synthetic frames that are resident in HBM before the
+timed region: every frame goes through NVF embed, ME embed, NVF detect and ME detect (image workloads; the
+reference's testForImage protocol, main.cpp:167-223) or ME embed + ME detect (video workload, main.cpp:343-410).
+`value` = frames/s over all ranks (device-timed, max over ranks); `e2e` = the same metric through the
+host-buffer C-ABI calls with pinned HOST buffers (H2D + D2H inside the timed region).
+The batch is larger than L2 (126 MB), so every step streams its inputs from HBM.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (rows, cols, frames per step, kind, dtype)
+    "image512": (512, 512, 256, "image", "f32"),
+    "image1080p": (1080, 1920, 64, "image", "f32"),
+    "image4k": (2160, 3840, 16, "image", "f32"),
+    "image8k": (4320, 7680, 4, "image", "f32"),
+    "batch256": (256, 256, 4096, "image", "f32"),
+    "video4k": (2160, 3840, 32, "video", "u8"),
+}
+# algorithmic (compulsory) bytes per pixel and kernel: every distinct operand read once, every output written
+# once (SURVEY.md §8d / DESIGN.md): f32 image, f32 W, f32 out; u8 frames: 1-byte pixels
+ALG_BYTES = {
+    "f32": {"rx_sweep": 4, "me_stats": 8, "nvf_stats": 8, "embed_apply": 12, "detect_apply": 8},
+    "u8": {"rx_sweep": 1, "me_stats": 5, "nvf_stats": 5, "embed_apply": 6, "detect_apply": 5},
+}
+PAIR_BYTES = {"f32": 20, "u8": 11}  # embed + detect per pixel
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx = float(f[1])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[0]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        if not sm:  # region shorter than the sampling period: take whatever was seen
+            for ts, line in self.rows:
+                try:
+                    sm.append(float(line.split(",")[0]))
+                except ValueError:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(rows, cols, n, dtype):
+    import util
+    base = util.natural_image(rows, cols, seed=1)
+    rng = np.random.default_rng(7)
+    out = np.empty((n, rows, cols), np.uint8 if dtype == "u8" else np.float32)
+    for i in range(n):  # distinct natural-statistics frames: cyclic shift + light noise
+        f = np.roll(base, (3 * i + 1, 5 * i + 2), (0, 1)) + rng.uniform(-2, 2, base.shape).astype(np.float32)
+        f = np.clip(f, 0, 255)
+        out[i] = np.rint(f) if dtype == "u8" else f
+    W = util.normal_w(rows, cols, seed=28390211)
+    return out, W
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_frame(oracle, img, W, kind):
+    """one frame through the same ops as the GPU step"""
+    if kind == "video":
+        st, out, a = oracle.embed_frame_u8(img, W, 40.0, oracle.ME)
+        oracle.detect_frame_u8(out, W, oracle.ME)
+        return
+    for mask in (oracle.NVF, oracle.ME):
+        o = oracle.embed(img, W, 40.0, mask)
+        oracle.detect(o["out"], W, mask)
+
+
+def cpu_baseline(oracle, frames, W, kind, budget_s=12.0):
+    t = time.perf_counter()
+    cpu_frame(oracle, frames[0], W, kind)  # warm-up + calibration
+    t1 = time.perf_counter() - t
+    n = int(max(2, min(len(frames), round(budget_s / max(t1, 1e-3)))))
+    t = time.perf_counter()
+    for i in range(n):
+        cpu_frame(oracle, frames[i % len(frames)], W, kind)
+    dt = time.perf_counter() - t
+    return n / dt, n
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle
+    rows, cols, nfr, kind, dtype = WORKLOADS[wl]
+    frames, W = make_inputs(rows, cols, min(nfr, 4), dtype)
+    # bounded sample per step so the whole run ends within minutes
+    t = time.perf_counter()
+    cpu_frame(oracle, frames[0], W, kind)
+    t1 = time.perf_counter() - t
+    per_step = int(max(1, min(8, round(3.0 / max(t1, 1e-3)))))
+    for _ in range(args.warmup):
+        cpu_frame(oracle, frames[0], W, kind)
+    t = time.perf_counter()
+    for s in range(args.steps):
+        for i in range(per_step):
+            cpu_frame(oracle, frames[(s * per_step + i) % len(frames)], W, kind)
+    dt = time.perf_counter() - t
+    fps = args.steps * per_step / dt
+    line = {
+        "impl": "reference", "metric": "embed+detect FPS (NVF & PE masks)" if kind == "image" else "embed+detect FPS (PE mask, u8 video frames)",
+        "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if dtype == "f32" else "u8->f32", "data": "synthetic",
+        "config": {"workload": wl, "rows": rows, "cols": cols, "frames_per_step": per_step, "p": 3, "psnr": 40.0,
+                   "ops_per_frame": "NVF embed, ME embed, NVF detect, ME detect" if kind == "image" else "ME embed, ME detect"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": oracle.num_threads(), "kind": "port",
+                         "sample": "%d frame(s) per step x %d steps of %s on the host CPU (OpenMP oracle restating "
+                                   "Watermark.cpp; ArrayFire/OpenCL are not installable offline)" % (per_step, args.steps, wl)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="image1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exact", action="store_true", help="f32 products in Rx/rx instead of the reference's fp16 rounding")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = args.workload
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pkg = importlib.import_module("watermarking-gpu_b200")
+    C = pkg.C
+
+    rows, cols, nfr, kind, dtype = WORKLOADS[wl]
+    npx = rows * cols
+    frames_np, W = make_inputs(rows, cols, nfr, dtype)
+    stream = torch.cuda.Stream(device=dev)
+    wm = pkg.Watermark(rows, cols, W, 3, 40.0, device=local_rank, stream=stream.cuda_stream)
+    if args.exact:
+        wm.set_option(pkg.OPT_FP16_PRODUCTS, 0)
+    tdt = torch.uint8 if dtype == "u8" else torch.float32
+    dt_code = pkg.U8 if dtype == "u8" else pkg.F32
+    # image workloads: ArrayFire layout (column-major); video: row-major Y planes
+    layout = pkg.ROW_MAJOR if kind == "video" else pkg.COL_MAJOR
+    mem = frames_np if layout == pkg.ROW_MAJOR else np.ascontiguousarray(frames_np.transpose(0, 2, 1))
+    d_in = torch.from_numpy(mem).to(dev)
+    d_out = [torch.empty_like(d_in) for _ in range(2)]  # NVF-marked, ME-marked
+    a_host = [np.zeros(nfr, np.float32) for _ in range(2)]
+    c_host = [np.zeros(nfr, np.float32) for _ in range(2)]
+    st_host = np.zeros(nfr, np.int32)
+    di = pkg.image_desc(d_in.data_ptr(), rows, cols, layout, dt_code)
+    do = [pkg.image_desc(t.data_ptr(), rows, cols, layout, dt_code) for t in d_out]
+
+    vctx_e = pkg.VideoProcessingContext(wm, rows, cols, 1, linesize=cols, frames_on_device=True)
+
+    def step():
+        if kind == "video":
+            pkg.process_frames(vctx_e, pkg.VIDEO_EMBED, d_in.data_ptr(), d_out[1].data_ptr(), 0, nfr, a_host[1])
+            pkg.process_frames(vctx_e, pkg.VIDEO_DETECT, d_out[1].data_ptr(), None, 0, nfr, c_host[1])
+            return
+        for k, mask in enumerate((pkg.NVF, pkg.ME)):
+            wm.embed_batch(0, di, di, do[k], npx, npx, npx, nfr, mask, a_host[k], st_host)
+            wm.detect_batch(0, do[k], npx, nfr, mask, c_host[k], st_host)
+        wm.sync(0)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        wm.set_option(pkg.OPT_KERNEL_TIMING, 1)
+        wm.kernel_times(reset=True)
+        l0 = wm.launch_count
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        launches = wm.launch_count - l0
+        ktimes = wm.kernel_times(reset=True)
+        wm.set_option(pkg.OPT_KERNEL_TIMING, 0)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    fps = world * nfr * args.steps / (ms * 1e-3)
+
+    # ---- e2e: the host-buffer C-ABI calls, pinned host memory, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = min(nfr, 8)
+        pin_in = torch.from_numpy(mem[:n_e2e].copy()).pin_memory()
+        pin_out = torch.empty_like(pin_in).pin_memory()
+        fb = pin_in[0].numel() * pin_in.element_size()
+
+        def e2e_frame(i):
+            src, dst = pin_in[i].numpy(), pin_out[i].numpy()
+            if kind == "video":
+                wm.make_watermark_host(src, src, dst, pkg.ME, layout)
+                wm.detect_watermark_host(dst, pkg.ME, layout)
+                return 2 * fb, fb
+            for mask in (pkg.NVF, pkg.ME):
+                wm.make_watermark_host(src, src, dst, mask, layout)
+                wm.detect_watermark_host(dst, mask, layout)
+            return 4 * fb, 2 * fb
+
+        with torch.cuda.stream(stream):
+            for i in range(min(3, n_e2e)):
+                e2e_frame(i)
+            barrier()
+            reps = max(1, args.steps // 2)
+            tt = time.perf_counter()
+            h2d = d2h = 0
+            for r in range(reps):
+                for i in range(n_e2e):
+                    a_, b_ = e2e_frame(i)
+                    h2d += a_
+                    d2h += b_
+            torch.cuda.synchronize(dev)
+            e2e_s = time.perf_counter() - tt
+        if dist is not None:
+            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": world * reps * n_e2e / e2e_s, "unit": "frames/s",
+               "h2d_bytes_per_step": int(h2d / reps), "d2h_bytes_per_step": int(d2h / reps),
+               "frames_per_step": n_e2e, "api": "wm_embed_host / wm_detect_host (pinned host buffers)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (largest share of device time in the timed region) ----
+    peak, peak_src = peaks()
+    kern = []
+    for name, (n, tot_ms) in ktimes.items():
+        if n == 0:
+            continue
+        per_launch_px = npx * (nfr if kind == "image" else 1)
+        alg = ALG_BYTES[dtype][name] * per_launch_px
+        avg_ms = tot_ms / n
+        kern.append({"kernel": name, "launches": n, "avg_ms": avg_ms, "total_ms": tot_ms,
+                     "alg_bytes_per_launch": alg, "achieved_gbs": alg / (avg_ms * 1e-3) / 1e9})
+    kern.sort(key=lambda k: -k["total_ms"])
+    dom = kern[0] if kern else None
+    roof = None
+    if dom:
+        roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dom["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": dom["alg_bytes_per_launch"], "avg_launch_ms": dom["avg_ms"]}
+        tr = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the ncu --set full capture
+        if os.path.exists(tr):
+            try:
+                roof["traffic"] = json.load(open(tr)).get(wl, {}).get(dom["kernel"])
+            except Exception:
+                pass
+    # whole-step effective bandwidth on the compulsory bytes of embed+detect pairs
+    pairs = 2 if kind == "image" else 1
+    step_bytes = PAIR_BYTES[dtype] * npx * nfr * pairs
+    cb = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle
+        v, n = cpu_baseline(oracle, frames_np, W, kind)
+        cb = {"value": v, "unit": "frames/s", "cores": oracle.num_threads(), "kind": "port",
+              "sample": "%d frames of %s, same ops per frame, OpenMP oracle (restates Watermark.cpp; the reference's "
+                        "ArrayFire/OpenCL stack cannot be built offline)" % (n, wl)}
+    line = {
+        "metric": "embed+detect FPS (NVF & PE masks)" if kind == "image" else "embed+detect FPS (PE mask, u8 video frames)",
+        "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if dtype == "f32" else "u8->f32", "data": "synthetic",
+        "config": {"workload": wl, "rows": rows, "cols": cols, "frames_per_step": nfr, "p": 3, "psnr": 40.0,
+                   "layout": "col-major (ArrayFire)" if layout == pkg.COL_MAJOR else "row-major Y plane",
+                   "ops_per_frame": "NVF embed, ME embed, NVF detect, ME detect" if kind == "image" else "ME embed, ME detect",
+                   "fp16_products": not args.exact,
+                   "l2": "inputs larger than L2: %.0f MB of frames + W per step" % ((d_in.numel() * d_in.element_size() + W.nbytes) / 1e6),
+                   "sharding": "frames sharded by rank, no collective on the data path"},
+        "step_effective_gbs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+        "step_frac_of_peak": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
+        "roofline": roof, "kernels": kern, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks,
+        "results": {"a_nvf": float(a_host[0][0]), "a_me": float(a_host[1][0]), "corr_nvf": float(c_host[0][0]),
+                    "corr_me": float(c_host[1][0])},
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,938 @@
+// wm_api.cu — context, launch orchestration and the C ABI declared in include/wm_b200.h.
+//
+// Mirrors the reference's Watermark object (Watermark_GPU/Watermark.{hpp,cpp}): a ctx owns W, the strength
+// factor and per-slot workspaces (the reference owns one staging texture => one object per concurrent caller;
+// here each slot has its own stream + workspace so one ctx can pipeline frames).  There is no CPU fallback.
+#include "wm_kernels.cuh"
+#include "../../include/wm_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace wm;
+
+#define WM_VERSION_STR "wm_b200 0.1 (sm_100a)"
+
+namespace {
+
+constexpr int NSLOTS = 4;
+thread_local std::string g_create_error;
+
+struct WShared {  // W is shared between clones, like the ref-counted af::array (Watermark.cpp:31)
+    int device = 0;
+    float* row_major = nullptr;  // rows x cols
+    float* col_major = nullptr;  // lazily transposed copy for WM_COL_MAJOR images
+    std::mutex mu;
+    ~WShared()
+    {
+        cudaSetDevice(device);
+        if (row_major) cudaFree(row_major);
+        if (col_major) cudaFree(col_major);
+    }
+};
+
+struct TimedLaunch { int kernel; cudaEvent_t e0, e1; };
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int batch_cap = 0;
+    size_t part_cap = 0;     // doubles
+    double* part = nullptr;  // sweep partials, then stats/detect partials (separate regions)
+    unsigned* counters = nullptr;  // [3][batch_cap]
+    Scal* scal = nullptr;
+    ScalDbg* dbg = nullptr;
+    Scal* scal_host = nullptr;  // pinned
+    // pending result delivery
+    int pending = 0;  // 0 none, 1 embed, 2 detect
+    int pend_batch = 0;
+    float* pend_scalar = nullptr;
+    int* pend_status = nullptr;
+    // staging for the host-buffer API / video driver
+    void* stage_in = nullptr; size_t stage_in_cap = 0;
+    void* stage_base = nullptr; size_t stage_base_cap = 0;
+    void* stage_out = nullptr; size_t stage_out_cap = 0;
+    std::vector<TimedLaunch> timed;
+};
+
+}  // namespace
+
+struct wm_ctx {
+    int device = 0, sms = 148;
+    int64_t rows = 0, cols = 0;
+    int p = 3;
+    float psnr = 0.f, strength = 0.f;
+    std::shared_ptr<WShared> w;
+    Slot slots[NSLOTS];
+    int opt_fp16 = 1, opt_timing = 0, opt_tma = 1;
+    bool inject_coef = false;
+    float injected[8];
+    std::string err;
+    double ktime_ms[WM_K_COUNT] = {0};
+    int64_t kcount[WM_K_COUNT] = {0};
+    int64_t launches = 0;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace {
+
+int fail(wm_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(ctx, WM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+struct View {  // an image reduced to lines x pixels
+    void* ptr; int L, P; long long ld, pstride; int channels; int dtype; bool transposed;
+};
+
+int make_view(wm_ctx* ctx, const wm_image* im, View* v, bool allow_rgb)
+{
+    if (!im || !im->data) return fail(ctx, WM_ERR_ARG, "null image");
+    if (im->rows != ctx->rows || im->cols != ctx->cols)
+        return fail(ctx, WM_ERR_DIMS, "image dims " + std::to_string(im->rows) + "x" + std::to_string(im->cols) +
+                                          " != watermark dims " + std::to_string(ctx->rows) + "x" + std::to_string(ctx->cols));
+    if (im->layout != WM_COL_MAJOR && im->layout != WM_ROW_MAJOR) return fail(ctx, WM_ERR_ARG, "bad layout");
+    if (im->dtype != WM_F32 && im->dtype != WM_U8) return fail(ctx, WM_ERR_ARG, "bad dtype");
+    const int ch = im->channels <= 0 ? 1 : im->channels;
+    if (ch != 1 && !(allow_rgb && ch == 3)) return fail(ctx, WM_ERR_ARG, "channels must be 1 (or 3 for base/out)");
+    v->transposed = im->layout == WM_COL_MAJOR;
+    v->L = (int)(v->transposed ? im->cols : im->rows);
+    v->P = (int)(v->transposed ? im->rows : im->cols);
+    v->ld = im->ld > 0 ? im->ld : v->P;
+    if (v->ld < v->P) return fail(ctx, WM_ERR_ARG, "ld smaller than the contiguous dimension");
+    v->pstride = im->plane_stride > 0 ? im->plane_stride : (long long)v->L * v->ld;
+    v->channels = ch;
+    v->dtype = im->dtype;
+    v->ptr = im->data;
+    return WM_OK;
+}
+
+bool vec_ok(const void* p, long long ld, long long bstride, long long pstride, int dtype)
+{
+    const uintptr_t al = dtype == WM_F32 ? 16 : 4;
+    return ((uintptr_t)p % al == 0) && (ld % 4 == 0) && (bstride % 4 == 0) && (pstride % 4 == 0);
+}
+
+int ensure_slot(wm_ctx* ctx, Slot& s, int batch, int gx_max, int nsweep, int nframe)
+{
+    if (batch > s.batch_cap) {
+        if (s.counters) cudaFree(s.counters);
+        if (s.scal) cudaFree(s.scal);
+        if (s.dbg) cudaFree(s.dbg);
+        if (s.scal_host) cudaFreeHost(s.scal_host);
+        s.counters = nullptr; s.scal = nullptr; s.dbg = nullptr; s.scal_host = nullptr;
+        CU(cudaMalloc(&s.counters, sizeof(unsigned) * 3 * batch));
+        CU(cudaMemsetAsync(s.counters, 0, sizeof(unsigned) * 3 * batch, s.stream));
+        CU(cudaMalloc(&s.scal, sizeof(Scal) * batch));
+        CU(cudaMemsetAsync(s.scal, 0, sizeof(Scal) * batch, s.stream));
+        CU(cudaMalloc(&s.dbg, sizeof(ScalDbg) * batch));
+        CU(cudaMemsetAsync(s.dbg, 0, sizeof(ScalDbg) * batch, s.stream));
+        CU(cudaMallocHost(&s.scal_host, sizeof(Scal) * batch));
+        s.batch_cap = batch;
+    }
+    const size_t need = (size_t)batch * ((size_t)nsweep * NLAG + (size_t)nframe * NFRM + (size_t)gx_max * 3);
+    if (need > s.part_cap) {
+        if (s.part) cudaFree(s.part);
+        s.part = nullptr;
+        CU(cudaMalloc(&s.part, need * sizeof(double)));
+        s.part_cap = need;
+    }
+    return WM_OK;
+}
+
+int ensure_stage(wm_ctx* ctx, void** p, size_t* cap, size_t bytes)
+{
+    if (bytes > *cap) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        CU(cudaMalloc(p, bytes));
+        *cap = bytes;
+    }
+    return WM_OK;
+}
+
+const float* w_for(wm_ctx* ctx, bool transposed, cudaStream_t st, int* rc)
+{
+    *rc = WM_OK;
+    WShared& w = *ctx->w;
+    if (!transposed) return w.row_major;
+    std::lock_guard<std::mutex> g(w.mu);
+    if (!w.col_major) {
+        if (cudaMalloc(&w.col_major, sizeof(float) * ctx->rows * ctx->cols) != cudaSuccess) {
+            *rc = fail(ctx, WM_ERR_CUDA, "cudaMalloc(W col-major)");
+            return nullptr;
+        }
+        const dim3 blk(32, 8), grd((unsigned)((ctx->cols + 31) / 32), (unsigned)((ctx->rows + 31) / 32));
+        k_transpose<<<grd, blk, 0, st>>>(w.row_major, w.col_major, (int)ctx->rows, (int)ctx->cols);
+        cudaStreamSynchronize(st);  // other slots/clones may use it right away
+    }
+    return w.col_major;
+}
+
+struct Geo { int L, P, tiles_p, tiles_l, ntiles; };
+Geo geo(int L, int P)
+{
+    Geo g;
+    g.L = L; g.P = P;
+    g.tiles_p = (P + TP - 1) / TP;
+    g.tiles_l = (L + TL - 1) / TL;
+    g.ntiles = g.tiles_p * g.tiles_l;
+    return g;
+}
+
+struct Plan { int nsweep, nframe, gx_stats, gx_detect; };
+Plan plan(const wm_ctx* ctx, const Geo& g, int batch)
+{
+    Plan p;
+    const long long ring = 4LL * (g.L + g.P);
+    if (batch == 1) {
+        p.nsweep = std::min(g.ntiles, 2 * ctx->sms);
+        p.gx_stats = std::min(g.ntiles, 3 * ctx->sms);
+        p.gx_detect = std::min(g.ntiles, 2 * ctx->sms);
+        p.nframe = (int)std::min<long long>(64, std::max<long long>(1, (ring + NT * 32 - 1) / (NT * 32)));
+    } else {
+        const int per = std::max(1, std::min(g.ntiles, (4 * ctx->sms + batch - 1) / batch));
+        p.nsweep = p.gx_stats = p.gx_detect = per;
+        p.nframe = (int)std::min<long long>(64, std::max<long long>(1, (ring + NT * 64 - 1) / (NT * 64)));
+    }
+    return p;
+}
+
+// ---- timing brackets ----
+cudaEvent_t get_event(wm_ctx* ctx)
+{
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct KTimer {
+    wm_ctx* ctx; Slot& s; int k; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KTimer(wm_ctx* c, Slot& sl, int kernel) : ctx(c), s(sl), k(kernel)
+    {
+        ctx->launches++;
+        if (ctx->opt_timing) { e0 = get_event(ctx); e1 = get_event(ctx); cudaEventRecord(e0, s.stream); }
+    }
+    ~KTimer()
+    {
+        if (e0) { cudaEventRecord(e1, s.stream); s.timed.push_back({k, e0, e1}); }
+    }
+};
+void drain_timers(wm_ctx* ctx, Slot& s)
+{
+    for (auto& t : s.timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) { ctx->ktime_ms[t.kernel] += ms; ctx->kcount[t.kernel]++; }
+        ctx->event_pool.push_back(t.e0);
+        ctx->event_pool.push_back(t.e1);
+    }
+    s.timed.clear();
+}
+
+// ---- kernel dispatch over (pixel type, out type, mask, transposed) ----
+template <typename PixT>
+void launch_sweep_t(bool fp16, dim3 grid, cudaStream_t st, const SweepArgs& a)
+{
+    if (fp16) k_sweep<PixT, true><<<grid, NT, 0, st>>>(a);
+    else k_sweep<PixT, false><<<grid, NT, 0, st>>>(a);
+}
+void launch_sweep(int dtype, bool fp16, dim3 grid, cudaStream_t st, const SweepArgs& a)
+{
+    if (dtype == WM_F32) launch_sweep_t<float>(fp16, grid, st, a); else launch_sweep_t<uint8_t>(fp16, grid, st, a);
+}
+
+#define WM_DISPATCH_MT(FN, PIX, mask, tr, ...)                                   \
+    do {                                                                         \
+        if ((mask) == WM_MASK_ME) { if (tr) FN<PIX, 0, true> __VA_ARGS__; else FN<PIX, 0, false> __VA_ARGS__; } \
+        else { if (tr) FN<PIX, 1, true> __VA_ARGS__; else FN<PIX, 1, false> __VA_ARGS__; }                    \
+    } while (0)
+
+void launch_stats(int dtype, int mask, bool tr, dim3 grid, cudaStream_t st, const StatsArgs& a)
+{
+    if (dtype == WM_F32) WM_DISPATCH_MT(k_stats, float, mask, tr, <<<grid, NT, 0, st>>>(a));
+    else WM_DISPATCH_MT(k_stats, uint8_t, mask, tr, <<<grid, NT, 0, st>>>(a));
+}
+
+template <typename PixT, typename OutT>
+void launch_apply_t(int mask, bool tr, dim3 grid, cudaStream_t st, const ApplyArgs& a)
+{
+    if (mask == WM_MASK_ME) { if (tr) k_apply<PixT, OutT, 0, true><<<grid, NT, 0, st>>>(a); else k_apply<PixT, OutT, 0, false><<<grid, NT, 0, st>>>(a); }
+    else { if (tr) k_apply<PixT, OutT, 1, true><<<grid, NT, 0, st>>>(a); else k_apply<PixT, OutT, 1, false><<<grid, NT, 0, st>>>(a); }
+}
+void launch_apply(int in_dtype, int out_dtype, int mask, bool tr, dim3 grid, cudaStream_t st, const ApplyArgs& a)
+{
+    if (in_dtype == WM_F32) {
+        if (out_dtype == WM_F32) launch_apply_t<float, float>(mask, tr, grid, st, a); else launch_apply_t<float, uint8_t>(mask, tr, grid, st, a);
+    } else {
+        if (out_dtype == WM_F32) launch_apply_t<uint8_t, float>(mask, tr, grid, st, a); else launch_apply_t<uint8_t, uint8_t>(mask, tr, grid, st, a);
+    }
+}
+
+template <typename PixT, int MASK, bool TR>
+void launch_detect_one(dim3 grid, cudaStream_t st, const DetectArgs& a)
+{
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaFuncSetAttribute(k_detect<PixT, MASK, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, DET_SMEM);
+        attr_set[dev & 63] = true;
+    }
+    k_detect<PixT, MASK, TR><<<grid, NT, DET_SMEM, st>>>(a);
+}
+void launch_detect(int dtype, int mask, bool tr, dim3 grid, cudaStream_t st, const DetectArgs& a)
+{
+#define WM_DET(PIX)                                                                                   \
+    if (mask == WM_MASK_ME) { if (tr) launch_detect_one<PIX, 0, true>(grid, st, a); else launch_detect_one<PIX, 0, false>(grid, st, a); } \
+    else { if (tr) launch_detect_one<PIX, 1, true>(grid, st, a); else launch_detect_one<PIX, 1, false>(grid, st, a); }
+    if (dtype == WM_F32) { WM_DET(float) } else { WM_DET(uint8_t) }
+#undef WM_DET
+}
+
+// enqueue the Rx sweep (+ solve), or the injection of debug coefficients
+int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int batch, const Geo& g, const Plan& pl)
+{
+    if (ctx->inject_coef) {
+        for (int b = 0; b < batch; b++) {
+            Scal h;
+            memset(&h, 0, sizeof h);
+            memcpy(h.coef, ctx->injected, sizeof h.coef);
+            CU(cudaMemcpyAsync(s.scal + b, &h, sizeof h, cudaMemcpyHostToDevice, s.stream));
+            CU(cudaStreamSynchronize(s.stream));  // h is a stack temporary
+        }
+        return WM_OK;
+    }
+    SweepArgs a;
+    a.img = v.ptr; a.ld = v.ld; a.bstride = bstride;
+    a.L = g.L; a.P = g.P; a.tiles_p = g.tiles_p; a.ntiles = g.ntiles;
+    a.nsweep = pl.nsweep; a.nframe = pl.nframe;
+    a.vec_ok = vec_ok(v.ptr, v.ld, bstride, 0, v.dtype);
+    a.transposed = v.transposed;
+    a.part = s.part;
+    a.counter = s.counters;
+    a.scal = s.scal; a.dbg = s.dbg;
+    {
+        KTimer t(ctx, s, WM_K_SWEEP);
+        launch_sweep(v.dtype, ctx->opt_fp16 != 0, dim3(pl.nsweep + pl.nframe, batch), s.stream, a);
+    }
+    CU(cudaGetLastError());
+    return WM_OK;
+}
+
+size_t stats_part_offset(const Plan& pl, int batch) { return (size_t)batch * ((size_t)pl.nsweep * NLAG + (size_t)pl.nframe * NFRM); }
+
+int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm_image* out, int64_t in_stride,
+             int64_t base_stride, int64_t out_stride, int batch, int mask)
+{
+    if (!ctx) return WM_ERR_ARG;
+    if (slot < 0 || slot >= NSLOTS) return fail(ctx, WM_ERR_ARG, "bad slot");
+    if (mask != WM_MASK_ME && mask != WM_MASK_NVF) return fail(ctx, WM_ERR_ARG, "bad mask type");
+    if (batch < 1 || batch > 65535) return fail(ctx, WM_ERR_ARG, "batch must be 1..65535");
+    View vi, vb, vo;
+    int rc;
+    if ((rc = make_view(ctx, in, &vi, false))) return rc;
+    if ((rc = make_view(ctx, base ? base : in, &vb, true))) return rc;
+    if ((rc = make_view(ctx, out, &vo, true))) return rc;
+    if (vb.transposed != vi.transposed || vo.transposed != vi.transposed) return fail(ctx, WM_ERR_ARG, "in/base/out layouts differ");
+    if (vb.dtype != vi.dtype) return fail(ctx, WM_ERR_ARG, "base dtype must equal input dtype");
+    if (vo.channels != vb.channels) return fail(ctx, WM_ERR_ARG, "out channels != base channels");
+    if (vo.ptr == vi.ptr) return fail(ctx, WM_ERR_ARG, "out must not alias the gray input (neighbour reads race with stores)");
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slots[slot];
+    const Geo g = geo(vi.L, vi.P);
+    const Plan pl = plan(ctx, g, batch);
+    if ((rc = ensure_slot(ctx, s, batch, std::max(pl.gx_stats, pl.gx_detect), pl.nsweep, pl.nframe))) return rc;
+    const float* W = w_for(ctx, vi.transposed, s.stream, &rc);
+    if (rc) return rc;
+    if (mask == WM_MASK_ME) {
+        if ((rc = enqueue_sweep(ctx, s, vi, in_stride, batch, g, pl))) return rc;
+    }
+    StatsArgs sa;
+    sa.img = vi.ptr; sa.ld = vi.ld; sa.bstride = in_stride;
+    sa.W = W;
+    sa.L = g.L; sa.P = g.P; sa.tiles_p = g.tiles_p; sa.ntiles = g.ntiles;
+    sa.vec_ok = vec_ok(vi.ptr, vi.ld, in_stride, 0, vi.dtype);
+    sa.w_vec_ok = (g.P % 4 == 0);
+    sa.strength = ctx->strength;
+    sa.part = s.part + stats_part_offset(pl, batch);
+    sa.counter = s.counters + s.batch_cap;
+    sa.scal = s.scal; sa.dbg = s.dbg;
+    {
+        KTimer t(ctx, s, mask == WM_MASK_ME ? WM_K_ME_STATS : WM_K_NVF_STATS);
+        launch_stats(vi.dtype, mask, vi.transposed, dim3(pl.gx_stats, batch), s.stream, sa);
+    }
+    CU(cudaGetLastError());
+    ApplyArgs aa;
+    aa.img = vi.ptr; aa.ld = vi.ld; aa.bstride = in_stride;
+    aa.W = W;
+    aa.base = vb.ptr; aa.base_ld = vb.ld; aa.base_bstride = base_stride; aa.base_pstride = vb.pstride;
+    aa.out = vo.ptr; aa.out_ld = vo.ld; aa.out_bstride = out_stride; aa.out_pstride = vo.pstride;
+    aa.channels = vb.channels;
+    aa.same_base = (vb.ptr == vi.ptr && vb.ld == vi.ld && base_stride == in_stride && vb.channels == 1);
+    aa.L = g.L; aa.P = g.P; aa.tiles_p = g.tiles_p; aa.ntiles = g.ntiles;
+    aa.vec_ok = sa.vec_ok; aa.w_vec_ok = sa.w_vec_ok;
+    aa.base_vec_ok = vec_ok(vb.ptr, vb.ld, base_stride, vb.channels > 1 ? vb.pstride : 0, vb.dtype);
+    aa.out_vec_ok = vec_ok(vo.ptr, vo.ld, out_stride, vo.channels > 1 ? vo.pstride : 0, vo.dtype);
+    aa.scal = s.scal;
+    {
+        KTimer t(ctx, s, WM_K_APPLY);
+        launch_apply(vi.dtype, vo.dtype, mask, vi.transposed, dim3(pl.gx_stats, batch), s.stream, aa);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s.scal_host, s.scal, sizeof(Scal) * batch, cudaMemcpyDeviceToHost, s.stream));
+    s.pending = 1;
+    s.pend_batch = batch;
+    return WM_OK;
+}
+
+int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, int batch, int mask)
+{
+    if (!ctx) return WM_ERR_ARG;
+    if (slot < 0 || slot >= NSLOTS) return fail(ctx, WM_ERR_ARG, "bad slot");
+    if (mask != WM_MASK_ME && mask != WM_MASK_NVF) return fail(ctx, WM_ERR_ARG, "bad mask type");
+    if (batch < 1 || batch > 65535) return fail(ctx, WM_ERR_ARG, "batch must be 1..65535");
+    View v;
+    int rc;
+    if ((rc = make_view(ctx, img, &v, false))) return rc;
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slots[slot];
+    const Geo g = geo(v.L, v.P);
+    const Plan pl = plan(ctx, g, batch);
+    if ((rc = ensure_slot(ctx, s, batch, std::max(pl.gx_stats, pl.gx_detect), pl.nsweep, pl.nframe))) return rc;
+    const float* W = w_for(ctx, v.transposed, s.stream, &rc);
+    if (rc) return rc;
+    if ((rc = enqueue_sweep(ctx, s, v, img_stride, batch, g, pl))) return rc;
+    DetectArgs da;
+    da.img = v.ptr; da.ld = v.ld; da.bstride = img_stride;
+    da.W = W;
+    da.L = g.L; da.P = g.P; da.tiles_p = g.tiles_p; da.ntiles = g.ntiles;
+    da.vec_ok = vec_ok(v.ptr, v.ld, img_stride, 0, v.dtype);
+    da.w_vec_ok = (g.P % 4 == 0);
+    da.part = s.part + stats_part_offset(pl, batch);
+    da.counter = s.counters + 2 * s.batch_cap;
+    da.scal = s.scal; da.dbg = s.dbg;
+    {
+        KTimer t(ctx, s, WM_K_DETECT);
+        launch_detect(v.dtype, mask, v.transposed, dim3(pl.gx_detect, batch), s.stream, da);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s.scal_host, s.scal, sizeof(Scal) * batch, cudaMemcpyDeviceToHost, s.stream));
+    s.pending = 2;
+    s.pend_batch = batch;
+    return WM_OK;
+}
+
+// wait for a slot and deliver its scalars; returns the first non-zero status of the batch (or error)
+int finish_slot(wm_ctx* ctx, Slot& s)
+{
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(s.stream));
+    drain_timers(ctx, s);
+    int rc = WM_OK;
+    if (s.pending) {
+        for (int b = 0; b < s.pend_batch; b++) {
+            const Scal& h = s.scal_host[b];
+            if (s.pend_scalar) {
+                if (s.pending == 1) { if (h.status != WM_SINGULAR) s.pend_scalar[b] = h.a; }  // untouched when unsolvable (Watermark.cpp:164-165)
+                else s.pend_scalar[b] = h.status == 0 ? h.corr : 0.0f;                        // Watermark.cpp:246-247
+            }
+            if (s.pend_status) s.pend_status[b] = h.status;
+            if (h.status != 0 && rc == WM_OK) rc = h.status;
+        }
+    }
+    s.pending = 0;
+    s.pend_scalar = nullptr;
+    s.pend_status = nullptr;
+    return rc;
+}
+
+int load_w_file(wm_ctx* ctx, const char* path, int64_t rows, int64_t cols, std::vector<float>* w)
+{
+    // Watermark.cpp:62-75
+    FILE* f = path ? fopen(path, "rb") : nullptr;
+    if (!f) return fail(ctx, WM_ERR_W_FILE, std::string("Error opening '") + (path ? path : "(null)") + "' file for Random noise W array");
+    fseek(f, 0, SEEK_END);
+    const long long bytes = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if ((long long)(rows * cols * (int64_t)sizeof(float)) != bytes) {
+        fclose(f);
+        return fail(ctx, WM_ERR_W_SIZE, "Error: W file total elements != image dimensions! W file total elements: " +
+                                            std::to_string(bytes / (long long)sizeof(float)) + ", Image width: " + std::to_string(cols) +
+                                            ", Image height: " + std::to_string(rows));
+    }
+    w->resize((size_t)(rows * cols));
+    const size_t got = fread(w->data(), sizeof(float), w->size(), f);
+    fclose(f);
+    if (got != w->size()) return fail(ctx, WM_ERR_W_FILE, "short read on W file");
+    return WM_OK;
+}
+
+int upload_w(wm_ctx* ctx, int64_t rows, int64_t cols, const float* w_host)
+{
+    auto ws = std::make_shared<WShared>();
+    ws->device = ctx->device;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc(&ws->row_major, sizeof(float) * rows * cols));
+    CU(cudaMemcpy(ws->row_major, w_host, sizeof(float) * rows * cols, cudaMemcpyHostToDevice));
+    ctx->w = ws;
+    ctx->rows = rows;
+    ctx->cols = cols;
+    return WM_OK;
+}
+
+int init_slots(wm_ctx* ctx, void* user_stream)
+{
+    CU(cudaSetDevice(ctx->device));
+    for (int i = 0; i < NSLOTS; i++) {
+        Slot& s = ctx->slots[i];
+        if (i == 0 && user_stream) { s.stream = (cudaStream_t)user_stream; s.own_stream = false; }
+        else { CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)); s.own_stream = true; }
+    }
+    return WM_OK;
+}
+
+void free_slot(Slot& s)
+{
+    if (s.part) cudaFree(s.part);
+    if (s.counters) cudaFree(s.counters);
+    if (s.scal) cudaFree(s.scal);
+    if (s.dbg) cudaFree(s.dbg);
+    if (s.scal_host) cudaFreeHost(s.scal_host);
+    if (s.stage_in) cudaFree(s.stage_in);
+    if (s.stage_base) cudaFree(s.stage_base);
+    if (s.stage_out) cudaFree(s.stage_out);
+    for (auto& t : s.timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
+    s = Slot();
+}
+
+int create_common(wm_ctx** out, int64_t rows, int64_t cols, int p, float psnr, int device, void* stream, wm_ctx** made)
+{
+    wm_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, WM_ERR_ARG, "null out");
+    *out = nullptr;
+    // Watermark.cpp:24-25
+    if (p != 3 && p != 5 && p != 7 && p != 9) return fail(nullptr, WM_ERR_BAD_P, "Wrong p parameter: " + std::to_string(p) + "!");
+    if (p != 3) return fail(nullptr, WM_ERR_BAD_P, "p = " + std::to_string(p) + ": only p = 3 is implemented (main.cpp:89 enforces 3)");
+    if (!(psnr > 0.0f)) return fail(nullptr, WM_ERR_ARG, "psnr must be > 0 (main.cpp:96)");
+    if (rows < 3 || cols < 3 || rows > (1 << 30) / 4 || cols > (1 << 30) / 4) return fail(nullptr, WM_ERR_DIMS, "unsupported image dims");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, WM_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, WM_ERR_NO_DEVICE, "invalid device " + std::to_string(device));
+    ctx = new wm_ctx();
+    ctx->device = device;
+    ctx->p = p;
+    ctx->psnr = psnr;
+    ctx->strength = 255.0f / sqrtf(powf(10.0f, psnr / 10.0f));  // Watermark.cpp:22
+    cudaSetDevice(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sms = prop.multiProcessorCount;
+    const int rc = init_slots(ctx, stream);
+    if (rc) { g_create_error = ctx->err; delete ctx; return rc; }
+    *made = ctx;
+    (void)rows; (void)cols;
+    return WM_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* wm_version(void) { return WM_VERSION_STR; }
+
+int wm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int wm_create(wm_ctx** out, int64_t rows, int64_t cols, const float* w_host, int p, float psnr, int device, void* stream)
+{
+    wm_ctx* ctx = nullptr;
+    int rc = create_common(out, rows, cols, p, psnr, device, stream, &ctx);
+    if (rc) return rc;
+    if (!w_host) { delete ctx; return fail(nullptr, WM_ERR_ARG, "null W"); }
+    rc = upload_w(ctx, rows, cols, w_host);
+    if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
+    *out = ctx;
+    return WM_OK;
+}
+
+int wm_create_from_file(wm_ctx** out, int64_t rows, int64_t cols, const char* w_path, int p, float psnr, int device, void* stream)
+{
+    wm_ctx* ctx = nullptr;
+    int rc = create_common(out, rows, cols, p, psnr, device, stream, &ctx);
+    if (rc) return rc;
+    std::vector<float> w;
+    rc = load_w_file(ctx, w_path, rows, cols, &w);
+    if (!rc) rc = upload_w(ctx, rows, cols, w.data());
+    if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
+    *out = ctx;
+    return WM_OK;
+}
+
+int wm_clone(const wm_ctx* src, wm_ctx** out)
+{
+    if (!src || !out) return WM_ERR_ARG;
+    wm_ctx* ctx = new wm_ctx();
+    ctx->device = src->device; ctx->sms = src->sms;
+    ctx->rows = src->rows; ctx->cols = src->cols;
+    ctx->p = src->p; ctx->psnr = src->psnr; ctx->strength = src->strength;
+    ctx->w = src->w;
+    ctx->opt_fp16 = src->opt_fp16; ctx->opt_timing = src->opt_timing; ctx->opt_tma = src->opt_tma;
+    const int rc = init_slots(ctx, nullptr);
+    if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
+    *out = ctx;
+    return WM_OK;
+}
+
+int wm_reinitialize(wm_ctx* ctx, int64_t rows, int64_t cols, const float* w_host)
+{
+    if (!ctx || !w_host) return WM_ERR_ARG;
+    if (rows < 3 || cols < 3) return fail(ctx, WM_ERR_DIMS, "unsupported image dims");
+    wm_sync(ctx, -1);
+    return upload_w(ctx, rows, cols, w_host);
+}
+
+int wm_reinitialize_from_file(wm_ctx* ctx, int64_t rows, int64_t cols, const char* w_path)
+{
+    if (!ctx) return WM_ERR_ARG;
+    std::vector<float> w;
+    const int rc = load_w_file(ctx, w_path, rows, cols, &w);
+    if (rc) return rc;
+    return wm_reinitialize(ctx, rows, cols, w.data());
+}
+
+void wm_destroy(wm_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < NSLOTS; i++) {
+        if (ctx->slots[i].stream) cudaStreamSynchronize(ctx->slots[i].stream);
+        free_slot(ctx->slots[i]);
+    }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    delete ctx;
+}
+
+int wm_set_option(wm_ctx* ctx, int option, int value)
+{
+    if (!ctx) return WM_ERR_ARG;
+    switch (option) {
+    case WM_OPT_FP16_PRODUCTS: ctx->opt_fp16 = value != 0; return WM_OK;
+    case WM_OPT_KERNEL_TIMING: ctx->opt_timing = value != 0; return WM_OK;
+    case WM_OPT_USE_TMA: ctx->opt_tma = value != 0; return WM_OK;
+    default: return fail(ctx, WM_ERR_ARG, "unknown option");
+    }
+}
+
+const char* wm_last_error(const wm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+float wm_strength_factor(const wm_ctx* ctx) { return ctx ? ctx->strength : 0.0f; }
+int wm_num_slots(const wm_ctx*) { return NSLOTS; }
+
+int wm_sync(wm_ctx* ctx, int slot)
+{
+    if (!ctx) return WM_ERR_ARG;
+    if (slot >= NSLOTS) return fail(ctx, WM_ERR_ARG, "bad slot");
+    int rc = WM_OK;
+    for (int i = (slot < 0 ? 0 : slot); i < (slot < 0 ? NSLOTS : slot + 1); i++) {
+        const int r = finish_slot(ctx, ctx->slots[i]);
+        if (r < 0) return r;
+        if (r && !rc) rc = r;
+    }
+    return rc;
+}
+
+int wm_embed_batch(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm_image* out, int64_t in_stride,
+                   int64_t base_stride, int64_t out_stride, int batch, int mask, float* a_host, int* status_host)
+{
+    if (!ctx) return WM_ERR_ARG;
+    if (slot < 0 || slot >= NSLOTS) return fail(ctx, WM_ERR_ARG, "bad slot");
+    if (ctx->slots[slot].pending) { const int r = finish_slot(ctx, ctx->slots[slot]); if (r < 0) return r; }
+    const int rc = do_embed(ctx, slot, in, base, out, in_stride, base_stride, out_stride, batch, mask);
+    if (rc) return rc;
+    ctx->slots[slot].pend_scalar = a_host;
+    ctx->slots[slot].pend_status = status_host;
+    return WM_OK;
+}
+
+int wm_detect_batch(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, int batch, int mask, float* corr_host, int* status_host)
+{
+    if (!ctx) return WM_ERR_ARG;
+    if (slot < 0 || slot >= NSLOTS) return fail(ctx, WM_ERR_ARG, "bad slot");
+    if (ctx->slots[slot].pending) { const int r = finish_slot(ctx, ctx->slots[slot]); if (r < 0) return r; }
+    const int rc = do_detect(ctx, slot, img, img_stride, batch, mask);
+    if (rc) return rc;
+    ctx->slots[slot].pend_scalar = corr_host;
+    ctx->slots[slot].pend_status = status_host;
+    return WM_OK;
+}
+
+int wm_embed(wm_ctx* ctx, const wm_image* in, const wm_image* base, wm_image* out, int mask, float* a_host)
+{
+    const int rc = wm_embed_batch(ctx, 0, in, base, out, 0, 0, 0, 1, mask, a_host, nullptr);
+    if (rc) return rc;
+    return finish_slot(ctx, ctx->slots[0]);
+}
+
+int wm_detect(wm_ctx* ctx, const wm_image* img, int mask, float* corr_host)
+{
+    const int rc = wm_detect_batch(ctx, 0, img, 0, 1, mask, corr_host, nullptr);
+    if (rc) return rc;
+    return finish_slot(ctx, ctx->slots[0]);
+}
+
+static size_t image_bytes(const wm_image* im, int64_t* elems_per_plane)
+{
+    const bool tr = im->layout == WM_COL_MAJOR;
+    const int64_t L = tr ? im->cols : im->rows, P = tr ? im->rows : im->cols;
+    const int64_t ld = im->ld > 0 ? im->ld : P;
+    const int ch = im->channels <= 0 ? 1 : im->channels;
+    const int64_t ps = im->plane_stride > 0 ? im->plane_stride : L * ld;
+    if (elems_per_plane) *elems_per_plane = ps;
+    return (size_t)(ps * (ch - 1) + L * ld) * (im->dtype == WM_F32 ? 4 : 1);
+}
+
+int wm_embed_host(wm_ctx* ctx, const wm_image* in, const wm_image* base, wm_image* out, int mask, float* a_host)
+{
+    if (!ctx || !in || !out || !in->data || !out->data) return WM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slots[0];
+    if (s.pending) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+    const wm_image* b = base ? base : in;
+    const size_t nin = image_bytes(in, nullptr), nb = image_bytes(b, nullptr), nout = image_bytes(out, nullptr);
+    int rc;
+    if ((rc = ensure_stage(ctx, &s.stage_in, &s.stage_in_cap, nin))) return rc;
+    if ((rc = ensure_stage(ctx, &s.stage_out, &s.stage_out_cap, nout))) return rc;
+    CU(cudaMemcpyAsync(s.stage_in, in->data, nin, cudaMemcpyHostToDevice, s.stream));
+    wm_image din = *in, dbase = *b, dout = *out;
+    din.data = s.stage_in;
+    if (b->data == in->data) dbase.data = s.stage_in;
+    else {
+        if ((rc = ensure_stage(ctx, &s.stage_base, &s.stage_base_cap, nb))) return rc;
+        CU(cudaMemcpyAsync(s.stage_base, b->data, nb, cudaMemcpyHostToDevice, s.stream));
+        dbase.data = s.stage_base;
+    }
+    dout.data = s.stage_out;
+    rc = do_embed(ctx, 0, &din, &dbase, &dout, 0, 0, 0, 1, mask);
+    if (rc) return rc;
+    s.pend_scalar = a_host;
+    CU(cudaMemcpyAsync(out->data, s.stage_out, nout, cudaMemcpyDeviceToHost, s.stream));
+    return finish_slot(ctx, s);
+}
+
+int wm_detect_host(wm_ctx* ctx, const wm_image* img, int mask, float* corr_host)
+{
+    if (!ctx || !img || !img->data) return WM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slots[0];
+    if (s.pending) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+    const size_t n = image_bytes(img, nullptr);
+    int rc;
+    if ((rc = ensure_stage(ctx, &s.stage_in, &s.stage_in_cap, n))) return rc;
+    CU(cudaMemcpyAsync(s.stage_in, img->data, n, cudaMemcpyHostToDevice, s.stream));
+    wm_image d = *img;
+    d.data = s.stage_in;
+    rc = do_detect(ctx, 0, &d, 0, 1, mask);
+    if (rc) return rc;
+    s.pend_scalar = corr_host;
+    return finish_slot(ctx, s);
+}
+
+int wm_debug_get(wm_ctx* ctx, int what, void* dst)
+{
+    if (!ctx || !dst) return WM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slots[0];
+    if (!s.scal) return fail(ctx, WM_ERR_ARG, "no call made yet");
+    CU(cudaStreamSynchronize(s.stream));
+    Scal h;
+    ScalDbg d;
+    CU(cudaMemcpy(&h, s.scal, sizeof h, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&d, s.dbg, sizeof d, cudaMemcpyDeviceToHost));
+    switch (what) {
+    case WM_DBG_RX: memcpy(dst, d.Rx, sizeof d.Rx); return WM_OK;
+    case WM_DBG_RXVEC: memcpy(dst, d.rx, sizeof d.rx); return WM_OK;
+    case WM_DBG_COEFFS: memcpy(dst, h.coef, sizeof h.coef); return WM_OK;
+    case WM_DBG_SCALARS: {
+        double* o = (double*)dst;
+        o[0] = h.status; o[1] = h.a; o[2] = h.emax; o[3] = d.sum2; o[4] = d.dot; o[5] = d.nz; o[6] = d.nu; o[7] = h.corr;
+        return WM_OK;
+    }
+    default: return fail(ctx, WM_ERR_ARG, "unknown debug item");
+    }
+}
+
+int wm_debug_set_coeffs(wm_ctx* ctx, const float* c)
+{
+    if (!ctx) return WM_ERR_ARG;
+    ctx->inject_coef = c != nullptr;
+    if (c) memcpy(ctx->injected, c, sizeof ctx->injected);
+    return WM_OK;
+}
+
+int wm_debug_plane(wm_ctx* ctx, const wm_image* img, int what, float* dst_dev)
+{
+    if (!ctx || !dst_dev) return WM_ERR_ARG;
+    if (what != WM_DBG_ERRSEQ && what != WM_DBG_MASK_NVF) return fail(ctx, WM_ERR_ARG, "plane must be ERRSEQ or MASK_NVF");
+    View v;
+    int rc;
+    if ((rc = make_view(ctx, img, &v, false))) return rc;
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slots[0];
+    if (s.pending) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+    const Geo g = geo(v.L, v.P);
+    const Plan pl = plan(ctx, g, 1);
+    if ((rc = ensure_slot(ctx, s, 1, std::max(pl.gx_stats, pl.gx_detect), pl.nsweep, pl.nframe))) return rc;
+    if (what == WM_DBG_ERRSEQ) {
+        if ((rc = enqueue_sweep(ctx, s, v, 0, 1, g, pl))) return rc;
+    }
+    PlaneArgs pa;
+    pa.img = v.ptr; pa.ld = v.ld;
+    pa.L = g.L; pa.P = g.P; pa.tiles_p = g.tiles_p; pa.ntiles = g.ntiles;
+    pa.vec_ok = vec_ok(v.ptr, v.ld, 0, 0, v.dtype);
+    pa.scal = s.scal;
+    pa.dst = dst_dev;
+    const dim3 grid(std::min(g.ntiles, 3 * ctx->sms));
+#define WM_PLANE(PIX)                                                                                             \
+    if (what == WM_DBG_ERRSEQ) { if (v.transposed) k_plane<PIX, 0, true><<<grid, NT, 0, s.stream>>>(pa); else k_plane<PIX, 0, false><<<grid, NT, 0, s.stream>>>(pa); } \
+    else { if (v.transposed) k_plane<PIX, 1, true><<<grid, NT, 0, s.stream>>>(pa); else k_plane<PIX, 1, false><<<grid, NT, 0, s.stream>>>(pa); }
+    if (v.dtype == WM_F32) { WM_PLANE(float) } else { WM_PLANE(uint8_t) }
+#undef WM_PLANE
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s.stream));
+    return WM_OK;
+}
+
+int64_t wm_get_kernel_times(wm_ctx* ctx, int kernel, double* total_ms, int reset)
+{
+    if (!ctx || kernel < 0 || kernel >= WM_K_COUNT) return -1;
+    const int64_t n = ctx->kcount[kernel];
+    if (total_ms) *total_ms = ctx->ktime_ms[kernel];
+    if (reset) { ctx->kcount[kernel] = 0; ctx->ktime_ms[kernel] = 0.0; }
+    return n;
+}
+
+int64_t wm_launch_count(const wm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- video driver (videoprocessingcontext.hpp:13-29, main.cpp:319-410) ----
+int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames, uint8_t* out, int64_t first_index,
+                          int64_t n_frames, float* scalars)
+{
+    if (!v || !v->watermark || !frames) return WM_ERR_ARG;
+    wm_ctx* ctx = v->watermark;
+    if (mode != WM_VIDEO_EMBED && mode != WM_VIDEO_DETECT) return fail(ctx, WM_ERR_ARG, "bad mode");
+    if (v->height != ctx->rows || v->width != ctx->cols) return fail(ctx, WM_ERR_DIMS, "frame dims != watermark dims");
+    if (v->watermark_interval < 1) return fail(ctx, WM_ERR_ARG, "watermark_interval must be >= 1");
+    if (mode == WM_VIDEO_EMBED && !out) return fail(ctx, WM_ERR_ARG, "embed needs an output buffer");
+    const int64_t H = v->height, Wd = v->width;
+    const int64_t linesize = v->linesize > 0 ? v->linesize : Wd;
+    if (linesize < Wd) return fail(ctx, WM_ERR_ARG, "linesize < width");
+    const int64_t fstride = v->frame_stride > 0 ? v->frame_stride : H * linesize;
+    const int64_t ostride = H * Wd;
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    for (int i = 0; i < NSLOTS; i++)
+        if (ctx->slots[i].pending) { const int r = finish_slot(ctx, ctx->slots[i]); if (r < 0) return r; }
+    const float nanv = nanf("");
+    for (int64_t i = 0; i < n_frames; i++) {
+        const int64_t gidx = first_index + i;
+        const bool gated = (gidx % v->watermark_interval) == 0;  // main.cpp:346,395 (global frame index)
+        const int si = (int)(i % NSLOTS);
+        Slot& s = ctx->slots[si];
+        if (s.pending) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+        const uint8_t* src = frames + i * fstride;
+        uint8_t* dst = out ? out + i * ostride : nullptr;
+        if (!gated) {
+            if (mode == WM_VIDEO_EMBED) {  // copy-through, dropping the row padding (main.cpp:362-366)
+                CU(cudaMemcpy2DAsync(dst, Wd, src, linesize, Wd, H,
+                                     v->frames_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToHost, s.stream));
+                if (scalars) scalars[i] = nanv;
+            } else if (scalars) scalars[i] = nanv;
+            continue;
+        }
+        wm_image fin;
+        memset(&fin, 0, sizeof fin);
+        fin.rows = H; fin.cols = Wd; fin.channels = 1; fin.layout = WM_ROW_MAJOR; fin.dtype = WM_U8;
+        if (v->frames_on_device) {
+            fin.data = (void*)src; fin.ld = linesize;  // strided reads: no repack pass needed
+        } else {
+            if ((rc = ensure_stage(ctx, &s.stage_in, &s.stage_in_cap, (size_t)(H * Wd)))) return rc;
+            CU(cudaMemcpy2DAsync(s.stage_in, Wd, src, linesize, Wd, H, cudaMemcpyHostToDevice, s.stream));  // repack on the fly
+            fin.data = s.stage_in; fin.ld = Wd;
+        }
+        if (mode == WM_VIDEO_EMBED) {
+            wm_image fout = fin;
+            fout.ld = Wd;
+            if (v->frames_on_device) fout.data = dst;
+            else {
+                if ((rc = ensure_stage(ctx, &s.stage_out, &s.stage_out_cap, (size_t)(H * Wd)))) return rc;
+                fout.data = s.stage_out;
+            }
+            rc = do_embed(ctx, si, &fin, &fin, &fout, 0, 0, 0, 1, WM_MASK_ME);  // main.cpp:356,380
+            if (rc) return rc;
+            if (!v->frames_on_device) CU(cudaMemcpyAsync(dst, s.stage_out, (size_t)(H * Wd), cudaMemcpyDeviceToHost, s.stream));
+        } else {
+            rc = do_detect(ctx, si, &fin, 0, 1, WM_MASK_ME);  // main.cpp:406
+            if (rc) return rc;
+        }
+        s.pend_scalar = scalars ? scalars + i : nullptr;
+    }
+    for (int i = 0; i < NSLOTS; i++) { const int r = finish_slot(ctx, ctx->slots[i]); if (r < 0) return r; }
+    return n_frames;
+}
+
+// ---- helpers ----
+void* wm_dev_alloc(wm_ctx* ctx, int64_t bytes)
+{
+    if (ctx) cudaSetDevice(ctx->device);
+    void* p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void wm_dev_free(wm_ctx* ctx, void* p)
+{
+    if (ctx) cudaSetDevice(ctx->device);
+    if (p) cudaFree(p);
+}
+int wm_dev_upload(wm_ctx* ctx, void* dst, const void* src, int64_t bytes)
+{
+    if (ctx) cudaSetDevice(ctx->device);
+    return cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice) == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+int wm_dev_download(wm_ctx* ctx, void* dst, const void* src, int64_t bytes)
+{
+    if (ctx) cudaSetDevice(ctx->device);
+    return cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+void* wm_host_alloc_pinned(int64_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void wm_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

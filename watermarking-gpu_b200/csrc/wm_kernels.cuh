@@ -1,0 +1,938 @@
+// wm_kernels.cuh — sm_100a kernels of the watermark hot path.
+//
+// Coordinates.  Every image is seen as `L` lines of `P` contiguous pixels with a leading dimension `ld`
+// (elements): a WM_ROW_MAJOR image has L = rows, P = cols; a WM_COL_MAJOR (ArrayFire) image has L = cols,
+// P = rows and the kernels run "transposed" (template flag TR): the arithmetic is restated in the reference's
+// (row, col) order so results are identical in both layouts (NVF is transpose-symmetric, the
+// ME system is a permutation).
+//
+// Reference neighbour order k = 0..7 = raster order of the 3x3 window minus the centre, (dy, dx)
+// (kernels/me_p3.hpp:46-54, kernels/scaled_neighbors_p3.hpp:35-42); reads outside the image clamp to the
+// edge (CLK_ADDRESS_CLAMP_TO_EDGE, kernels/nvf.hpp:9).
+//
+// Kernels (one launch each, every one ends with a deterministic last-block second stage):
+//   k_sweep   Rx/rx autocorrelation sweep (replaces kernel `me` kernels/me_p3.hpp:23-83 + af::sum
+//             Watermark.cpp:140-151) + one-warp 8x8 LU solve (af::solve, Watermark.cpp:203)
+//   k_stats   pass 1 of makeWatermark: mask (NVF kernels/nvf.hpp:37-50 or |e| of Watermark.cpp:210-214),
+//             sum (mask.W)^2 and max|e| -> watermarkStrength (Watermark.cpp:169-170)
+//   k_apply   pass 2 of makeWatermark: clamp(base + a.mask.W, 0, 255) (Watermark.cpp:171)
+//   k_detect  detectWatermark after the sweep: e_z, u = mask.W, e_u and the three correlation sums
+//             (Watermark.cpp:221-231,248-249) in one pass
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace wm {
+
+constexpr int TP = 128;          // tile width  (contiguous pixels)
+constexpr int TL = 32;           // tile height (lines)
+constexpr int NT = 256;          // threads per CTA: 32 lanes x 4 px, 8 warps x 4 lines
+constexpr int HP = 4;            // column halo kept in smem (4 keeps 16-byte alignment; 2 are needed at most)
+constexpr int SW = TP + 2 * HP;  // smem row stride in floats (136)
+constexpr int NLAG = 13;         // distinct lags of the upper triangle of Rx
+constexpr int NFRM = 44;         // frame partials: 8 rx + 36 Rx (upper triangle)
+constexpr int NTOT = NLAG + NFRM;
+
+// per-image scalars living in device memory (one per batch entry), mirrored to pinned host memory
+struct Scal {
+    float coef[8];   // reference order
+    int status;      // 0 ok, 1 singular, 2 zero mask
+    float a;         // watermarkStrength
+    float emax;      // max|e| (ME embed)
+    float corr;
+};
+// parity/debug side-band (one per batch entry, only read back by wm_debug_get)
+struct ScalDbg {
+    double sum2;     // sum (|e| W)^2 or sum (nvf W)^2
+    double dot, nz, nu;
+    double Rx[64];   // reference order, full symmetric
+    double rx[8];
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// ------------------------------------------------------------------------------------------------
+// tile loader (plain path): fills rows [l_org, l_org+NROWS) x cols [p_org, p_org+SW) of the image into
+// smem as float, coordinates clamped to the image (replicate border).  p_org is a multiple of 4, so a
+// 4-pixel chunk is one aligned 16-byte (f32) / 4-byte (u8) global load when vec_ok.
+// ------------------------------------------------------------------------------------------------
+template <typename PixT, int NROWS>
+__device__ __forceinline__ void load_tile(float* __restrict__ tile, const PixT* __restrict__ img, long long ld,
+                                          int L, int P, int l_org, int p_org, bool vec_ok)
+{
+    constexpr int CH = SW / 4;
+    for (int idx = threadIdx.x; idx < NROWS * CH; idx += NT) {
+        const int r = idx / CH, c = idx - r * CH;
+        const int l = clampi(l_org + r, 0, L - 1);
+        const int p = p_org + 4 * c;
+        const PixT* row = img + (long long)l * ld;
+        float4 v;
+        if (vec_ok && p >= 0 && p + 3 < P) {
+            if constexpr (sizeof(PixT) == 4) {
+                v = __ldg(reinterpret_cast<const float4*>(row + p));
+            } else {
+                const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(row + p));
+                v = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+            }
+        } else {
+            v.x = (float)row[clampi(p, 0, P - 1)];
+            v.y = (float)row[clampi(p + 1, 0, P - 1)];
+            v.z = (float)row[clampi(p + 2, 0, P - 1)];
+            v.w = (float)row[clampi(p + 3, 0, P - 1)];
+        }
+        *reinterpret_cast<float4*>(tile + r * SW + 4 * c) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic reductions
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-level sum of NV doubles per thread -> out[0..NV) valid in thread 0..NV-1 via smem `red` (8*NV doubles)
+template <int NV>
+__device__ __forceinline__ void block_sum(const double (&v)[NV], double* red /* [8][NV] */)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const double s = warp_sum(v[i]);
+        if (lane == 0) red[w * NV + i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < NT / 32; k++) s += red[k * NV + threadIdx.x];
+        red[threadIdx.x] = s;  // row 0 is only read by its own column's thread
+    }
+    __syncthreads();
+}
+
+// last-block election (threadFenceReduction pattern); counter wraps back to 0 by itself
+__device__ __forceinline__ bool last_block(unsigned* counter, unsigned nblocks)
+{
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicInc(counter, nblocks - 1);
+        s_last = (prev == nblocks - 1);
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+// fixed-order sum over blocks of column v of a [nblk][nv] f64 partial array, executed by one warp
+__device__ __forceinline__ double column_sum(const double* part, int nblk, int nv, int v)
+{
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int b = lane; b < nblk; b += 32) s += __ldcg(part + (size_t)b * nv + v);
+    return warp_sum(s);
+}
+__device__ __forceinline__ float column_max(const double* part, int nblk, int nv, int v)
+{
+    const int lane = threadIdx.x & 31;
+    float s = 0.0f;
+    for (int b = lane; b < nblk; b += 32) s = fmaxf(s, (float)__ldcg(part + (size_t)b * nv + v));
+    return warp_max(s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp16 product rounding (kernels/me_p3.hpp:10-20: vstore_half of each product, then f32 sums)
+// ------------------------------------------------------------------------------------------------
+// a0 += (float)half(x); a1 += (float)half(y): one packed cvt + two mixed-precision adds (FHADD on sm_100a)
+__device__ __forceinline__ void acc2_f16(float& a0, float& a1, float x, float y)
+{
+    asm("{\n\t.reg .b32 h;\n\t.reg .b16 lo, hi;\n\t"
+        "cvt.rn.f16x2.f32 h, %3, %2;\n\t"
+        "mov.b32 {lo, hi}, h;\n\t"
+        "add.rn.f32.f16 %0, lo, %0;\n\t"
+        "add.rn.f32.f16 %1, hi, %1;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "f"(x), "f"(y));
+}
+__device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
+
+// ------------------------------------------------------------------------------------------------
+// per-pixel arithmetic, restated from the reference kernels in their own operation order
+// ------------------------------------------------------------------------------------------------
+// r0,r1,r2: the three window lines (l-1, l, l+1); element [j], [j+1], [j+2] are pixels p-1, p, p+1.
+// kernels/scaled_neighbors_p3.hpp:34-43 — dot += coeffs[k]*n_k, k ascending (mad allowed: fused)
+template <bool TR>
+__device__ __forceinline__ float predict(const float (&c)[8], const float* r0, const float* r1, const float* r2, int j)
+{
+    float d;
+    if constexpr (!TR) {
+        d = __fmul_rn(c[0], r0[j]);
+        d = __fmaf_rn(c[1], r0[j + 1], d);
+        d = __fmaf_rn(c[2], r0[j + 2], d);
+        d = __fmaf_rn(c[3], r1[j], d);
+        d = __fmaf_rn(c[4], r1[j + 2], d);
+        d = __fmaf_rn(c[5], r2[j], d);
+        d = __fmaf_rn(c[6], r2[j + 1], d);
+        d = __fmaf_rn(c[7], r2[j + 2], d);
+    } else {  // (dl, dp) = (dx, dy)
+        d = __fmul_rn(c[0], r0[j]);
+        d = __fmaf_rn(c[1], r1[j], d);
+        d = __fmaf_rn(c[2], r2[j], d);
+        d = __fmaf_rn(c[3], r0[j + 1], d);
+        d = __fmaf_rn(c[4], r2[j + 1], d);
+        d = __fmaf_rn(c[5], r0[j + 2], d);
+        d = __fmaf_rn(c[6], r1[j + 2], d);
+        d = __fmaf_rn(c[7], r2[j + 2], d);
+    }
+    return d;
+}
+
+// kernels/nvf.hpp:37-50 — sum / sumSq over the window rows-outer cols-inner, naive variance
+template <bool TR>
+__device__ __forceinline__ float nvf_mask(const float* r0, const float* r1, const float* r2, int j)
+{
+    float s = 0.0f, q = 0.0f;
+#define WM_NVF_ACC(v) { const float t_ = (v); s = __fadd_rn(s, t_); q = __fmaf_rn(t_, t_, q); }
+    if constexpr (!TR) {
+        WM_NVF_ACC(r0[j]) WM_NVF_ACC(r0[j + 1]) WM_NVF_ACC(r0[j + 2])
+        WM_NVF_ACC(r1[j]) WM_NVF_ACC(r1[j + 1]) WM_NVF_ACC(r1[j + 2])
+        WM_NVF_ACC(r2[j]) WM_NVF_ACC(r2[j + 1]) WM_NVF_ACC(r2[j + 2])
+    } else {
+        WM_NVF_ACC(r0[j]) WM_NVF_ACC(r1[j]) WM_NVF_ACC(r2[j])
+        WM_NVF_ACC(r0[j + 1]) WM_NVF_ACC(r1[j + 1]) WM_NVF_ACC(r2[j + 1])
+        WM_NVF_ACC(r0[j + 2]) WM_NVF_ACC(r1[j + 2]) WM_NVF_ACC(r2[j + 2])
+    }
+#undef WM_NVF_ACC
+    const float mean = __fdiv_rn(s, 9.0f);
+    const float var = __fmaf_rn(-mean, mean, __fdiv_rn(q, 9.0f));
+    return __fdiv_rn(var, __fadd_rn(1.0f, var));
+}
+
+// 6-float window (pixels p-1 .. p+4 of one smem line) for a thread's 4 pixels; sc = smem column of pixel 0
+__device__ __forceinline__ void load_win6(float (&w)[6], const float* line, int sc)
+{
+    w[0] = line[sc - 1];
+    const float4 v = *reinterpret_cast<const float4*>(line + sc);
+    w[1] = v.x; w[2] = v.y; w[3] = v.z; w[4] = v.w;
+    w[5] = line[sc + 4];
+}
+
+// ================================================================================================
+// k_sweep: Rx / rx.  Lag-symmetric core + naive 2-pixel frame (identity in SURVEY.md §0):
+//   Rx[i][j] = sum_{q in core} X(q) Xc(q + o_j - o_i)  +  sum_{p : p+o_i not in core} Xc(p+o_i) Xc(p+o_j)
+//   rx[i]    = sum_{q in core} X(q) Xc(q -/+ o_i)      +  frame,         core = lines 1..L-2 x pixels 1..P-2
+// so a core pixel costs 13 products (lags (0,0..2), (1,-2..2), (2,-2..2)) instead of 44.  Identical products
+// round identically, so the fp16 rounding of kernels/me_p3.hpp commutes with the regrouping.
+// Blocks [0, nsweep) walk tiles (static round-robin => fixed summation order), blocks [nsweep, nsweep+nframe)
+// take the frame ring.  f32 accumulation is bounded to 8 px (exact for integer-valued pixels), then f64.
+// The last block to finish sums the per-block partials in fixed order, assembles the 8x8 system in the
+// reference's neighbour order and solves it in one warp (f64 LU, partial pivoting).
+// ================================================================================================
+struct SweepArgs {
+    const void* img;
+    long long ld, bstride;  // elements
+    int L, P, tiles_p, ntiles;
+    int nsweep, nframe;
+    int vec_ok, transposed;
+    double* part;        // [batch][nsweep*NLAG + nframe*NFRM]
+    unsigned* counter;   // [batch]
+    Scal* scal;          // [batch]
+    ScalDbg* dbg;        // [batch]
+};
+
+__device__ __forceinline__ int lag_index(int dl, int dp) { return dl == 0 ? dp : (dl == 1 ? 5 + dp : 10 + dp); }
+
+__device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* sc, ScalDbg* dbg, int transposed, double* M /* smem [8][9] */)
+{
+    // internal (line, pixel) raster order of the 8 neighbours
+    const int DLc[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+    const int DPc[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+    // reference index k -> internal index (identity, or the transpose permutation)
+    const int PERM_T[8] = {0, 3, 5, 1, 6, 2, 4, 7};
+    const int lane = threadIdx.x & 31;
+    // assemble (72 entries over 32 lanes)
+    for (int e = lane; e < 72; e += 32) {
+        const int a = e / 9, b = e - a * 9;
+        const int ia = transposed ? PERM_T[a] : a;
+        double v;
+        if (b < 8) {
+            const int ib = transposed ? PERM_T[b] : b;
+            const int i = min(ia, ib), j = max(ia, ib);
+            const int tri = i * 8 - (i * (i - 1)) / 2 + (j - i);
+            v = tot[lag_index(DLc[j] - DLc[i], DPc[j] - DPc[i])] + tot[NLAG + 8 + tri];
+        } else {
+            const int lg = ia <= 3 ? lag_index(-DLc[ia], -DPc[ia]) : lag_index(DLc[ia], DPc[ia]);
+            v = tot[lg] + tot[NLAG + ia];
+        }
+        M[e] = v;
+        if (b < 8) dbg->Rx[a * 8 + b] = v; else dbg->rx[a] = v;
+    }
+    __syncwarp();
+    double A[9];
+    const bool rowlane = lane < 8;
+#pragma unroll
+    for (int j = 0; j < 9; j++) A[j] = rowlane ? M[lane * 9 + j] : 0.0;
+    double amax = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) amax = fmax(amax, fabs(A[j]));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    amax = __shfl_sync(0xffffffffu, amax, 0);
+    int singular = (!(amax > 0.0)) || !isfinite(amax);
+    const double tol = 1e-12 * amax;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        // first maximal |A[i][k]|, i >= k
+        double v = (rowlane && lane >= k) ? fabs(A[k]) : -1.0;
+        int idx = lane;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        const int piv = __shfl_sync(0xffffffffu, idx, 0);
+        const double pv = __shfl_sync(0xffffffffu, v, 0);
+        if (!(pv > tol)) singular = 1;
+        double pr[9];
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const double rk = __shfl_sync(0xffffffffu, A[j], k);
+            const double rp = __shfl_sync(0xffffffffu, A[j], piv & 7);
+            if (lane == k) A[j] = rp; else if (lane == piv) A[j] = rk;
+            pr[j] = rp;  // row k after the swap
+        }
+        if (rowlane && lane > k) {
+            const double f = __ddiv_rn(A[k], pr[k]);
+#pragma unroll
+            for (int j = k; j < 9; j++) A[j] = __dsub_rn(A[j], __dmul_rn(f, pr[j]));
+        }
+    }
+    double cc[8];
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        double s = A[8];
+#pragma unroll
+        for (int j = i + 1; j < 8; j++) s = __dsub_rn(s, __dmul_rn(A[j], cc[j]));
+        const double ci = __ddiv_rn(s, A[i]);
+        cc[i] = __shfl_sync(0xffffffffu, ci, i);
+    }
+    if (lane == 0) {
+        sc->status = singular ? 1 : 0;
+        sc->corr = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sc->coef[k] = singular ? 0.0f : (float)cc[k];
+    }
+}
+
+template <typename PixT, bool FP16>
+__global__ void __launch_bounds__(NT, 2) k_sweep(const SweepArgs a)
+{
+    __shared__ __align__(16) float tile[(TL + 2) * SW];
+    __shared__ double red[8 * NFRM];
+    const int b = blockIdx.y;
+    const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
+    const int L = a.L, P = a.P;
+    double* part = a.part + (size_t)b * ((size_t)a.nsweep * NLAG + (size_t)a.nframe * NFRM);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+
+    if ((int)blockIdx.x < a.nsweep) {
+        double dacc[NLAG];
+#pragma unroll
+        for (int v = 0; v < NLAG; v++) dacc[v] = 0.0;
+        for (int t = blockIdx.x; t < a.ntiles; t += a.nsweep) {
+            const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+            const int l0 = tl * TL, p0 = tp * TP;
+            __syncthreads();
+            load_tile<PixT, TL + 2>(tile, img, a.ld, L, P, l0, p0 - HP, a.vec_ok != 0);
+            __syncthreads();
+            float e0[NLAG], e1[NLAG];  // even / odd pixel accumulators
+#pragma unroll
+            for (int v = 0; v < NLAG; v++) { e0[v] = 0.0f; e1[v] = 0.0f; }
+            const float* base = tile + (4 * w) * SW + 4 * lane + 2;  // window col 0 = pixel (p0+4*lane) - 2
+            const int pb = p0 + 4 * lane;
+            bool vp[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) vp[j] = (pb + j >= 1) && (pb + j <= P - 2);
+            float A[8], B[8], C[8];
+            auto loadrow = [](float (&r)[8], const float* s) {
+                const float2 x = *reinterpret_cast<const float2*>(s);
+                const float4 y = *reinterpret_cast<const float4*>(s + 2);
+                const float2 z = *reinterpret_cast<const float2*>(s + 6);
+                r[0] = x.x; r[1] = x.y; r[2] = y.x; r[3] = y.y; r[4] = y.z; r[5] = y.w; r[6] = z.x; r[7] = z.y;
+            };
+            loadrow(A, base);
+            loadrow(B, base + SW);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                loadrow(C, base + (r + 2) * SW);
+                const int l = l0 + 4 * w + r;
+                const bool vl = (l >= 1) && (l <= L - 2);
+#pragma unroll
+                for (int jj = 0; jj < 4; jj += 2) {
+                    const float x0 = (vl && vp[jj]) ? A[jj + 2] : 0.0f;
+                    const float x1 = (vl && vp[jj + 1]) ? A[jj + 3] : 0.0f;
+                    // lag (0, d): A; lag (1, d): B; lag (2, d): C
+#define WM_LAG(v, R, off)                                                                               \
+    if constexpr (FP16) acc2_f16(e0[v], e1[v], __fmul_rn(x0, R[jj + 2 + (off)]), __fmul_rn(x1, R[jj + 3 + (off)])); \
+    else { e0[v] = __fmaf_rn(x0, R[jj + 2 + (off)], e0[v]); e1[v] = __fmaf_rn(x1, R[jj + 3 + (off)], e1[v]); }
+                    WM_LAG(0, A, 0) WM_LAG(1, A, 1) WM_LAG(2, A, 2)
+                    WM_LAG(3, B, -2) WM_LAG(4, B, -1) WM_LAG(5, B, 0) WM_LAG(6, B, 1) WM_LAG(7, B, 2)
+                    WM_LAG(8, C, -2) WM_LAG(9, C, -1) WM_LAG(10, C, 0) WM_LAG(11, C, 1) WM_LAG(12, C, 2)
+#undef WM_LAG
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) { A[i] = B[i]; B[i] = C[i]; }
+            }
+#pragma unroll
+            for (int v = 0; v < NLAG; v++) dacc[v] += (double)e0[v] + (double)e1[v];
+        }
+        __syncthreads();
+        block_sum<NLAG>(dacc, red);
+        if (threadIdx.x < NLAG) part[(size_t)blockIdx.x * NLAG + threadIdx.x] = red[threadIdx.x];
+    } else {
+        // ---- frame ring: pixels within 2 of the border, naive products guarded by "partner not in core" ----
+        const int fb = blockIdx.x - a.nsweep;
+        const int ntop = min(2, L), lbot = max(2, L - 2), nbot = L - lbot > 0 ? L - lbot : 0;
+        const int nmid = max(0, L - 4);
+        const int ncl = min(2, P), pright = max(2, P - 2), ncr = P - pright > 0 ? P - pright : 0;
+        const long long n1 = (long long)ntop * P, n2 = n1 + (long long)nbot * P;
+        const long long count = n2 + (long long)nmid * (ncl + ncr);
+        double facc[NFRM];
+#pragma unroll
+        for (int v = 0; v < NFRM; v++) facc[v] = 0.0;
+        for (long long idx = (long long)fb * NT + threadIdx.x; idx < count; idx += (long long)a.nframe * NT) {
+            int l, p;
+            if (idx < n1) { l = (int)(idx / P); p = (int)(idx - (long long)l * P); }
+            else if (idx < n2) { const long long i2 = idx - n1; const int q = (int)(i2 / P); l = lbot + q; p = (int)(i2 - (long long)q * P); }
+            else { const long long i3 = idx - n2; const int q = (int)(i3 / (ncl + ncr)); const int c = (int)(i3 - (long long)q * (ncl + ncr)); l = 2 + q; p = c < ncl ? c : pright + (c - ncl); }
+            float n[8];
+            bool nc[8];  // neighbour position NOT in core
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int dl = m < 3 ? -1 : (m < 5 ? 0 : 1);
+                const int dp = m < 3 ? m - 1 : (m == 3 ? -1 : (m == 4 ? 1 : m - 6));
+                const int ll = l + dl, pp = p + dp;
+                nc[m] = !(ll >= 1 && ll <= L - 2 && pp >= 1 && pp <= P - 2);
+                n[m] = (float)img[(long long)clampi(ll, 0, L - 1) * a.ld + clampi(pp, 0, P - 1)];
+            }
+            const float x = (float)img[(long long)l * a.ld + p];
+            const bool xc = !(l >= 1 && l <= L - 2 && p >= 1 && p <= P - 2);
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const bool use = m <= 3 ? nc[m] : xc;
+                float pr = __fmul_rn(n[m], x);
+                if constexpr (FP16) pr = round_f16(pr);
+                if (use) facc[m] += (double)pr;
+            }
+            int t = 8;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = i; j < 8; j++, t++) {
+                    float pr = __fmul_rn(n[i], n[j]);
+                    if constexpr (FP16) pr = round_f16(pr);
+                    if (nc[i]) facc[t] += (double)pr;
+                }
+        }
+        block_sum<NFRM>(facc, red);
+        if (threadIdx.x < NFRM) part[(size_t)a.nsweep * NLAG + (size_t)fb * NFRM + threadIdx.x] = red[threadIdx.x];
+    }
+
+    // ---- second stage + solve in the last block ----
+    if (!last_block(a.counter + b, gridDim.x)) return;
+    __shared__ double tot[NTOT];
+    __shared__ double M[72];
+    for (int v = w; v < NTOT; v += NT / 32) {
+        const double s = v < NLAG ? column_sum(part, a.nsweep, NLAG, v)
+                                  : column_sum(part + (size_t)a.nsweep * NLAG, a.nframe, NFRM, v - NLAG);
+        if (lane == 0) tot[v] = s;
+    }
+    __syncthreads();
+    if (w == 0) solve_system(tot, a.scal + b, a.dbg + b, a.transposed, M);
+}
+
+// ================================================================================================
+// k_stats: pass 1 of makeWatermark.  MASK = WM_MASK_ME: e = I - pred (Watermark.cpp:210), accumulates
+// sum (|e| W)^2 and max|e| (the max cancels out of a.mask.W — SURVEY.md §0 — so no separate max pass);
+// MASK = WM_MASK_NVF: sum (nvf W)^2.  Last block: a = strength / (||mask.W|| / sqrt(N)) (Watermark.cpp:170).
+// ================================================================================================
+struct StatsArgs {
+    const void* img;
+    long long ld, bstride;
+    const float* W;  // dense L x P in the image's layout
+    int L, P, tiles_p, ntiles;
+    int vec_ok, w_vec_ok;
+    float strength;
+    double* part;       // [batch][gridDim.x][2]
+    unsigned* counter;  // [batch]
+    Scal* scal;
+    ScalDbg* dbg;
+};
+
+template <typename PixT, int MASK, bool TR>
+__global__ void __launch_bounds__(NT, 3) k_stats(const StatsArgs a)
+{
+    __shared__ __align__(16) float tile[(TL + 2) * SW];
+    __shared__ double red[8 * 2];
+    const int b = blockIdx.y;
+    Scal* sc = a.scal + b;
+    if (MASK == 0 && sc->status != 0) return;  // singular: a untouched, apply copies base through
+    const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
+    const int L = a.L, P = a.P;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
+    double dsum = 0.0;
+    float emax = 0.0f;
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+        const int l0 = tl * TL, p0 = tp * TP;
+        const int pb = p0 + 4 * lane;
+        // W for my 4 x 4 pixels straight from global (issued before the tile barrier)
+        float4 wv[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int l = l0 + 4 * w + r;
+            wv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (l < L && pb < P) {
+                const float* wr = a.W + (long long)l * P + pb;
+                if (a.w_vec_ok && pb + 3 < P) wv[r] = __ldg(reinterpret_cast<const float4*>(wr));
+                else {
+                    wv[r].x = wr[0];
+                    if (pb + 1 < P) wv[r].y = wr[1];
+                    if (pb + 2 < P) wv[r].z = wr[2];
+                    if (pb + 3 < P) wv[r].w = wr[3];
+                }
+            }
+        }
+        __syncthreads();
+        load_tile<PixT, TL + 2>(tile, img, a.ld, L, P, l0 - 1, p0 - HP, a.vec_ok != 0);
+        __syncthreads();
+        const float* base = tile + (4 * w) * SW;  // smem line of image line l-1 for r = 0
+        const int scol = 4 * lane + HP;
+        float r0[6], r1[6], r2[6];
+        load_win6(r0, base, scol);
+        load_win6(r1, base + SW, scol);
+        float fs = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            load_win6(r2, base + (r + 2) * SW, scol);
+            const int l = l0 + 4 * w + r;
+            const float wq[4] = {wv[r].x, wv[r].y, wv[r].z, wv[r].w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (l < L && pb + j < P) {
+                    float m;
+                    if constexpr (MASK == 0) {
+                        m = fabsf(__fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j)));
+                        emax = fmaxf(emax, m);
+                    } else {
+                        m = nvf_mask<TR>(r0, r1, r2, j);
+                    }
+                    const float u = __fmul_rn(m, wq[j]);
+                    fs = __fmaf_rn(u, u, fs);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
+        }
+        dsum += (double)fs;
+    }
+    const double v2[2] = {dsum, (double)emax};
+    {   // block reduce: sum and max
+        const double s = warp_sum(v2[0]);
+        const float m = warp_max(emax);
+        if (lane == 0) { red[w * 2] = s; red[w * 2 + 1] = (double)m; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ss = 0.0, mm = 0.0;
+            for (int k = 0; k < NT / 32; k++) { ss += red[k * 2]; mm = fmax(mm, red[k * 2 + 1]); }
+            double* part = a.part + ((size_t)b * gridDim.x + blockIdx.x) * 2;
+            part[0] = ss; part[1] = mm;
+        }
+    }
+    if (!last_block(a.counter + b, gridDim.x)) return;
+    if (w == 0) {
+        const double* part = a.part + (size_t)b * gridDim.x * 2;
+        const double S2 = column_sum(part, gridDim.x, 2, 0);
+        const float mx = column_max(part, gridDim.x, 2, 1);
+        if (lane == 0) {
+            double nrm = sqrt(S2);
+            if (MASK == 0) nrm = nrm / (double)mx;
+            const double N = (double)L * (double)P;
+            const float av = a.strength / (float)(nrm / sqrt(N));
+            sc->a = av;
+            sc->emax = mx;
+            a.dbg[b].sum2 = S2;
+            sc->status = (nrm > 0.0) ? 0 : 2;
+        }
+    }
+}
+
+// ================================================================================================
+// k_apply: pass 2 of makeWatermark — out = clamp(base + (mask.W).a, 0, 255) per channel (Watermark.cpp:169-171);
+// u8 output truncates like `.as(u8)` (main.cpp:356,380).  status != 0 copies base through unchanged.
+// ================================================================================================
+struct ApplyArgs {
+    const void* img;
+    long long ld, bstride;
+    const float* W;
+    const void* base;   // PixT, channels planes
+    long long base_ld, base_bstride, base_pstride;
+    void* out;          // OutT
+    long long out_ld, out_bstride, out_pstride;
+    int channels, same_base;
+    int L, P, tiles_p, ntiles;
+    int vec_ok, w_vec_ok, base_vec_ok, out_vec_ok;
+    const Scal* scal;
+};
+
+template <typename T> __device__ __forceinline__ T to_out(float v);
+template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ uint8_t to_out<uint8_t>(float v) { return (uint8_t)v; }  // truncation
+
+template <typename PixT, typename OutT, int MASK, bool TR>
+__global__ void __launch_bounds__(NT, 3) k_apply(const ApplyArgs a)
+{
+    __shared__ __align__(16) float tile[(TL + 2) * SW];
+    const int b = blockIdx.y;
+    const Scal* sc = a.scal + b;
+    const int status = sc->status;
+    const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
+    const PixT* bas = reinterpret_cast<const PixT*>(a.base) + (long long)b * a.base_bstride;
+    OutT* out = reinterpret_cast<OutT*>(a.out) + (long long)b * a.out_bstride;
+    const int L = a.L, P = a.P;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
+    const float av = sc->a, mx = sc->emax;
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+        const int l0 = tl * TL, p0 = tp * TP;
+        const int pb = p0 + 4 * lane;
+        float4 wv[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int l = l0 + 4 * w + r;
+            wv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (status == 0 && l < L && pb < P) {
+                const float* wr = a.W + (long long)l * P + pb;
+                if (a.w_vec_ok && pb + 3 < P) wv[r] = __ldg(reinterpret_cast<const float4*>(wr));
+                else {
+                    wv[r].x = wr[0];
+                    if (pb + 1 < P) wv[r].y = wr[1];
+                    if (pb + 2 < P) wv[r].z = wr[2];
+                    if (pb + 3 < P) wv[r].w = wr[3];
+                }
+            }
+        }
+        __syncthreads();
+        if (status == 0) load_tile<PixT, TL + 2>(tile, img, a.ld, L, P, l0 - 1, p0 - HP, a.vec_ok != 0);
+        __syncthreads();
+        const float* tb = tile + (4 * w) * SW;
+        const int scol = 4 * lane + HP;
+        float r0[6], r1[6], r2[6];
+        if (status == 0) { load_win6(r0, tb, scol); load_win6(r1, tb + SW, scol); }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int l = l0 + 4 * w + r;
+            float au[4] = {0.f, 0.f, 0.f, 0.f};  // u = mask*W per pixel
+            if (status == 0) {
+                load_win6(r2, tb + (r + 2) * SW, scol);
+                const float wq[4] = {wv[r].x, wv[r].y, wv[r].z, wv[r].w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float m;
+                    if constexpr (MASK == 0) m = __fdiv_rn(fabsf(__fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j))), mx);
+                    else m = nvf_mask<TR>(r0, r1, r2, j);
+                    au[j] = __fmul_rn(m, wq[j]);
+                }
+            }
+            if (l < L && pb < P) {
+                for (int ch = 0; ch < a.channels; ch++) {
+                    float bv[4];
+                    if (a.same_base && status == 0) {
+                        bv[0] = r1[1]; bv[1] = r1[2]; bv[2] = r1[3]; bv[3] = r1[4];
+                    } else {
+                        const PixT* br = bas + (long long)ch * a.base_pstride + (long long)l * a.base_ld + pb;
+                        if (a.base_vec_ok && pb + 3 < P) {
+                            if constexpr (sizeof(PixT) == 4) {
+                                const float4 v = __ldg(reinterpret_cast<const float4*>(br));
+                                bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+                            } else {
+                                const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(br));
+                                bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) bv[j] = (pb + j < P) ? (float)br[j] : 0.0f;
+                        }
+                    }
+                    float ov[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float v = status == 0 ? __fmaf_rn(au[j], av, bv[j]) : bv[j];
+                        if (status == 0) v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);
+                        ov[j] = v;
+                    }
+                    OutT* orow = out + (long long)ch * a.out_pstride + (long long)l * a.out_ld + pb;
+                    if (a.out_vec_ok && pb + 3 < P) {
+                        if constexpr (sizeof(OutT) == 4) {
+                            *reinterpret_cast<float4*>(orow) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                        } else {
+                            *reinterpret_cast<uchar4*>(orow) =
+                                make_uchar4(to_out<uint8_t>(ov[0]), to_out<uint8_t>(ov[1]), to_out<uint8_t>(ov[2]), to_out<uint8_t>(ov[3]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) if (pb + j < P) orow[j] = to_out<OutT>(ov[j]);
+                    }
+                }
+            }
+            if (status == 0) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// k_detect: after k_sweep on the watermarked image Z.  Per tile: Z (halo 2) and W (halo 1) in smem;
+// phase 1 computes e_z (kept in registers) and u = mask.W (ME: |e_z|.W — the 1/max|e| scale cancels in
+// the correlation; NVF: nvf.W) over the tile plus a 1-pixel ring, into smem; cells of the ring that fall
+// outside the image replicate the edge value of u (the reference re-stages u into a clamp-to-edge
+// texture, Watermark.cpp:221-225); phase 2 computes e_u = u - pred(u) and accumulates <e_u,e_z>,
+// |e_z|^2, |e_u|^2.  Last block: corr = dot / (|e_z| |e_u|) (Watermark.cpp:228-231).
+// ================================================================================================
+struct DetectArgs {
+    const void* img;
+    long long ld, bstride;
+    const float* W;
+    int L, P, tiles_p, ntiles;
+    int vec_ok, w_vec_ok;
+    double* part;       // [batch][gridDim.x][3]
+    unsigned* counter;
+    Scal* scal;
+    ScalDbg* dbg;
+};
+constexpr int DET_SMEM = ((TL + 4) + 2 * (TL + 2)) * SW * 4;  // Z, W, u tiles
+
+template <typename PixT, int MASK, bool TR>
+__global__ void __launch_bounds__(NT, 2) k_detect(const DetectArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    float* zt = smem;                       // (TL+4) x SW : lines l0-2 .. l0+TL+1
+    float* wt = zt + (TL + 4) * SW;         // (TL+2) x SW : lines l0-1 .. l0+TL
+    float* ut = wt + (TL + 2) * SW;         // (TL+2) x SW : same frame as wt
+    __shared__ double red[8 * 3];
+    const int b = blockIdx.y;
+    Scal* sc = a.scal + b;
+    if (sc->status != 0) return;  // singular: corr = 0 was written by the sweep
+    const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
+    const int L = a.L, P = a.P;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = sc->coef[k];
+    double ddot = 0.0, dnz = 0.0, dnu = 0.0;
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+        const int l0 = tl * TL, p0 = tp * TP;
+        const int pb = p0 + 4 * lane;
+        __syncthreads();
+        load_tile<PixT, TL + 4>(zt, img, a.ld, L, P, l0 - 2, p0 - HP, a.vec_ok != 0);
+        load_tile<float, TL + 2>(wt, a.W, P, L, P, l0 - 1, p0 - HP, a.w_vec_ok != 0);
+        __syncthreads();
+        const int scol = 4 * lane + HP;
+        float ez[4][4];
+        // ---- phase 1a: my 4 x 4 pixels ----
+        {
+            const float* zb = zt + (4 * w + 1) * SW;  // smem line of image line l-1 for r = 0
+            float r0[6], r1[6], r2[6];
+            load_win6(r0, zb, scol);
+            load_win6(r1, zb + SW, scol);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                load_win6(r2, zb + (r + 2) * SW, scol);
+                const float4 wv = *reinterpret_cast<const float4*>(wt + (4 * w + r + 1) * SW + scol);
+                const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+                float uu[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float e = __fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j));
+                    ez[r][j] = e;
+                    float m;
+                    if constexpr (MASK == 0) m = fabsf(e); else m = nvf_mask<TR>(r0, r1, r2, j);
+                    uu[j] = __fmul_rn(m, wq[j]);
+                }
+                *reinterpret_cast<float4*>(ut + (4 * w + r + 1) * SW + scol) = make_float4(uu[0], uu[1], uu[2], uu[3]);
+#pragma unroll
+                for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
+            }
+        }
+        // ---- phase 1b: the 1-pixel ring around the tile (in-image cells only) ----
+        for (int idx = threadIdx.x; idx < 2 * (TP + 2) + 2 * TL; idx += NT) {
+            int rl, rp;  // relative to (l0, p0)
+            if (idx < TP + 2) { rl = -1; rp = idx - 1; }
+            else if (idx < 2 * (TP + 2)) { rl = TL; rp = idx - (TP + 2) - 1; }
+            else if (idx < 2 * (TP + 2) + TL) { rl = idx - 2 * (TP + 2); rp = -1; }
+            else { rl = idx - 2 * (TP + 2) - TL; rp = TP; }
+            const int l = l0 + rl, p = p0 + rp;
+            if (l >= 0 && l < L && p >= 0 && p < P) {
+                const float* zc = zt + (rl + 2) * SW + (rp + HP);
+                float q0[3] = {zc[-SW - 1], zc[-SW], zc[-SW + 1]};
+                float q1[3] = {zc[-1], zc[0], zc[1]};
+                float q2[3] = {zc[SW - 1], zc[SW], zc[SW + 1]};
+                float m;
+                if constexpr (MASK == 0) m = fabsf(__fsub_rn(q1[1], predict<TR>(c, q0, q1, q2, 0)));
+                else m = nvf_mask<TR>(q0, q1, q2, 0);
+                ut[(rl + 1) * SW + (rp + HP)] = __fmul_rn(m, wt[(rl + 1) * SW + (rp + HP)]);
+            }
+        }
+        __syncthreads();
+        // ---- border tiles: replicate u into ring cells outside the image (sources are in-image cells) ----
+        if (l0 == 0 || p0 == 0 || l0 + TL >= L || p0 + TP >= P) {
+            for (int idx = threadIdx.x; idx < (TL + 2) * (TP + 2); idx += NT) {
+                const int rl = idx / (TP + 2) - 1, rp = idx - (rl + 1) * (TP + 2) - 1;
+                const int l = l0 + rl, p = p0 + rp;
+                if (l < 0 || l >= L || p < 0 || p >= P) {
+                    const int lc = clampi(l, 0, L - 1) - l0, pc = clampi(p, 0, P - 1) - p0;
+                    ut[(rl + 1) * SW + (rp + HP)] = ut[(lc + 1) * SW + (pc + HP)];
+                }
+            }
+            __syncthreads();
+        }
+        // ---- phase 2: e_u and the correlation sums ----
+        {
+            const float* ub = ut + (4 * w) * SW;
+            float r0[6], r1[6], r2[6];
+            load_win6(r0, ub, scol);
+            load_win6(r1, ub + SW, scol);
+            float fd = 0.0f, fz = 0.0f, fu = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                load_win6(r2, ub + (r + 2) * SW, scol);
+                const int l = l0 + 4 * w + r;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (l < L && pb + j < P) {
+                        const float eu = __fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j));
+                        const float e = ez[r][j];
+                        fd = __fmaf_rn(eu, e, fd);
+                        fz = __fmaf_rn(e, e, fz);
+                        fu = __fmaf_rn(eu, eu, fu);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
+            }
+            ddot += (double)fd; dnz += (double)fz; dnu += (double)fu;
+        }
+    }
+    __syncthreads();
+    const double v3[3] = {ddot, dnz, dnu};
+    block_sum<3>(v3, red);
+    if (threadIdx.x < 3) a.part[((size_t)b * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = red[threadIdx.x];
+    if (!last_block(a.counter + b, gridDim.x)) return;
+    if (w < 3) {
+        const double s = column_sum(a.part + (size_t)b * gridDim.x * 3, gridDim.x, 3, w);
+        if (lane == 0) red[w] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a.dbg[b].dot = red[0]; a.dbg[b].nz = red[1]; a.dbg[b].nu = red[2];
+        const float dotf = (float)red[0];
+        sc->corr = dotf / (float)(sqrt(red[1]) * sqrt(red[2]));
+    }
+}
+
+// ================================================================================================
+// debug planes (parity access to Watermark.hpp:52-58 privates): e = I - pred, or the NVF mask, dense output
+// ================================================================================================
+struct PlaneArgs {
+    const void* img;
+    long long ld;
+    int L, P, tiles_p, ntiles, vec_ok;
+    const Scal* scal;
+    float* dst;  // dense L x P
+};
+template <typename PixT, int WHAT /*0 errseq, 1 nvf*/, bool TR>
+__global__ void __launch_bounds__(NT, 3) k_plane(const PlaneArgs a)
+{
+    __shared__ __align__(16) float tile[(TL + 2) * SW];
+    const PixT* img = reinterpret_cast<const PixT*>(a.img);
+    const int L = a.L, P = a.P;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = a.scal->coef[k];
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+        const int l0 = tl * TL, p0 = tp * TP, pb = p0 + 4 * lane;
+        __syncthreads();
+        load_tile<PixT, TL + 2>(tile, img, a.ld, L, P, l0 - 1, p0 - HP, a.vec_ok != 0);
+        __syncthreads();
+        const float* tb = tile + (4 * w) * SW;
+        const int scol = 4 * lane + HP;
+        float r0[6], r1[6], r2[6];
+        load_win6(r0, tb, scol);
+        load_win6(r1, tb + SW, scol);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            load_win6(r2, tb + (r + 2) * SW, scol);
+            const int l = l0 + 4 * w + r;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (l < L && pb + j < P) {
+                    float v;
+                    if constexpr (WHAT == 0) v = __fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j));
+                    else v = nvf_mask<TR>(r0, r1, r2, j);
+                    a.dst[(long long)l * P + pb + j] = v;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
+        }
+    }
+}
+
+// dense transpose (rows x cols row-major -> col-major), used once per ctx for W
+__global__ void k_transpose(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols)
+{
+    __shared__ float t[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8)
+        if (r0 + i < rows && c < cols) t[i][threadIdx.x] = src[(long long)(r0 + i) * cols + c];
+    __syncthreads();
+    const int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += 8)
+        if (c0 + i < cols && r < rows) dst[(long long)(c0 + i) * rows + r] = t[threadIdx.x][i];
+}
+
+// strided u8 plane -> contiguous (main.cpp:348-353 repack), or plain copy-through of gated-off frames
+__global__ void k_repack_u8(const uint8_t* __restrict__ src, long long src_ld, uint8_t* __restrict__ dst, int H, int Wd)
+{
+    const long long n = (long long)H * Wd;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / Wd), c = (int)(i - (long long)r * Wd);
+        dst[i] = src[(long long)r * src_ld + c];
+    }
+}
+
+}  // namespace wm
