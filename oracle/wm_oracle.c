@@ -8,11 +8,13 @@
  *
  * PARITY STATUS: the reference ships no tests, no golden vectors and no
  * recorded outputs and cannot be built offline (ArrayFire
- * un-vendored, no OpenCL platform).  The three OpenCL kernels are pinned by
- * executing the reference's own kernel source under a CPU OpenCL-C shim
- * (oracle/clshim → oracle/_ref, see oracle/README.md); the ArrayFire library
- * calls between them (sum, solve, norm, dot, max, clamp) are restated from
- * their documented semantics => for those "parity unpinned".
+ * un-vendored, no OpenCL platform).  The three OpenCL kernels are PINNED: the
+ * reference's own kernel source runs on the CPU under an OpenCL-C shim
+ * (oracle/clshim -> oracle/_ref, see oracle/README.md) and
+ * tests/test_oracle_vs_reference_kernels.py requires bit-for-bit agreement.
+ * The ArrayFire library calls between them (sum, solve, norm, dot, max,
+ * clamp) are restated from their documented semantics => for those
+ * "parity unpinned".
  *
  * Conventions: all images are ROW-MAJOR (rows x cols) float arrays,
  * img[r*cols + c], i.e. the logical (row, col) indexing of the reference's
