@@ -448,3 +448,38 @@ def test_full_size_properties(wmb, oracle, rows, cols):
         assert abs(a1 - o["a"]) / o["a"] <= 1e-3
         assert np.abs(g1 - o["out"]).max() <= 1e-4 * 255
     wm.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# TMA tile pipeline vs the plain cooperative loader: same arithmetic, so bit-identical results
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,cols", [(64, 64), (128, 32), (200, 96), (132, 260), (512, 512), (1080, 1920)])
+def test_tma_and_plain_paths_agree(wmb, oracle, rows, cols):
+    img = util.natural_image(rows, cols, seed=rows + 3 * cols)
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    res = {}
+    for tma in (1, 0):
+        wm.set_option(wmb.OPT_USE_TMA, tma)
+        for layout in LAYOUTS:
+            d = wmb.DeviceArray.from_numpy(wm, img, layout)
+            for mask in (wmb.ME, wmb.NVF):
+                out, a, st = wm.makeWatermark(d, d, mask)
+                got = out.numpy()
+                dz = wmb.DeviceArray.from_numpy(wm, got, layout)
+                corr, st2 = wm.detectWatermark(dz, mask)
+                Rx = wm.debug(wmb.DBG_RX)
+                res[(tma, layout, mask)] = (a, got, corr, Rx, st, st2)
+    for layout in LAYOUTS:
+        for mask in (wmb.ME, wmb.NVF):
+            a1, g1, c1, R1, s1, t1 = res[(1, layout, mask)]
+            a0, g0, c0, R0, s0, t0 = res[(0, layout, mask)]
+            report("tma_vs_plain %dx%d layout=%d mask=%d a %g/%g corr %g/%g dpix=%g" % (
+                rows, cols, layout, mask, a1, a0, c1, c0, np.abs(g1 - g0).max()))
+            assert s1 == 0 and t1 == 0 and s0 == 0 and t0 == 0
+            assert a1 == a0 and c1 == c0 and np.array_equal(g1, g0) and np.array_equal(R1, R0)
+    if rows <= 512:
+        o = oracle.embed(img, W, 40.0, wmb.ME)
+        assert abs(res[(1, 1, wmb.ME)][0] - o["a"]) / o["a"] <= 1e-3
+        assert np.abs(res[(1, 1, wmb.ME)][1] - o["out"]).max() <= 1e-4 * 255
+    wm.close()

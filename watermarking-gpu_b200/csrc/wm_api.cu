@@ -200,13 +200,13 @@ Plan plan(const wm_ctx* ctx, const Geo& g, int batch)
     const long long ring = 4LL * (g.L + g.P);
     if (batch == 1) {
         p.nsweep = std::min(g.ntiles, 2 * ctx->sms);
-        p.gx_stats = std::min(g.ntiles, 3 * ctx->sms);
+        p.gx_stats = std::min(g.ntiles, 2 * ctx->sms);
         p.gx_detect = std::min(g.ntiles, 2 * ctx->sms);
-        p.nframe = (int)std::min<long long>(64, std::max<long long>(1, (ring + NT * 32 - 1) / (NT * 32)));
+        p.nframe = (int)std::min<long long>(64, std::max<long long>(1, (ring + NT * 8 - 1) / (NT * 8)));
     } else {
         const int per = std::max(1, std::min(g.ntiles, (4 * ctx->sms + batch - 1) / batch));
         p.nsweep = p.gx_stats = p.gx_detect = per;
-        p.nframe = (int)std::min<long long>(64, std::max<long long>(1, (ring + NT * 64 - 1) / (NT * 64)));
+        p.nframe = (int)std::min<long long>(64, std::max<long long>(1, (ring + NT * 16 - 1) / (NT * 16)));
     }
     return p;
 }
@@ -246,64 +246,104 @@ void drain_timers(wm_ctx* ctx, Slot& s)
     s.timed.clear();
 }
 
-// ---- kernel dispatch over (pixel type, out type, mask, transposed) ----
-template <typename PixT>
-void launch_sweep_t(bool fp16, dim3 grid, cudaStream_t st, const SweepArgs& a)
+// ---- TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no libcuda link) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn()
 {
-    if (fp16) k_sweep<PixT, true><<<grid, NT, 0, st>>>(a);
-    else k_sweep<PixT, false><<<grid, NT, 0, st>>>(a);
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
 }
-void launch_sweep(int dtype, bool fp16, dim3 grid, cudaStream_t st, const SweepArgs& a)
+// f32 tensor (pixel, line, image) with a (boxP x boxL x 1) box; out-of-bounds elements are zero-filled
+bool make_tmap(CUtensorMap* tm, const void* ptr, int P, int L, int B, long long ld, long long bstride, int boxP, int boxL)
 {
-    if (dtype == WM_F32) launch_sweep_t<float>(fp16, grid, st, a); else launch_sweep_t<uint8_t>(fp16, grid, st, a);
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)L, (cuuint64_t)std::max(B, 1)};
+    const long long bs = (B > 1 && bstride > 0) ? bstride : (long long)L * ld;
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)bs * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)boxP, (cuuint32_t)boxL, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool tma_ok(const wm_ctx* ctx, const View& v, long long bstride, int batch)
+{
+    return ctx->opt_tma && v.dtype == WM_F32 && ((uintptr_t)v.ptr % 16 == 0) && (v.ld % 4 == 0) && (v.P % 4 == 0) &&
+           (batch == 1 || bstride % 4 == 0) && encode_fn() != nullptr;
 }
 
-#define WM_DISPATCH_MT(FN, PIX, mask, tr, ...)                                   \
-    do {                                                                         \
-        if ((mask) == WM_MASK_ME) { if (tr) FN<PIX, 0, true> __VA_ARGS__; else FN<PIX, 0, false> __VA_ARGS__; } \
-        else { if (tr) FN<PIX, 1, true> __VA_ARGS__; else FN<PIX, 1, false> __VA_ARGS__; }                    \
+// ---- kernel dispatch over (pixel type, out type, mask, transposed, TMA) ----
+template <typename K>
+void set_smem(K kernel, int bytes)
+{
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+#define WM_LAUNCH(KERNEL, SMEM, ...)                                   \
+    do {                                                               \
+        static bool done_[64] = {false};                               \
+        int dev_ = 0;                                                  \
+        cudaGetDevice(&dev_);                                          \
+        if (!done_[dev_ & 63]) { set_smem(KERNEL, SMEM); done_[dev_ & 63] = true; } \
+        KERNEL<<<grid, NT, SMEM, st>>>(__VA_ARGS__);                   \
     } while (0)
 
-void launch_stats(int dtype, int mask, bool tr, dim3 grid, cudaStream_t st, const StatsArgs& a)
+void launch_sweep(int dtype, bool fp16, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const SweepArgs& a)
 {
-    if (dtype == WM_F32) WM_DISPATCH_MT(k_stats, float, mask, tr, <<<grid, NT, 0, st>>>(a));
-    else WM_DISPATCH_MT(k_stats, uint8_t, mask, tr, <<<grid, NT, 0, st>>>(a));
+    if (dtype == WM_F32) {
+        if (tma) { if (fp16) WM_LAUNCH((k_sweep<float, true, true>), sweep_smem(true), tmI, a); else WM_LAUNCH((k_sweep<float, false, true>), sweep_smem(true), tmI, a); }
+        else { if (fp16) WM_LAUNCH((k_sweep<float, true, false>), sweep_smem(false), tmI, a); else WM_LAUNCH((k_sweep<float, false, false>), sweep_smem(false), tmI, a); }
+    } else {
+        if (fp16) WM_LAUNCH((k_sweep<uint8_t, true, false>), sweep_smem(false), tmI, a); else WM_LAUNCH((k_sweep<uint8_t, false, false>), sweep_smem(false), tmI, a);
+    }
 }
 
-template <typename PixT, typename OutT>
-void launch_apply_t(int mask, bool tr, dim3 grid, cudaStream_t st, const ApplyArgs& a)
+template <typename PixT, bool TMA>
+void launch_stats_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
 {
-    if (mask == WM_MASK_ME) { if (tr) k_apply<PixT, OutT, 0, true><<<grid, NT, 0, st>>>(a); else k_apply<PixT, OutT, 0, false><<<grid, NT, 0, st>>>(a); }
-    else { if (tr) k_apply<PixT, OutT, 1, true><<<grid, NT, 0, st>>>(a); else k_apply<PixT, OutT, 1, false><<<grid, NT, 0, st>>>(a); }
+    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_stats<PixT, 0, true, TMA>), embed_smem(TMA), tmI, tmW, a); else WM_LAUNCH((k_stats<PixT, 0, false, TMA>), embed_smem(TMA), tmI, tmW, a); }
+    else { if (tr) WM_LAUNCH((k_stats<PixT, 1, true, TMA>), embed_smem(TMA), tmI, tmW, a); else WM_LAUNCH((k_stats<PixT, 1, false, TMA>), embed_smem(TMA), tmI, tmW, a); }
 }
-void launch_apply(int in_dtype, int out_dtype, int mask, bool tr, dim3 grid, cudaStream_t st, const ApplyArgs& a)
+void launch_stats(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
+{
+    if (dtype == WM_F32) { if (tma) launch_stats_t<float, true>(mask, tr, grid, st, tmI, tmW, a); else launch_stats_t<float, false>(mask, tr, grid, st, tmI, tmW, a); }
+    else launch_stats_t<uint8_t, false>(mask, tr, grid, st, tmI, tmW, a);
+}
+
+template <typename PixT, typename OutT, bool TMA>
+void launch_apply_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
+{
+    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 0, true, TMA>), embed_smem(TMA), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 0, false, TMA>), embed_smem(TMA), tmI, tmW, a); }
+    else { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 1, true, TMA>), embed_smem(TMA), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 1, false, TMA>), embed_smem(TMA), tmI, tmW, a); }
+}
+void launch_apply(int in_dtype, int out_dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI,
+                  const CUtensorMap& tmW, const EmbedArgs& a)
 {
     if (in_dtype == WM_F32) {
-        if (out_dtype == WM_F32) launch_apply_t<float, float>(mask, tr, grid, st, a); else launch_apply_t<float, uint8_t>(mask, tr, grid, st, a);
+        if (out_dtype == WM_F32) { if (tma) launch_apply_t<float, float, true>(mask, tr, grid, st, tmI, tmW, a); else launch_apply_t<float, float, false>(mask, tr, grid, st, tmI, tmW, a); }
+        else { if (tma) launch_apply_t<float, uint8_t, true>(mask, tr, grid, st, tmI, tmW, a); else launch_apply_t<float, uint8_t, false>(mask, tr, grid, st, tmI, tmW, a); }
     } else {
-        if (out_dtype == WM_F32) launch_apply_t<uint8_t, float>(mask, tr, grid, st, a); else launch_apply_t<uint8_t, uint8_t>(mask, tr, grid, st, a);
+        if (out_dtype == WM_F32) launch_apply_t<uint8_t, float, false>(mask, tr, grid, st, tmI, tmW, a); else launch_apply_t<uint8_t, uint8_t, false>(mask, tr, grid, st, tmI, tmW, a);
     }
 }
 
-template <typename PixT, int MASK, bool TR>
-void launch_detect_one(dim3 grid, cudaStream_t st, const DetectArgs& a)
+template <typename PixT, bool TMA>
+void launch_detect_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
 {
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev & 63]) {
-        cudaFuncSetAttribute(k_detect<PixT, MASK, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, DET_SMEM);
-        attr_set[dev & 63] = true;
-    }
-    k_detect<PixT, MASK, TR><<<grid, NT, DET_SMEM, st>>>(a);
+    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_detect<PixT, 0, true, TMA>), detect_smem(TMA), tmZ, tmW, a); else WM_LAUNCH((k_detect<PixT, 0, false, TMA>), detect_smem(TMA), tmZ, tmW, a); }
+    else { if (tr) WM_LAUNCH((k_detect<PixT, 1, true, TMA>), detect_smem(TMA), tmZ, tmW, a); else WM_LAUNCH((k_detect<PixT, 1, false, TMA>), detect_smem(TMA), tmZ, tmW, a); }
 }
-void launch_detect(int dtype, int mask, bool tr, dim3 grid, cudaStream_t st, const DetectArgs& a)
+void launch_detect(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
 {
-#define WM_DET(PIX)                                                                                   \
-    if (mask == WM_MASK_ME) { if (tr) launch_detect_one<PIX, 0, true>(grid, st, a); else launch_detect_one<PIX, 0, false>(grid, st, a); } \
-    else { if (tr) launch_detect_one<PIX, 1, true>(grid, st, a); else launch_detect_one<PIX, 1, false>(grid, st, a); }
-    if (dtype == WM_F32) { WM_DET(float) } else { WM_DET(uint8_t) }
-#undef WM_DET
+    if (dtype == WM_F32) { if (tma) launch_detect_t<float, true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_t<float, false>(mask, tr, grid, st, tmZ, tmW, a); }
+    else launch_detect_t<uint8_t, false>(mask, tr, grid, st, tmZ, tmW, a);
 }
 
 // enqueue the Rx sweep (+ solve), or the injection of debug coefficients
@@ -328,9 +368,13 @@ int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int ba
     a.part = s.part;
     a.counter = s.counters;
     a.scal = s.scal; a.dbg = s.dbg;
+    CUtensorMap tmI;
+    memset(&tmI, 0, sizeof tmI);
+    bool tma = tma_ok(ctx, v, bstride, batch);
+    if (tma) tma = make_tmap(&tmI, v.ptr, g.P, g.L, batch, v.ld, bstride, SW, TL + 2);
     {
         KTimer t(ctx, s, WM_K_SWEEP);
-        launch_sweep(v.dtype, ctx->opt_fp16 != 0, dim3(pl.nsweep + pl.nframe, batch), s.stream, a);
+        launch_sweep(v.dtype, ctx->opt_fp16 != 0, tma, dim3(pl.nsweep + pl.nframe, batch), s.stream, tmI, a);
     }
     CU(cudaGetLastError());
     return WM_OK;
@@ -364,36 +408,37 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     if (mask == WM_MASK_ME) {
         if ((rc = enqueue_sweep(ctx, s, vi, in_stride, batch, g, pl))) return rc;
     }
-    StatsArgs sa;
-    sa.img = vi.ptr; sa.ld = vi.ld; sa.bstride = in_stride;
-    sa.W = W;
-    sa.L = g.L; sa.P = g.P; sa.tiles_p = g.tiles_p; sa.ntiles = g.ntiles;
-    sa.vec_ok = vec_ok(vi.ptr, vi.ld, in_stride, 0, vi.dtype);
-    sa.w_vec_ok = (g.P % 4 == 0);
-    sa.strength = ctx->strength;
-    sa.part = s.part + stats_part_offset(pl, batch);
-    sa.counter = s.counters + s.batch_cap;
-    sa.scal = s.scal; sa.dbg = s.dbg;
+    EmbedArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.img = vi.ptr; ea.ld = vi.ld; ea.bstride = in_stride;
+    ea.W = W;
+    ea.L = g.L; ea.P = g.P; ea.tiles_p = g.tiles_p; ea.ntiles = g.ntiles;
+    ea.vec_ok = vec_ok(vi.ptr, vi.ld, in_stride, 0, vi.dtype);
+    ea.w_vec_ok = (g.P % 4 == 0);
+    ea.strength = ctx->strength;
+    ea.part = s.part + stats_part_offset(pl, batch);
+    ea.counter = s.counters + s.batch_cap;
+    ea.scal = s.scal; ea.dbg = s.dbg;
+    ea.base = vb.ptr; ea.base_ld = vb.ld; ea.base_bstride = base_stride; ea.base_pstride = vb.pstride;
+    ea.out = vo.ptr; ea.out_ld = vo.ld; ea.out_bstride = out_stride; ea.out_pstride = vo.pstride;
+    ea.channels = vb.channels;
+    ea.same_base = (vb.ptr == vi.ptr && vb.ld == vi.ld && base_stride == in_stride && vb.channels == 1);
+    ea.base_vec_ok = vec_ok(vb.ptr, vb.ld, base_stride, vb.channels > 1 ? vb.pstride : 0, vb.dtype);
+    ea.out_vec_ok = vec_ok(vo.ptr, vo.ld, out_stride, vo.channels > 1 ? vo.pstride : 0, vo.dtype);
+    CUtensorMap tmI, tmW;
+    memset(&tmI, 0, sizeof tmI);
+    memset(&tmW, 0, sizeof tmW);
+    bool tma = tma_ok(ctx, vi, in_stride, batch);
+    if (tma) tma = make_tmap(&tmI, vi.ptr, g.P, g.L, batch, vi.ld, in_stride, SW, TL + 2) &&
+                   make_tmap(&tmW, W, g.P, g.L, 1, g.P, 0, TP, TL);
     {
         KTimer t(ctx, s, mask == WM_MASK_ME ? WM_K_ME_STATS : WM_K_NVF_STATS);
-        launch_stats(vi.dtype, mask, vi.transposed, dim3(pl.gx_stats, batch), s.stream, sa);
+        launch_stats(vi.dtype, mask, vi.transposed, tma, dim3(pl.gx_stats, batch), s.stream, tmI, tmW, ea);
     }
     CU(cudaGetLastError());
-    ApplyArgs aa;
-    aa.img = vi.ptr; aa.ld = vi.ld; aa.bstride = in_stride;
-    aa.W = W;
-    aa.base = vb.ptr; aa.base_ld = vb.ld; aa.base_bstride = base_stride; aa.base_pstride = vb.pstride;
-    aa.out = vo.ptr; aa.out_ld = vo.ld; aa.out_bstride = out_stride; aa.out_pstride = vo.pstride;
-    aa.channels = vb.channels;
-    aa.same_base = (vb.ptr == vi.ptr && vb.ld == vi.ld && base_stride == in_stride && vb.channels == 1);
-    aa.L = g.L; aa.P = g.P; aa.tiles_p = g.tiles_p; aa.ntiles = g.ntiles;
-    aa.vec_ok = sa.vec_ok; aa.w_vec_ok = sa.w_vec_ok;
-    aa.base_vec_ok = vec_ok(vb.ptr, vb.ld, base_stride, vb.channels > 1 ? vb.pstride : 0, vb.dtype);
-    aa.out_vec_ok = vec_ok(vo.ptr, vo.ld, out_stride, vo.channels > 1 ? vo.pstride : 0, vo.dtype);
-    aa.scal = s.scal;
     {
         KTimer t(ctx, s, WM_K_APPLY);
-        launch_apply(vi.dtype, vo.dtype, mask, vi.transposed, dim3(pl.gx_stats, batch), s.stream, aa);
+        launch_apply(vi.dtype, vo.dtype, mask, vi.transposed, tma, dim3(pl.gx_stats, batch), s.stream, tmI, tmW, ea);
     }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(s.scal_host, s.scal, sizeof(Scal) * batch, cudaMemcpyDeviceToHost, s.stream));
@@ -428,9 +473,15 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     da.part = s.part + stats_part_offset(pl, batch);
     da.counter = s.counters + 2 * s.batch_cap;
     da.scal = s.scal; da.dbg = s.dbg;
+    CUtensorMap tmZ, tmW;
+    memset(&tmZ, 0, sizeof tmZ);
+    memset(&tmW, 0, sizeof tmW);
+    bool tma = tma_ok(ctx, v, img_stride, batch);
+    if (tma) tma = make_tmap(&tmZ, v.ptr, g.P, g.L, batch, v.ld, img_stride, SW, TL + 4) &&
+                   make_tmap(&tmW, W, g.P, g.L, 1, g.P, 0, SW, TL + 2);
     {
         KTimer t(ctx, s, WM_K_DETECT);
-        launch_detect(v.dtype, mask, v.transposed, dim3(pl.gx_detect, batch), s.stream, da);
+        launch_detect(v.dtype, mask, v.transposed, tma, dim3(pl.gx_detect, batch), s.stream, tmZ, tmW, da);
     }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(s.scal_host, s.scal, sizeof(Scal) * batch, cudaMemcpyDeviceToHost, s.stream));

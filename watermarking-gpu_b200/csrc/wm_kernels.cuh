@@ -18,9 +18,17 @@
 //   k_apply   pass 2 of makeWatermark: clamp(base + a.mask.W, 0, 255) (Watermark.cpp:171)
 //   k_detect  detectWatermark after the sweep: e_z, u = mask.W, e_u and the three correlation sums
 //             (Watermark.cpp:221-231,248-249) in one pass
+//
+// Data movement.  Every kernel is persistent over 128 x 32 pixel tiles.  With TMA = true (f32 images whose base and
+// strides are 16-byte aligned) one elected thread streams the tiles (+ halo) and the matching W tiles into a ring
+// of shared-memory stages with cp.async.bulk.tensor (3-D tensor maps: pixel, line, image) signalled through
+// mbarriers, so the loads of tile i+2 are in flight while tile i is computed; out-of-image halo cells arrive
+// zero-filled and are overwritten with the replicated edge value (clamp-to-edge) by the few CTAs on the image
+// frame.  With TMA = false (u8 frames, odd strides) a cooperative clamped loader fills a single stage.
 #pragma once
-#include <cuda_runtime.h>
+#include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace wm {
@@ -33,6 +41,19 @@ constexpr int SW = TP + 2 * HP;  // smem row stride in floats (136)
 constexpr int NLAG = 13;         // distinct lags of the upper triangle of Rx
 constexpr int NFRM = 44;         // frame partials: 8 rx + 36 Rx (upper triangle)
 constexpr int NTOT = NLAG + NFRM;
+
+constexpr int align128(int x) { return (x + 127) & ~127; }
+// shared-memory stage layouts (bytes)
+constexpr int SZ_I34 = align128((TL + 2) * SW * 4);  // image tile with 1 (or 0+2) halo lines
+constexpr int SZ_I36 = align128((TL + 4) * SW * 4);  // image tile with 2 halo lines (detect)
+constexpr int SZ_WT = TL * TP * 4;                   // W tile, no halo
+constexpr int SWEEP_STAGE = SZ_I34;
+constexpr int EMBED_STAGE = SZ_I34 + SZ_WT;
+constexpr int DETECT_STAGE = SZ_I36 + SZ_I34;        // Z (halo 2) + W (halo 1)
+constexpr int SWEEP_NST = 3, EMBED_NST = 3, DETECT_NST = 2;
+constexpr int sweep_smem(bool tma) { return (tma ? SWEEP_NST : 1) * SWEEP_STAGE; }
+constexpr int embed_smem(bool tma) { return (tma ? EMBED_NST : 1) * EMBED_STAGE; }
+constexpr int detect_smem(bool tma) { return (tma ? DETECT_NST : 1) * DETECT_STAGE + SZ_I34; }  // + u tile
 
 // per-image scalars living in device memory (one per batch entry), mirrored to pinned host memory
 struct Scal {
@@ -53,9 +74,41 @@ struct ScalDbg {
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 // ------------------------------------------------------------------------------------------------
-// tile loader (plain path): fills rows [l_org, l_org+NROWS) x cols [p_org, p_org+SW) of the image into
-// smem as float, coordinates clamped to the image (replicate border).  p_org is a multiple of 4, so a
-// 4-pixel chunk is one aligned 16-byte (f32) / 4-byte (u8) global load when vec_ok.
+// TMA / mbarrier primitives (PTX; SASS: UTMALDG, SYNCS)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// plain tile loaders (TMA = false): rows [l_org, l_org+NROWS) x cols [p_org, p_org+SW) of the image into smem
+// as float, coordinates clamped to the image (replicate border).  p_org is a multiple of 4, so a 4-pixel chunk
+// is one aligned 16-byte (f32) / 4-byte (u8) global load when vec_ok.
 // ------------------------------------------------------------------------------------------------
 template <typename PixT, int NROWS>
 __device__ __forceinline__ void load_tile(float* __restrict__ tile, const PixT* __restrict__ img, long long ld,
@@ -84,6 +137,58 @@ __device__ __forceinline__ void load_tile(float* __restrict__ tile, const PixT* 
         *reinterpret_cast<float4*>(tile + r * SW + 4 * c) = v;
     }
 }
+// W tile without halo: TL x TP floats at (l0, p0); cells outside the image are never used
+__device__ __forceinline__ void load_w_tile(float* __restrict__ wt, const float* __restrict__ W, int L, int P, int l0,
+                                            int p0, bool vec_ok)
+{
+    constexpr int CH = TP / 4;
+    for (int idx = threadIdx.x; idx < TL * CH; idx += NT) {
+        const int r = idx / CH, c = idx - r * CH;
+        const int l = l0 + r, p = p0 + 4 * c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l < L && p < P) {
+            const float* wr = W + (long long)l * P + p;
+            if (vec_ok && p + 3 < P) v = __ldg(reinterpret_cast<const float4*>(wr));
+            else {
+                v.x = wr[0];
+                if (p + 1 < P) v.y = wr[1];
+                if (p + 2 < P) v.z = wr[2];
+                if (p + 3 < P) v.w = wr[3];
+            }
+        }
+        *reinterpret_cast<float4*>(wt + r * TP + 4 * c) = v;
+    }
+}
+
+// TMA tiles arrive zero-filled outside the image: overwrite those cells with the replicated edge value.
+// Sources are in-image cells, targets out-of-image cells, so one pass needs no intermediate barrier.
+template <int NROWS>
+__device__ __forceinline__ bool tile_on_frame(int l_org, int p_org, int L, int P)
+{
+    return l_org < 0 || l_org + NROWS > L || p_org < 0 || p_org + SW > P;
+}
+template <int NROWS>
+__device__ __forceinline__ void fix_border(float* tile, int l_org, int p_org, int L, int P)
+{
+    const int r_lo = max(0, -l_org), r_hi = min(NROWS, L - l_org);  // in-image rows [r_lo, r_hi)
+    const int c_lo = max(0, -p_org), c_hi = min(SW, P - p_org);     // in-image cols [c_lo, c_hi)
+    const int ncol_out = c_lo + (SW - c_hi);
+    if (ncol_out > 0) {
+        for (int idx = threadIdx.x; idx < (r_hi - r_lo) * ncol_out; idx += NT) {
+            const int rr = idx / ncol_out, j = idx - rr * ncol_out;
+            const int r = r_lo + rr, c = j < c_lo ? j : c_hi + (j - c_lo);
+            tile[r * SW + c] = tile[r * SW + clampi(c, c_lo, c_hi - 1)];
+        }
+    }
+    const int nrow_out = r_lo + (NROWS - r_hi);
+    if (nrow_out > 0) {
+        for (int idx = threadIdx.x; idx < nrow_out * SW; idx += NT) {
+            const int j = idx / SW, c = idx - j * SW;
+            const int r = j < r_lo ? j : r_hi + (j - r_lo);
+            tile[r * SW + c] = tile[clampi(r, r_lo, r_hi - 1) * SW + clampi(c, c_lo, c_hi - 1)];
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // deterministic reductions
@@ -101,9 +206,9 @@ __device__ __forceinline__ float warp_max(float v)
     return v;
 }
 
-// block-level sum of NV doubles per thread -> out[0..NV) valid in thread 0..NV-1 via smem `red` (8*NV doubles)
+// block-level sum of NV doubles per thread -> red[0..NV) (valid for thread t < NV at red[t]); red: [8][NV] doubles
 template <int NV>
-__device__ __forceinline__ void block_sum(const double (&v)[NV], double* red /* [8][NV] */)
+__device__ __forceinline__ void block_sum(const double (&v)[NV], double* red)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -169,6 +274,23 @@ __device__ __forceinline__ void acc2_f16(float& a0, float& a1, float x, float y)
 __device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
 
 // ------------------------------------------------------------------------------------------------
+// exact divisions without the generic IEEE slow path (Markstein: q = RN(a*y), r = a - q*b exactly, RN(q + r*y)
+// is the correctly rounded a/b when y = RN(1/b)).  x/9: verified exhaustively against x/9.0f for every float
+// in [0, 2^24]; a/b: exact for a/b above ~2^-100 (the operands here are 0 or >= 2^-30).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float div9(float x)
+{
+    const float rc = 0x1.c71c72p-4f;  // RN(1/9)
+    const float q = __fmul_rn(x, rc);
+    return __fmaf_rn(__fmaf_rn(-q, 9.0f, x), rc, q);
+}
+__device__ __forceinline__ float div_by(float a, float b, float rb /* = __frcp_rn(b) */)
+{
+    const float q = __fmul_rn(a, rb);
+    return __fmaf_rn(__fmaf_rn(-q, b, a), rb, q);
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-pixel arithmetic, restated from the reference kernels in their own operation order
 // ------------------------------------------------------------------------------------------------
 // r0,r1,r2: the three window lines (l-1, l, l+1); element [j], [j+1], [j+2] are pixels p-1, p, p+1.
@@ -203,20 +325,22 @@ __device__ __forceinline__ float predict(const float (&c)[8], const float* r0, c
 template <bool TR>
 __device__ __forceinline__ float nvf_mask(const float* r0, const float* r1, const float* r2, int j)
 {
-    float s = 0.0f, q = 0.0f;
+    float s, q;
 #define WM_NVF_ACC(v) { const float t_ = (v); s = __fadd_rn(s, t_); q = __fmaf_rn(t_, t_, q); }
     if constexpr (!TR) {
-        WM_NVF_ACC(r0[j]) WM_NVF_ACC(r0[j + 1]) WM_NVF_ACC(r0[j + 2])
+        s = r0[j]; q = __fmul_rn(s, s);
+        WM_NVF_ACC(r0[j + 1]) WM_NVF_ACC(r0[j + 2])
         WM_NVF_ACC(r1[j]) WM_NVF_ACC(r1[j + 1]) WM_NVF_ACC(r1[j + 2])
         WM_NVF_ACC(r2[j]) WM_NVF_ACC(r2[j + 1]) WM_NVF_ACC(r2[j + 2])
     } else {
-        WM_NVF_ACC(r0[j]) WM_NVF_ACC(r1[j]) WM_NVF_ACC(r2[j])
+        s = r0[j]; q = __fmul_rn(s, s);
+        WM_NVF_ACC(r1[j]) WM_NVF_ACC(r2[j])
         WM_NVF_ACC(r0[j + 1]) WM_NVF_ACC(r1[j + 1]) WM_NVF_ACC(r2[j + 1])
         WM_NVF_ACC(r0[j + 2]) WM_NVF_ACC(r1[j + 2]) WM_NVF_ACC(r2[j + 2])
     }
 #undef WM_NVF_ACC
-    const float mean = __fdiv_rn(s, 9.0f);
-    const float var = __fmaf_rn(-mean, mean, __fdiv_rn(q, 9.0f));
+    const float mean = div9(s);
+    const float var = __fmaf_rn(-mean, mean, div9(q));
     return __fdiv_rn(var, __fadd_rn(1.0f, var));
 }
 
@@ -235,10 +359,10 @@ __device__ __forceinline__ void load_win6(float (&w)[6], const float* line, int 
 //   rx[i]    = sum_{q in core} X(q) Xc(q -/+ o_i)      +  frame,         core = lines 1..L-2 x pixels 1..P-2
 // so a core pixel costs 13 products (lags (0,0..2), (1,-2..2), (2,-2..2)) instead of 44.  Identical products
 // round identically, so the fp16 rounding of kernels/me_p3.hpp commutes with the regrouping.
-// Blocks [0, nsweep) walk tiles (static round-robin => fixed summation order), blocks [nsweep, nsweep+nframe)
-// take the frame ring.  f32 accumulation is bounded to 8 px (exact for integer-valued pixels), then f64.
-// The last block to finish sums the per-block partials in fixed order, assembles the 8x8 system in the
-// reference's neighbour order and solves it in one warp (f64 LU, partial pivoting).
+// Blocks [0, nframe) take the frame ring, blocks [nframe, nframe+nsweep) walk tiles (static round-robin =>
+// fixed summation order).  f32 accumulation is bounded to 32 px per accumulator (exact for integer-valued
+// pixels: 32 * 65504 < 2^24), then f64.  The last block to finish sums the per-block partials in fixed order,
+// assembles the 8x8 system in the reference's neighbour order and solves it in one warp (f64 LU, partial pivoting).
 // ================================================================================================
 struct SweepArgs {
     const void* img;
@@ -337,74 +461,122 @@ __device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* sc, Scal
     }
 }
 
-template <typename PixT, bool FP16>
-__global__ void __launch_bounds__(NT, 2) k_sweep(const SweepArgs a)
+// the 13-lag products of one thread's 4 px x 4 lines; FULL = every pixel of the tile is a core pixel
+template <bool FP16, bool FULL>
+__device__ __forceinline__ void sweep_tile(const float* __restrict__ tile, int l0, int p0, int L, int P,
+                                           float (&e0)[NLAG], float (&e1)[NLAG])
 {
-    __shared__ __align__(16) float tile[(TL + 2) * SW];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float* base = tile + (4 * w) * SW + 4 * lane + 2;  // window col 0 = pixel (p0 + 4*lane) - 2
+    const int pb = p0 + 4 * lane;
+    bool vp[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) vp[j] = FULL || ((pb + j >= 1) && (pb + j <= P - 2));
+    float A[8], B[8], C[8];
+    auto loadrow = [](float (&r)[8], const float* s) {
+        const float2 x = *reinterpret_cast<const float2*>(s);
+        const float4 y = *reinterpret_cast<const float4*>(s + 2);
+        const float2 z = *reinterpret_cast<const float2*>(s + 6);
+        r[0] = x.x; r[1] = x.y; r[2] = y.x; r[3] = y.y; r[4] = y.z; r[5] = y.w; r[6] = z.x; r[7] = z.y;
+    };
+    loadrow(A, base);
+    loadrow(B, base + SW);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        loadrow(C, base + (r + 2) * SW);
+        const int l = l0 + 4 * w + r;
+        const bool vl = FULL || ((l >= 1) && (l <= L - 2));
+#pragma unroll
+        for (int jj = 0; jj < 4; jj += 2) {
+            const float x0 = (FULL || (vl && vp[jj])) ? A[jj + 2] : 0.0f;
+            const float x1 = (FULL || (vl && vp[jj + 1])) ? A[jj + 3] : 0.0f;
+            // lag (0, d): A; lag (1, d): B; lag (2, d): C
+#define WM_LAG(v, R, off)                                                                                           \
+    if constexpr (FP16) acc2_f16(e0[v], e1[v], __fmul_rn(x0, R[jj + 2 + (off)]), __fmul_rn(x1, R[jj + 3 + (off)])); \
+    else { e0[v] = __fmaf_rn(x0, R[jj + 2 + (off)], e0[v]); e1[v] = __fmaf_rn(x1, R[jj + 3 + (off)], e1[v]); }
+            WM_LAG(0, A, 0) WM_LAG(1, A, 1) WM_LAG(2, A, 2)
+            WM_LAG(3, B, -2) WM_LAG(4, B, -1) WM_LAG(5, B, 0) WM_LAG(6, B, 1) WM_LAG(7, B, 2)
+            WM_LAG(8, C, -2) WM_LAG(9, C, -1) WM_LAG(10, C, 0) WM_LAG(11, C, 1) WM_LAG(12, C, 2)
+#undef WM_LAG
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { A[i] = B[i]; B[i] = C[i]; }
+    }
+}
+
+template <typename PixT, bool FP16, bool TMA>
+__global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtensorMap tmI, const SweepArgs a)
+{
+    static_assert(!TMA || sizeof(PixT) == 4, "TMA path is f32 only");
+    extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * NFRM];
+    __shared__ __align__(8) uint64_t bars[SWEEP_NST];
     const int b = blockIdx.y;
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     const int L = a.L, P = a.P;
     double* part = a.part + (size_t)b * ((size_t)a.nsweep * NLAG + (size_t)a.nframe * NFRM);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
-    if ((int)blockIdx.x < a.nsweep) {
+    if ((int)blockIdx.x >= a.nframe) {
+        const int sb = blockIdx.x - a.nframe, step = a.nsweep;
+        constexpr int NST = TMA ? SWEEP_NST : 1;
+        auto stage = [&](int s) { return reinterpret_cast<float*>(dsm + (size_t)s * SWEEP_STAGE); };
+        auto issue = [&](int t, int s) {  // thread 0 only
+            const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+            mbar_expect_tx(&bars[s], (TL + 2) * SW * 4);
+            tma_load_3d(stage(s), &tmI, tp * TP - HP, tl * TL, b, &bars[s]);
+        };
+        if constexpr (TMA) {
+            if (threadIdx.x == 0) {
+                for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
+                fence_barrier_init();
+            }
+            __syncthreads();
+            if (threadIdx.x == 0)
+                for (int s = 0; s < NST - 1; s++)
+                    if (sb + s * step < a.ntiles) issue(sb + s * step, s);
+        }
         double dacc[NLAG];
+        float e0[NLAG], e1[NLAG];  // even / odd pixel accumulators
 #pragma unroll
-        for (int v = 0; v < NLAG; v++) dacc[v] = 0.0;
-        for (int t = blockIdx.x; t < a.ntiles; t += a.nsweep) {
+        for (int v = 0; v < NLAG; v++) { dacc[v] = 0.0; e0[v] = 0.0f; e1[v] = 0.0f; }
+        int k = 0;
+        for (int t = sb; t < a.ntiles; t += step, k++) {
             const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
             const int l0 = tl * TL, p0 = tp * TP;
-            __syncthreads();
-            load_tile<PixT, TL + 2>(tile, img, a.ld, L, P, l0, p0 - HP, a.vec_ok != 0);
-            __syncthreads();
-            float e0[NLAG], e1[NLAG];  // even / odd pixel accumulators
-#pragma unroll
-            for (int v = 0; v < NLAG; v++) { e0[v] = 0.0f; e1[v] = 0.0f; }
-            const float* base = tile + (4 * w) * SW + 4 * lane + 2;  // window col 0 = pixel (p0+4*lane) - 2
-            const int pb = p0 + 4 * lane;
-            bool vp[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) vp[j] = (pb + j >= 1) && (pb + j <= P - 2);
-            float A[8], B[8], C[8];
-            auto loadrow = [](float (&r)[8], const float* s) {
-                const float2 x = *reinterpret_cast<const float2*>(s);
-                const float4 y = *reinterpret_cast<const float4*>(s + 2);
-                const float2 z = *reinterpret_cast<const float2*>(s + 6);
-                r[0] = x.x; r[1] = x.y; r[2] = y.x; r[3] = y.y; r[4] = y.z; r[5] = y.w; r[6] = z.x; r[7] = z.y;
-            };
-            loadrow(A, base);
-            loadrow(B, base + SW);
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                loadrow(C, base + (r + 2) * SW);
-                const int l = l0 + 4 * w + r;
-                const bool vl = (l >= 1) && (l <= L - 2);
-#pragma unroll
-                for (int jj = 0; jj < 4; jj += 2) {
-                    const float x0 = (vl && vp[jj]) ? A[jj + 2] : 0.0f;
-                    const float x1 = (vl && vp[jj + 1]) ? A[jj + 3] : 0.0f;
-                    // lag (0, d): A; lag (1, d): B; lag (2, d): C
-#define WM_LAG(v, R, off)                                                                               \
-    if constexpr (FP16) acc2_f16(e0[v], e1[v], __fmul_rn(x0, R[jj + 2 + (off)]), __fmul_rn(x1, R[jj + 3 + (off)])); \
-    else { e0[v] = __fmaf_rn(x0, R[jj + 2 + (off)], e0[v]); e1[v] = __fmaf_rn(x1, R[jj + 3 + (off)], e1[v]); }
-                    WM_LAG(0, A, 0) WM_LAG(1, A, 1) WM_LAG(2, A, 2)
-                    WM_LAG(3, B, -2) WM_LAG(4, B, -1) WM_LAG(5, B, 0) WM_LAG(6, B, 1) WM_LAG(7, B, 2)
-                    WM_LAG(8, C, -2) WM_LAG(9, C, -1) WM_LAG(10, C, 0) WM_LAG(11, C, 1) WM_LAG(12, C, 2)
-#undef WM_LAG
+            const float* tile;
+            if constexpr (TMA) {
+                if (threadIdx.x == 0) {
+                    const int tn = t + (NST - 1) * step;
+                    if (tn < a.ntiles) { fence_proxy_async(); issue(tn, (k + NST - 1) % NST); }
                 }
-#pragma unroll
-                for (int i = 0; i < 8; i++) { A[i] = B[i]; B[i] = C[i]; }
+                mbar_wait(&bars[k % NST], (k / NST) & 1);
+                float* tw = stage(k % NST);
+                if (tile_on_frame<TL + 2>(l0, p0 - HP, L, P)) { fix_border<TL + 2>(tw, l0, p0 - HP, L, P); __syncthreads(); }
+                tile = tw;
+            } else {
+                __syncthreads();
+                load_tile<PixT, TL + 2>(stage(0), img, a.ld, L, P, l0, p0 - HP, a.vec_ok != 0);
+                __syncthreads();
+                tile = stage(0);
             }
+            const bool full = l0 >= 1 && l0 + TL <= L - 1 && p0 >= 1 && p0 + TP <= P - 1;
+            if (full) sweep_tile<FP16, true>(tile, l0, p0, L, P, e0, e1);
+            else sweep_tile<FP16, false>(tile, l0, p0, L, P, e0, e1);
+            if ((k & 3) == 3) {
 #pragma unroll
-            for (int v = 0; v < NLAG; v++) dacc[v] += (double)e0[v] + (double)e1[v];
+                for (int v = 0; v < NLAG; v++) { dacc[v] += (double)__fadd_rn(e0[v], e1[v]); e0[v] = 0.0f; e1[v] = 0.0f; }
+            }
+            if constexpr (TMA) __syncthreads();  // stage k % NST may be refilled from the next iteration on
         }
+#pragma unroll
+        for (int v = 0; v < NLAG; v++) dacc[v] += (double)__fadd_rn(e0[v], e1[v]);
         __syncthreads();
         block_sum<NLAG>(dacc, red);
-        if (threadIdx.x < NLAG) part[(size_t)blockIdx.x * NLAG + threadIdx.x] = red[threadIdx.x];
+        if (threadIdx.x < NLAG) part[(size_t)sb * NLAG + threadIdx.x] = red[threadIdx.x];
     } else {
         // ---- frame ring: pixels within 2 of the border, naive products guarded by "partner not in core" ----
-        const int fb = blockIdx.x - a.nsweep;
+        const int fb = blockIdx.x;
         const int ntop = min(2, L), lbot = max(2, L - 2), nbot = L - lbot > 0 ? L - lbot : 0;
         const int nmid = max(0, L - 4);
         const int ncl = min(2, P), pright = max(2, P - 2), ncr = P - pright > 0 ? P - pright : 0;
@@ -465,32 +637,117 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const SweepArgs a)
 }
 
 // ================================================================================================
-// k_stats: pass 1 of makeWatermark.  MASK = WM_MASK_ME: e = I - pred (Watermark.cpp:210), accumulates
-// sum (|e| W)^2 and max|e| (the max cancels out of a.mask.W — SURVEY.md §0 — so no separate max pass);
-// MASK = WM_MASK_NVF: sum (nvf W)^2.  Last block: a = strength / (||mask.W|| / sqrt(N)) (Watermark.cpp:170).
+// k_stats / k_apply share one stage layout: image tile (1-pixel halo) + W tile
 // ================================================================================================
-struct StatsArgs {
+struct EmbedArgs {
     const void* img;
     long long ld, bstride;
     const float* W;  // dense L x P in the image's layout
     int L, P, tiles_p, ntiles;
     int vec_ok, w_vec_ok;
     float strength;
-    double* part;       // [batch][gridDim.x][2]
-    unsigned* counter;  // [batch]
+    double* part;       // [batch][gridDim.x][2]       (stats)
+    unsigned* counter;  // [batch]                     (stats)
     Scal* scal;
     ScalDbg* dbg;
+    // apply only
+    const void* base;   // PixT, channels planes
+    long long base_ld, base_bstride, base_pstride;
+    void* out;          // OutT
+    long long out_ld, out_bstride, out_pstride;
+    int channels, same_base, base_vec_ok, out_vec_ok;
 };
 
-template <typename PixT, int MASK, bool TR>
-__global__ void __launch_bounds__(NT, 3) k_stats(const StatsArgs a)
+// persistent tile loop shared by k_stats and k_apply: calls body(tile, wtile, l0, p0) once per tile
+template <typename PixT, bool TMA, typename Body>
+__device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CUtensorMap* tmW, const EmbedArgs& a,
+                                                unsigned char* dsm, uint64_t* bars, Body body)
 {
-    __shared__ __align__(16) float tile[(TL + 2) * SW];
+    constexpr int NST = TMA ? EMBED_NST : 1;
+    const int b = blockIdx.y, step = gridDim.x;
+    const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
+    auto stage = [&](int s) { return reinterpret_cast<float*>(dsm + (size_t)s * EMBED_STAGE); };
+    auto issue = [&](int t, int s) {  // thread 0 only
+        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+        mbar_expect_tx(&bars[s], (TL + 2) * SW * 4 + SZ_WT);
+        tma_load_3d(stage(s), tmI, tp * TP - HP, tl * TL - 1, b, &bars[s]);
+        tma_load_3d(reinterpret_cast<unsigned char*>(stage(s)) + SZ_I34, tmW, tp * TP, tl * TL, 0, &bars[s]);
+    };
+    if constexpr (TMA) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int s = 0; s < NST - 1; s++)
+                if ((int)blockIdx.x + s * step < a.ntiles) issue(blockIdx.x + s * step, s);
+    }
+    int k = 0;
+    for (int t = blockIdx.x; t < a.ntiles; t += step, k++) {
+        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+        const int l0 = tl * TL, p0 = tp * TP;
+        float* tile;
+        if constexpr (TMA) {
+            if (threadIdx.x == 0) {
+                const int tn = t + (NST - 1) * step;
+                if (tn < a.ntiles) { fence_proxy_async(); issue(tn, (k + NST - 1) % NST); }
+            }
+            mbar_wait(&bars[k % NST], (k / NST) & 1);
+            tile = stage(k % NST);
+            if (tile_on_frame<TL + 2>(l0 - 1, p0 - HP, a.L, a.P)) { fix_border<TL + 2>(tile, l0 - 1, p0 - HP, a.L, a.P); __syncthreads(); }
+        } else {
+            tile = stage(0);
+            __syncthreads();
+            load_tile<PixT, TL + 2>(tile, img, a.ld, a.L, a.P, l0 - 1, p0 - HP, a.vec_ok != 0);
+            load_w_tile(tile + SZ_I34 / 4, a.W, a.L, a.P, l0, p0, a.w_vec_ok != 0);
+            __syncthreads();
+        }
+        body(tile, tile + SZ_I34 / 4, l0, p0);
+        if constexpr (TMA) __syncthreads();
+    }
+}
+
+// mask.W for one thread's 4 px x 4 lines: calls f(r, m[4], u[4], centre[4]) per line
+template <int MASK, bool TR, typename F>
+__device__ __forceinline__ void mask_lines(const float* __restrict__ tile, const float* __restrict__ wt, const float (&c)[8], F f)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float* tb = tile + (4 * w) * SW;  // smem line of image line l-1 for r = 0
+    const int scol = 4 * lane + HP;
+    float r0[6], r1[6], r2[6];
+    load_win6(r0, tb, scol);
+    load_win6(r1, tb + SW, scol);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        load_win6(r2, tb + (r + 2) * SW, scol);
+        const float4 wv = *reinterpret_cast<const float4*>(wt + (4 * w + r) * TP + 4 * lane);
+        const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+        float m[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if constexpr (MASK == 0) m[j] = fabsf(__fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j)));
+            else m[j] = nvf_mask<TR>(r0, r1, r2, j);
+        }
+        f(r, m, wq, r1);
+#pragma unroll
+        for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
+    }
+}
+
+// ---- k_stats: MASK = ME: sum (|e| W)^2 and max|e| (the max cancels out of a.mask.W — SURVEY.md §0 — so no
+// separate max pass); MASK = NVF: sum (nvf W)^2.  Last block: a = strength / (||mask.W|| / sqrt(N)) (Watermark.cpp:170)
+template <typename PixT, int MASK, bool TR, bool TMA>
+__global__ void __launch_bounds__(NT, 2) k_stats(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
+                                                 const EmbedArgs a)
+{
+    static_assert(!TMA || sizeof(PixT) == 4, "TMA path is f32 only");
+    extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * 2];
+    __shared__ __align__(8) uint64_t bars[EMBED_NST];
     const int b = blockIdx.y;
     Scal* sc = a.scal + b;
     if (MASK == 0 && sc->status != 0) return;  // singular: a untouched, apply copies base through
-    const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     const int L = a.L, P = a.P;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float c[8];
@@ -498,63 +755,25 @@ __global__ void __launch_bounds__(NT, 3) k_stats(const StatsArgs a)
     for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
     double dsum = 0.0;
     float emax = 0.0f;
-    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
-        const int l0 = tl * TL, p0 = tp * TP;
+    embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&](const float* tile, const float* wt, int l0, int p0) {
         const int pb = p0 + 4 * lane;
-        // W for my 4 x 4 pixels straight from global (issued before the tile barrier)
-        float4 wv[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int l = l0 + 4 * w + r;
-            wv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (l < L && pb < P) {
-                const float* wr = a.W + (long long)l * P + pb;
-                if (a.w_vec_ok && pb + 3 < P) wv[r] = __ldg(reinterpret_cast<const float4*>(wr));
-                else {
-                    wv[r].x = wr[0];
-                    if (pb + 1 < P) wv[r].y = wr[1];
-                    if (pb + 2 < P) wv[r].z = wr[2];
-                    if (pb + 3 < P) wv[r].w = wr[3];
-                }
-            }
-        }
-        __syncthreads();
-        load_tile<PixT, TL + 2>(tile, img, a.ld, L, P, l0 - 1, p0 - HP, a.vec_ok != 0);
-        __syncthreads();
-        const float* base = tile + (4 * w) * SW;  // smem line of image line l-1 for r = 0
-        const int scol = 4 * lane + HP;
-        float r0[6], r1[6], r2[6];
-        load_win6(r0, base, scol);
-        load_win6(r1, base + SW, scol);
+        const bool full = l0 + TL <= L && p0 + TP <= P;
         float fs = 0.0f;
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            load_win6(r2, base + (r + 2) * SW, scol);
+        mask_lines<MASK, TR>(tile, wt, c, [&](int r, const float (&m)[4], const float (&wq)[4], const float (&)[6]) {
             const int l = l0 + 4 * w + r;
-            const float wq[4] = {wv[r].x, wv[r].y, wv[r].z, wv[r].w};
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                if (l < L && pb + j < P) {
-                    float m;
-                    if constexpr (MASK == 0) {
-                        m = fabsf(__fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j)));
-                        emax = fmaxf(emax, m);
-                    } else {
-                        m = nvf_mask<TR>(r0, r1, r2, j);
-                    }
-                    const float u = __fmul_rn(m, wq[j]);
+                if (full || (l < L && pb + j < P)) {
+                    if (MASK == 0) emax = fmaxf(emax, m[j]);
+                    const float u = __fmul_rn(m[j], wq[j]);
                     fs = __fmaf_rn(u, u, fs);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
-        }
+        });
         dsum += (double)fs;
-    }
-    const double v2[2] = {dsum, (double)emax};
+    });
     {   // block reduce: sum and max
-        const double s = warp_sum(v2[0]);
+        const double s = warp_sum(dsum);
         const float m = warp_max(emax);
         if (lane == 0) { red[w * 2] = s; red[w * 2 + 1] = (double)m; }
         __syncthreads();
@@ -583,36 +802,37 @@ __global__ void __launch_bounds__(NT, 3) k_stats(const StatsArgs a)
     }
 }
 
-// ================================================================================================
-// k_apply: pass 2 of makeWatermark — out = clamp(base + (mask.W).a, 0, 255) per channel (Watermark.cpp:169-171);
-// u8 output truncates like `.as(u8)` (main.cpp:356,380).  status != 0 copies base through unchanged.
-// ================================================================================================
-struct ApplyArgs {
-    const void* img;
-    long long ld, bstride;
-    const float* W;
-    const void* base;   // PixT, channels planes
-    long long base_ld, base_bstride, base_pstride;
-    void* out;          // OutT
-    long long out_ld, out_bstride, out_pstride;
-    int channels, same_base;
-    int L, P, tiles_p, ntiles;
-    int vec_ok, w_vec_ok, base_vec_ok, out_vec_ok;
-    const Scal* scal;
-};
-
+// ---- k_apply: out = clamp(base + (mask.W).a, 0, 255) per channel (Watermark.cpp:169-171); u8 output truncates like
+// `.as(u8)` (main.cpp:356,380).  status != 0 copies base through unchanged (k_copy_base).
 template <typename T> __device__ __forceinline__ T to_out(float v);
 template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ uint8_t to_out<uint8_t>(float v) { return (uint8_t)v; }  // truncation
 
-template <typename PixT, typename OutT, int MASK, bool TR>
-__global__ void __launch_bounds__(NT, 3) k_apply(const ApplyArgs a)
+template <typename PixT, typename OutT>
+__device__ __forceinline__ void copy_base_through(const EmbedArgs& a)
 {
-    __shared__ __align__(16) float tile[(TL + 2) * SW];
+    const int b = blockIdx.y;
+    const PixT* bas = reinterpret_cast<const PixT*>(a.base) + (long long)b * a.base_bstride;
+    OutT* out = reinterpret_cast<OutT*>(a.out) + (long long)b * a.out_bstride;
+    const long long n = (long long)a.L * a.P;
+    for (int ch = 0; ch < a.channels; ch++)
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+            const int l = (int)(i / a.P), p = (int)(i - (long long)l * a.P);
+            out[(long long)ch * a.out_pstride + (long long)l * a.out_ld + p] =
+                to_out<OutT>((float)bas[(long long)ch * a.base_pstride + (long long)l * a.base_ld + p]);
+        }
+}
+
+template <typename PixT, typename OutT, int MASK, bool TR, bool TMA>
+__global__ void __launch_bounds__(NT, 2) k_apply(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
+                                                 const EmbedArgs a)
+{
+    static_assert(!TMA || sizeof(PixT) == 4, "TMA path is f32 only");
+    extern __shared__ __align__(128) unsigned char dsm[];
+    __shared__ __align__(8) uint64_t bars[EMBED_NST];
     const int b = blockIdx.y;
     const Scal* sc = a.scal + b;
-    const int status = sc->status;
-    const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
+    if (sc->status != 0) { copy_base_through<PixT, OutT>(a); return; }
     const PixT* bas = reinterpret_cast<const PixT*>(a.base) + (long long)b * a.base_bstride;
     OutT* out = reinterpret_cast<OutT*>(a.out) + (long long)b * a.out_bstride;
     const int L = a.L, P = a.P;
@@ -621,95 +841,56 @@ __global__ void __launch_bounds__(NT, 3) k_apply(const ApplyArgs a)
 #pragma unroll
     for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
     const float av = sc->a, mx = sc->emax;
-    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
-        const int l0 = tl * TL, p0 = tp * TP;
+    const float rmx = MASK == 0 ? __frcp_rn(mx) : 0.0f;
+    embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&](const float* tile, const float* wt, int l0, int p0) {
         const int pb = p0 + 4 * lane;
-        float4 wv[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
+        const bool full = l0 + TL <= L && p0 + TP <= P;
+        mask_lines<MASK, TR>(tile, wt, c, [&](int r, const float (&m)[4], const float (&wq)[4], const float (&r1)[6]) {
             const int l = l0 + 4 * w + r;
-            wv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (status == 0 && l < L && pb < P) {
-                const float* wr = a.W + (long long)l * P + pb;
-                if (a.w_vec_ok && pb + 3 < P) wv[r] = __ldg(reinterpret_cast<const float4*>(wr));
-                else {
-                    wv[r].x = wr[0];
-                    if (pb + 1 < P) wv[r].y = wr[1];
-                    if (pb + 2 < P) wv[r].z = wr[2];
-                    if (pb + 3 < P) wv[r].w = wr[3];
+            if (!(full || (l < L && pb < P))) return;
+            float au[4];  // u = mask * W (Watermark.cpp:169), mask = |e| / max|e| (Watermark.cpp:214)
+#pragma unroll
+            for (int j = 0; j < 4; j++) au[j] = __fmul_rn(MASK == 0 ? div_by(m[j], mx, rmx) : m[j], wq[j]);
+            for (int ch = 0; ch < a.channels; ch++) {
+                float bv[4];
+                if (a.same_base) {
+                    bv[0] = r1[1]; bv[1] = r1[2]; bv[2] = r1[3]; bv[3] = r1[4];
+                } else {
+                    const PixT* br = bas + (long long)ch * a.base_pstride + (long long)l * a.base_ld + pb;
+                    if (a.base_vec_ok && (full || pb + 3 < P)) {
+                        if constexpr (sizeof(PixT) == 4) {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(br));
+                            bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+                        } else {
+                            const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(br));
+                            bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) bv[j] = (pb + j < P) ? (float)br[j] : 0.0f;
+                    }
                 }
-            }
-        }
-        __syncthreads();
-        if (status == 0) load_tile<PixT, TL + 2>(tile, img, a.ld, L, P, l0 - 1, p0 - HP, a.vec_ok != 0);
-        __syncthreads();
-        const float* tb = tile + (4 * w) * SW;
-        const int scol = 4 * lane + HP;
-        float r0[6], r1[6], r2[6];
-        if (status == 0) { load_win6(r0, tb, scol); load_win6(r1, tb + SW, scol); }
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int l = l0 + 4 * w + r;
-            float au[4] = {0.f, 0.f, 0.f, 0.f};  // u = mask*W per pixel
-            if (status == 0) {
-                load_win6(r2, tb + (r + 2) * SW, scol);
-                const float wq[4] = {wv[r].x, wv[r].y, wv[r].z, wv[r].w};
+                float ov[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    float m;
-                    if constexpr (MASK == 0) m = __fdiv_rn(fabsf(__fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j))), mx);
-                    else m = nvf_mask<TR>(r0, r1, r2, j);
-                    au[j] = __fmul_rn(m, wq[j]);
+                    const float v = __fmaf_rn(au[j], av, bv[j]);
+                    ov[j] = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);  // af::clamp(., 0, 255)
+                }
+                OutT* orow = out + (long long)ch * a.out_pstride + (long long)l * a.out_ld + pb;
+                if (a.out_vec_ok && (full || pb + 3 < P)) {
+                    if constexpr (sizeof(OutT) == 4) {
+                        *reinterpret_cast<float4*>(orow) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                    } else {
+                        *reinterpret_cast<uchar4*>(orow) =
+                            make_uchar4(to_out<uint8_t>(ov[0]), to_out<uint8_t>(ov[1]), to_out<uint8_t>(ov[2]), to_out<uint8_t>(ov[3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (pb + j < P) orow[j] = to_out<OutT>(ov[j]);
                 }
             }
-            if (l < L && pb < P) {
-                for (int ch = 0; ch < a.channels; ch++) {
-                    float bv[4];
-                    if (a.same_base && status == 0) {
-                        bv[0] = r1[1]; bv[1] = r1[2]; bv[2] = r1[3]; bv[3] = r1[4];
-                    } else {
-                        const PixT* br = bas + (long long)ch * a.base_pstride + (long long)l * a.base_ld + pb;
-                        if (a.base_vec_ok && pb + 3 < P) {
-                            if constexpr (sizeof(PixT) == 4) {
-                                const float4 v = __ldg(reinterpret_cast<const float4*>(br));
-                                bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
-                            } else {
-                                const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(br));
-                                bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; j++) bv[j] = (pb + j < P) ? (float)br[j] : 0.0f;
-                        }
-                    }
-                    float ov[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        float v = status == 0 ? __fmaf_rn(au[j], av, bv[j]) : bv[j];
-                        if (status == 0) v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);
-                        ov[j] = v;
-                    }
-                    OutT* orow = out + (long long)ch * a.out_pstride + (long long)l * a.out_ld + pb;
-                    if (a.out_vec_ok && pb + 3 < P) {
-                        if constexpr (sizeof(OutT) == 4) {
-                            *reinterpret_cast<float4*>(orow) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-                        } else {
-                            *reinterpret_cast<uchar4*>(orow) =
-                                make_uchar4(to_out<uint8_t>(ov[0]), to_out<uint8_t>(ov[1]), to_out<uint8_t>(ov[2]), to_out<uint8_t>(ov[3]));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) if (pb + j < P) orow[j] = to_out<OutT>(ov[j]);
-                    }
-                }
-            }
-            if (status == 0) {
-#pragma unroll
-                for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
-            }
-        }
-    }
+        });
+    });
 }
 
 // ================================================================================================
@@ -731,34 +912,68 @@ struct DetectArgs {
     Scal* scal;
     ScalDbg* dbg;
 };
-constexpr int DET_SMEM = ((TL + 4) + 2 * (TL + 2)) * SW * 4;  // Z, W, u tiles
 
-template <typename PixT, int MASK, bool TR>
-__global__ void __launch_bounds__(NT, 2) k_detect(const DetectArgs a)
+template <typename PixT, int MASK, bool TR, bool TMA>
+__global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW,
+                                                  const DetectArgs a)
 {
-    extern __shared__ __align__(16) float smem[];
-    float* zt = smem;                       // (TL+4) x SW : lines l0-2 .. l0+TL+1
-    float* wt = zt + (TL + 4) * SW;         // (TL+2) x SW : lines l0-1 .. l0+TL
-    float* ut = wt + (TL + 2) * SW;         // (TL+2) x SW : same frame as wt
+    static_assert(!TMA || sizeof(PixT) == 4, "TMA path is f32 only");
+    extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * 3];
+    __shared__ __align__(8) uint64_t bars[DETECT_NST];
+    constexpr int NST = TMA ? DETECT_NST : 1;
+    float* ut = reinterpret_cast<float*>(dsm + (size_t)NST * DETECT_STAGE);  // (TL+2) x SW, lines l0-1 .. l0+TL
     const int b = blockIdx.y;
     Scal* sc = a.scal + b;
     if (sc->status != 0) return;  // singular: corr = 0 was written by the sweep
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     const int L = a.L, P = a.P;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, step = gridDim.x;
     float c[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) c[k] = sc->coef[k];
+    auto stage = [&](int s) { return reinterpret_cast<float*>(dsm + (size_t)s * DETECT_STAGE); };
+    auto issue = [&](int t, int s) {  // thread 0 only
+        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+        mbar_expect_tx(&bars[s], (TL + 4) * SW * 4 + (TL + 2) * SW * 4);
+        tma_load_3d(stage(s), &tmZ, tp * TP - HP, tl * TL - 2, b, &bars[s]);
+        tma_load_3d(reinterpret_cast<unsigned char*>(stage(s)) + SZ_I36, &tmW, tp * TP - HP, tl * TL - 1, 0, &bars[s]);
+    };
+    if constexpr (TMA) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int s = 0; s < NST - 1; s++)
+                if ((int)blockIdx.x + s * step < a.ntiles) issue(blockIdx.x + s * step, s);
+    }
     double ddot = 0.0, dnz = 0.0, dnu = 0.0;
-    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+    int k = 0;
+    for (int t = blockIdx.x; t < a.ntiles; t += step, k++) {
         const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
         const int l0 = tl * TL, p0 = tp * TP;
         const int pb = p0 + 4 * lane;
-        __syncthreads();
-        load_tile<PixT, TL + 4>(zt, img, a.ld, L, P, l0 - 2, p0 - HP, a.vec_ok != 0);
-        load_tile<float, TL + 2>(wt, a.W, P, L, P, l0 - 1, p0 - HP, a.w_vec_ok != 0);
-        __syncthreads();
+        float *zt, *wt;  // zt: (TL+4) x SW lines l0-2 ..; wt: (TL+2) x SW lines l0-1 ..
+        if constexpr (TMA) {
+            if (threadIdx.x == 0) {
+                const int tn = t + (NST - 1) * step;
+                if (tn < a.ntiles) { fence_proxy_async(); issue(tn, (k + NST - 1) % NST); }
+            }
+            mbar_wait(&bars[k % NST], (k / NST) & 1);
+            zt = stage(k % NST);
+            wt = zt + SZ_I36 / 4;
+            if (tile_on_frame<TL + 4>(l0 - 2, p0 - HP, L, P)) { fix_border<TL + 4>(zt, l0 - 2, p0 - HP, L, P); __syncthreads(); }
+        } else {
+            zt = stage(0);
+            wt = zt + SZ_I36 / 4;
+            __syncthreads();
+            load_tile<PixT, TL + 4>(zt, img, a.ld, L, P, l0 - 2, p0 - HP, a.vec_ok != 0);
+            load_tile<float, TL + 2>(wt, a.W, P, L, P, l0 - 1, p0 - HP, a.w_vec_ok != 0);
+            __syncthreads();
+        }
+        const bool full = l0 + TL <= L && p0 + TP <= P;
         const int scol = 4 * lane + HP;
         float ez[4][4];
         // ---- phase 1a: my 4 x 4 pixels ----
@@ -806,7 +1021,7 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const DetectArgs a)
             }
         }
         __syncthreads();
-        // ---- border tiles: replicate u into ring cells outside the image (sources are in-image cells) ----
+        // ---- tiles on the image frame: replicate u into cells outside the image (sources are in-image cells) ----
         if (l0 == 0 || p0 == 0 || l0 + TL >= L || p0 + TP >= P) {
             for (int idx = threadIdx.x; idx < (TL + 2) * (TP + 2); idx += NT) {
                 const int rl = idx / (TP + 2) - 1, rp = idx - (rl + 1) * (TP + 2) - 1;
@@ -831,7 +1046,7 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const DetectArgs a)
                 const int l = l0 + 4 * w + r;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    if (l < L && pb + j < P) {
+                    if (full || (l < L && pb + j < P)) {
                         const float eu = __fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j));
                         const float e = ez[r][j];
                         fd = __fmaf_rn(eu, e, fd);
@@ -844,6 +1059,7 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const DetectArgs a)
             }
             ddot += (double)fd; dnz += (double)fz; dnu += (double)fu;
         }
+        if constexpr (TMA) __syncthreads();  // ut and the stage are rewritten from the next iteration on
     }
     __syncthreads();
     const double v3[3] = {ddot, dnz, dnu};
@@ -923,16 +1139,6 @@ __global__ void k_transpose(const float* __restrict__ src, float* __restrict__ d
     const int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
     for (int i = threadIdx.y; i < 32; i += 8)
         if (c0 + i < cols && r < rows) dst[(long long)(c0 + i) * rows + r] = t[threadIdx.x][i];
-}
-
-// strided u8 plane -> contiguous (main.cpp:348-353 repack), or plain copy-through of gated-off frames
-__global__ void k_repack_u8(const uint8_t* __restrict__ src, long long src_ld, uint8_t* __restrict__ dst, int H, int Wd)
-{
-    const long long n = (long long)H * Wd;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / Wd), c = (int)(i - (long long)r * Wd);
-        dst[i] = src[(long long)r * src_ld + c];
-    }
 }
 
 }  // namespace wm
