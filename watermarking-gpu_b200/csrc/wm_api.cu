@@ -143,7 +143,8 @@ int ensure_slot(wm_ctx* ctx, Slot& s, int batch, int gx_max, int nsweep, int nfr
         CU(cudaMallocHost(&s.scal_host, sizeof(Scal) * batch));
         s.batch_cap = batch;
     }
-    const size_t need = (size_t)batch * ((size_t)nsweep * NLAG + (size_t)nframe * NFRM + (size_t)gx_max * 3);
+    const size_t need = (size_t)batch * ((size_t)nsweep * NTOT + (size_t)gx_max * 3);
+    (void)nframe;
     if (need > s.part_cap) {
         if (s.part) cudaFree(s.part);
         s.part = nullptr;
@@ -194,20 +195,17 @@ Geo geo(int L, int P)
 }
 
 struct Plan { int nsweep, nframe, gx_stats, gx_detect; };
+// Grids are sized so that every launch is at most ONE wave of 2 resident CTAs per SM (persistent tile loops):
+// a partial second wave would leave most SMs idle for a whole tile-loop's duration.
 Plan plan(const wm_ctx* ctx, const Geo& g, int batch)
 {
     Plan p;
-    const long long ring = 4LL * (g.L + g.P);
-    if (batch == 1) {
-        p.nsweep = std::min(g.ntiles, 2 * ctx->sms);
-        p.gx_stats = std::min(g.ntiles, 2 * ctx->sms);
-        p.gx_detect = std::min(g.ntiles, 2 * ctx->sms);
-        p.nframe = (int)std::min<long long>(64, std::max<long long>(1, (ring + NT * 8 - 1) / (NT * 8)));
-    } else {
-        const int per = std::max(1, std::min(g.ntiles, (4 * ctx->sms + batch - 1) / batch));
-        p.nsweep = p.gx_stats = p.gx_detect = per;
-        p.nframe = (int)std::min<long long>(64, std::max<long long>(1, (ring + NT * 16 - 1) / (NT * 16)));
-    }
+    const int cap = 2 * ctx->sms;              // resident CTAs per launch
+    const int per = std::max(1, cap / batch);  // CTAs per image
+    p.nframe = 0;                              // the frame ring is shared by the sweep blocks
+    p.nsweep = std::max(1, std::min(g.ntiles, per));
+    p.gx_stats = p.nsweep;
+    p.gx_detect = p.nsweep;
     return p;
 }
 
@@ -317,11 +315,17 @@ void launch_stats(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_
     else launch_stats_t<uint8_t, false>(mask, tr, grid, st, tmI, tmW, a);
 }
 
+template <typename PixT, typename OutT, bool TMA, bool SB>
+void launch_apply_s(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
+{
+    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 0, true, TMA, SB>), embed_smem(TMA), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 0, false, TMA, SB>), embed_smem(TMA), tmI, tmW, a); }
+    else { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 1, true, TMA, SB>), embed_smem(TMA), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 1, false, TMA, SB>), embed_smem(TMA), tmI, tmW, a); }
+}
 template <typename PixT, typename OutT, bool TMA>
 void launch_apply_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
 {
-    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 0, true, TMA>), embed_smem(TMA), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 0, false, TMA>), embed_smem(TMA), tmI, tmW, a); }
-    else { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 1, true, TMA>), embed_smem(TMA), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 1, false, TMA>), embed_smem(TMA), tmI, tmW, a); }
+    if (a.same_base) launch_apply_s<PixT, OutT, TMA, true>(mask, tr, grid, st, tmI, tmW, a);
+    else launch_apply_s<PixT, OutT, TMA, false>(mask, tr, grid, st, tmI, tmW, a);
 }
 void launch_apply(int in_dtype, int out_dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI,
                   const CUtensorMap& tmW, const EmbedArgs& a)
@@ -380,7 +384,7 @@ int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int ba
     return WM_OK;
 }
 
-size_t stats_part_offset(const Plan& pl, int batch) { return (size_t)batch * ((size_t)pl.nsweep * NLAG + (size_t)pl.nframe * NFRM); }
+size_t stats_part_offset(const Plan& pl, int batch) { return (size_t)batch * (size_t)pl.nsweep * NTOT; }
 
 int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm_image* out, int64_t in_stride,
              int64_t base_stride, int64_t out_stride, int batch, int mask)

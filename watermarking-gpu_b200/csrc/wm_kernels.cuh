@@ -170,22 +170,23 @@ __device__ __forceinline__ bool tile_on_frame(int l_org, int p_org, int L, int P
 template <int NROWS>
 __device__ __forceinline__ void fix_border(float* tile, int l_org, int p_org, int L, int P)
 {
+    // Only cells within 2 of the image are ever read by a valid pixel's window, so at most 2 lines above, 2 below,
+    // 2 columns left and 2 right are patched; every source is an in-image cell of this tile.
     const int r_lo = max(0, -l_org), r_hi = min(NROWS, L - l_org);  // in-image rows [r_lo, r_hi)
     const int c_lo = max(0, -p_org), c_hi = min(SW, P - p_org);     // in-image cols [c_lo, c_hi)
-    const int ncol_out = c_lo + (SW - c_hi);
-    if (ncol_out > 0) {
-        for (int idx = threadIdx.x; idx < (r_hi - r_lo) * ncol_out; idx += NT) {
-            const int rr = idx / ncol_out, j = idx - rr * ncol_out;
-            const int r = r_lo + rr, c = j < c_lo ? j : c_hi + (j - c_lo);
-            tile[r * SW + c] = tile[r * SW + clampi(c, c_lo, c_hi - 1)];
-        }
-    }
-    const int nrow_out = r_lo + (NROWS - r_hi);
-    if (nrow_out > 0) {
-        for (int idx = threadIdx.x; idx < nrow_out * SW; idx += NT) {
-            const int j = idx / SW, c = idx - j * SW;
-            const int r = j < r_lo ? j : r_hi + (j - r_lo);
+    const int ra = max(0, r_lo - 2), rb = min(NROWS, r_hi + 2);     // rows that matter [ra, rb)
+    for (int idx = threadIdx.x; idx < 4 * SW; idx += NT) {          // out-of-image rows (up to 4), all columns
+        const int j = idx / SW, c = idx - j * SW;
+        const int r = j < 2 ? r_lo - 1 - j : r_hi + (j - 2);
+        if (r >= ra && r < rb && (r < r_lo || r >= r_hi))
             tile[r * SW + c] = tile[clampi(r, r_lo, r_hi - 1) * SW + clampi(c, c_lo, c_hi - 1)];
+    }
+    if (c_lo > 0 || c_hi < SW) {
+        for (int idx = threadIdx.x; idx < 4 * NROWS; idx += NT) {   // in-image rows, out-of-image columns (up to 4)
+            const int r = idx >> 2, j = idx & 3;
+            const int c = j < 2 ? c_lo - 1 - j : c_hi + (j - 2);
+            if (r >= r_lo && r < r_hi && c >= 0 && c < SW && (c < c_lo || c >= c_hi))
+                tile[r * SW + c] = tile[r * SW + clampi(c, c_lo, c_hi - 1)];
         }
     }
 }
@@ -289,6 +290,19 @@ __device__ __forceinline__ float div_by(float a, float b, float rb /* = __frcp_r
     const float q = __fmul_rn(a, rb);
     return __fmaf_rn(__fmaf_rn(-q, b, a), rb, q);
 }
+// n/d for d in [0.9, 2^17], |n| <= d: the fast path of div.rn.f32 (reciprocal refined once, quotient refined twice)
+// without its range check and slow-path branch, which these operand ranges never take (checked on the host
+// against IEEE division over 1.5e9 operands of this range with the reciprocal seed perturbed by +-2 ulp).
+__device__ __forceinline__ float div_safe(float n, float d)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
+    y = __fmaf_rn(__fmaf_rn(-d, y, 1.0f), y, y);
+    y = __fmaf_rn(__fmaf_rn(-d, y, 1.0f), y, y);  // second refinement: exact even for a 2-ulp rcp.approx (host-verified)
+    float q = __fmul_rn(n, y);
+    q = __fmaf_rn(__fmaf_rn(-d, q, n), y, q);
+    return __fmaf_rn(__fmaf_rn(-d, q, n), y, q);
+}
 
 // ------------------------------------------------------------------------------------------------
 // per-pixel arithmetic, restated from the reference kernels in their own operation order
@@ -341,7 +355,7 @@ __device__ __forceinline__ float nvf_mask(const float* r0, const float* r1, cons
 #undef WM_NVF_ACC
     const float mean = div9(s);
     const float var = __fmaf_rn(-mean, mean, div9(q));
-    return __fdiv_rn(var, __fadd_rn(1.0f, var));
+    return div_safe(var, __fadd_rn(1.0f, var));
 }
 
 // 6-float window (pixels p-1 .. p+4 of one smem line) for a thread's 4 pixels; sc = smem column of pixel 0
@@ -359,8 +373,7 @@ __device__ __forceinline__ void load_win6(float (&w)[6], const float* line, int 
 //   rx[i]    = sum_{q in core} X(q) Xc(q -/+ o_i)      +  frame,         core = lines 1..L-2 x pixels 1..P-2
 // so a core pixel costs 13 products (lags (0,0..2), (1,-2..2), (2,-2..2)) instead of 44.  Identical products
 // round identically, so the fp16 rounding of kernels/me_p3.hpp commutes with the regrouping.
-// Blocks [0, nframe) take the frame ring, blocks [nframe, nframe+nsweep) walk tiles (static round-robin =>
-// fixed summation order).  f32 accumulation is bounded to 32 px per accumulator (exact for integer-valued
+// Every block walks its tiles (static round-robin => fixed summation order) and then a slice of the frame ring.  f32 accumulation is bounded to 32 px per accumulator (exact for integer-valued
 // pixels: 32 * 65504 < 2^24), then f64.  The last block to finish sums the per-block partials in fixed order,
 // assembles the 8x8 system in the reference's neighbour order and solves it in one warp (f64 LU, partial pivoting).
 // ================================================================================================
@@ -368,9 +381,9 @@ struct SweepArgs {
     const void* img;
     long long ld, bstride;  // elements
     int L, P, tiles_p, ntiles;
-    int nsweep, nframe;
+    int nsweep, nframe;  // nframe unused (kept 0): the ring is shared by the sweep blocks
     int vec_ok, transposed;
-    double* part;        // [batch][nsweep*NLAG + nframe*NFRM]
+    double* part;        // [batch][nsweep][NTOT]
     unsigned* counter;   // [batch]
     Scal* scal;          // [batch]
     ScalDbg* dbg;        // [batch]
@@ -514,11 +527,11 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
     const int b = blockIdx.y;
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     const int L = a.L, P = a.P;
-    double* part = a.part + (size_t)b * ((size_t)a.nsweep * NLAG + (size_t)a.nframe * NFRM);
+    double* part = a.part + (size_t)b * (size_t)a.nsweep * NTOT;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
-    if ((int)blockIdx.x >= a.nframe) {
-        const int sb = blockIdx.x - a.nframe, step = a.nsweep;
+    {
+        const int sb = blockIdx.x, step = a.nsweep;
         constexpr int NST = TMA ? SWEEP_NST : 1;
         auto stage = [&](int s) { return reinterpret_cast<float*>(dsm + (size_t)s * SWEEP_STAGE); };
         auto issue = [&](int t, int s) {  // thread 0 only
@@ -573,8 +586,10 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
         for (int v = 0; v < NLAG; v++) dacc[v] += (double)__fadd_rn(e0[v], e1[v]);
         __syncthreads();
         block_sum<NLAG>(dacc, red);
-        if (threadIdx.x < NLAG) part[(size_t)sb * NLAG + threadIdx.x] = red[threadIdx.x];
-    } else {
+        if (threadIdx.x < NLAG) part[(size_t)sb * NTOT + threadIdx.x] = red[threadIdx.x];
+        __syncthreads();
+    }
+    {
         // ---- frame ring: pixels within 2 of the border, naive products guarded by "partner not in core" ----
         const int fb = blockIdx.x;
         const int ntop = min(2, L), lbot = max(2, L - 2), nbot = L - lbot > 0 ? L - lbot : 0;
@@ -585,7 +600,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
         double facc[NFRM];
 #pragma unroll
         for (int v = 0; v < NFRM; v++) facc[v] = 0.0;
-        for (long long idx = (long long)fb * NT + threadIdx.x; idx < count; idx += (long long)a.nframe * NT) {
+        for (long long idx = (long long)fb * NT + threadIdx.x; idx < count; idx += (long long)a.nsweep * NT) {
             int l, p;
             if (idx < n1) { l = (int)(idx / P); p = (int)(idx - (long long)l * P); }
             else if (idx < n2) { const long long i2 = idx - n1; const int q = (int)(i2 / P); l = lbot + q; p = (int)(i2 - (long long)q * P); }
@@ -620,7 +635,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
                 }
         }
         block_sum<NFRM>(facc, red);
-        if (threadIdx.x < NFRM) part[(size_t)a.nsweep * NLAG + (size_t)fb * NFRM + threadIdx.x] = red[threadIdx.x];
+        if (threadIdx.x < NFRM) part[(size_t)fb * NTOT + NLAG + threadIdx.x] = red[threadIdx.x];
     }
 
     // ---- second stage + solve in the last block ----
@@ -628,8 +643,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
     __shared__ double tot[NTOT];
     __shared__ double M[72];
     for (int v = w; v < NTOT; v += NT / 32) {
-        const double s = v < NLAG ? column_sum(part, a.nsweep, NLAG, v)
-                                  : column_sum(part + (size_t)a.nsweep * NLAG, a.nframe, NFRM, v - NLAG);
+        const double s = column_sum(part, a.nsweep, NTOT, v);
         if (lane == 0) tot[v] = s;
     }
     __syncthreads();
@@ -708,7 +722,7 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
     }
 }
 
-// mask.W for one thread's 4 px x 4 lines: calls f(r, m[4], u[4], centre[4]) per line
+// mask.W for one thread's 4 px x 4 lines: calls f(r, m[4], w[4], centre-line window) per line
 template <int MASK, bool TR, typename F>
 __device__ __forceinline__ void mask_lines(const float* __restrict__ tile, const float* __restrict__ wt, const float (&c)[8], F f)
 {
@@ -735,6 +749,8 @@ __device__ __forceinline__ void mask_lines(const float* __restrict__ tile, const
     }
 }
 
+template <bool V> struct BoolTag { static constexpr bool value = V; };
+
 // ---- k_stats: MASK = ME: sum (|e| W)^2 and max|e| (the max cancels out of a.mask.W — SURVEY.md §0 — so no
 // separate max pass); MASK = NVF: sum (nvf W)^2.  Last block: a = strength / (||mask.W|| / sqrt(N)) (Watermark.cpp:170)
 template <typename PixT, int MASK, bool TR, bool TMA>
@@ -757,19 +773,22 @@ __global__ void __launch_bounds__(NT, 2) k_stats(const __grid_constant__ CUtenso
     float emax = 0.0f;
     embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&](const float* tile, const float* wt, int l0, int p0) {
         const int pb = p0 + 4 * lane;
-        const bool full = l0 + TL <= L && p0 + TP <= P;
         float fs = 0.0f;
-        mask_lines<MASK, TR>(tile, wt, c, [&](int r, const float (&m)[4], const float (&wq)[4], const float (&)[6]) {
-            const int l = l0 + 4 * w + r;
+        auto run = [&](auto tag) {
+            constexpr bool FULL = decltype(tag)::value;
+            mask_lines<MASK, TR>(tile, wt, c, [&](int r, const float (&m)[4], const float (&wq)[4], const float (&)[6]) {
+                const bool lok = FULL || (l0 + 4 * w + r < L);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (full || (l < L && pb + j < P)) {
-                    if (MASK == 0) emax = fmaxf(emax, m[j]);
-                    const float u = __fmul_rn(m[j], wq[j]);
+                for (int j = 0; j < 4; j++) {
+                    const bool ok = FULL || (lok && pb + j < P);
+                    const float mj = ok ? m[j] : 0.0f;  // branch-free masking of the tile overhang
+                    if (MASK == 0) emax = fmaxf(emax, mj);
+                    const float u = __fmul_rn(mj, wq[j]);
                     fs = __fmaf_rn(u, u, fs);
                 }
-            }
-        });
+            });
+        };
+        if (l0 + TL <= L && p0 + TP <= P) run(BoolTag<true>{}); else run(BoolTag<false>{});
         dsum += (double)fs;
     });
     {   // block reduce: sum and max
@@ -803,7 +822,8 @@ __global__ void __launch_bounds__(NT, 2) k_stats(const __grid_constant__ CUtenso
 }
 
 // ---- k_apply: out = clamp(base + (mask.W).a, 0, 255) per channel (Watermark.cpp:169-171); u8 output truncates like
-// `.as(u8)` (main.cpp:356,380).  status != 0 copies base through unchanged (k_copy_base).
+// `.as(u8)` (main.cpp:356,380).  status != 0 copies base through unchanged.
+// SB = the base IS the gray input (one channel, same buffer): no separate base loads (the video driver's case).
 template <typename T> __device__ __forceinline__ T to_out(float v);
 template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ uint8_t to_out<uint8_t>(float v) { return (uint8_t)v; }  // truncation
@@ -823,7 +843,19 @@ __device__ __forceinline__ void copy_base_through(const EmbedArgs& a)
         }
 }
 
-template <typename PixT, typename OutT, int MASK, bool TR, bool TMA>
+template <typename OutT>
+__device__ __forceinline__ void store4(OutT* orow, const float (&ov)[4], bool vec, int nvalid)
+{
+    if (vec) {
+        if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(orow) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        else *reinterpret_cast<uchar4*>(orow) = make_uchar4(to_out<uint8_t>(ov[0]), to_out<uint8_t>(ov[1]), to_out<uint8_t>(ov[2]), to_out<uint8_t>(ov[3]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j < nvalid) orow[j] = to_out<OutT>(ov[j]);
+    }
+}
+
+template <typename PixT, typename OutT, int MASK, bool TR, bool TMA, bool SB>
 __global__ void __launch_bounds__(NT, 2) k_apply(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
                                                  const EmbedArgs a)
 {
@@ -842,54 +874,47 @@ __global__ void __launch_bounds__(NT, 2) k_apply(const __grid_constant__ CUtenso
     for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
     const float av = sc->a, mx = sc->emax;
     const float rmx = MASK == 0 ? __frcp_rn(mx) : 0.0f;
+    const bool out_vec = a.out_vec_ok != 0, base_vec = a.base_vec_ok != 0;
+    const int channels = SB ? 1 : a.channels;
     embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&](const float* tile, const float* wt, int l0, int p0) {
         const int pb = p0 + 4 * lane;
-        const bool full = l0 + TL <= L && p0 + TP <= P;
-        mask_lines<MASK, TR>(tile, wt, c, [&](int r, const float (&m)[4], const float (&wq)[4], const float (&r1)[6]) {
-            const int l = l0 + 4 * w + r;
-            if (!(full || (l < L && pb < P))) return;
-            float au[4];  // u = mask * W (Watermark.cpp:169), mask = |e| / max|e| (Watermark.cpp:214)
+        auto run = [&](auto tag) {
+            constexpr bool FULL = decltype(tag)::value;
+            const int nvalid = FULL ? 4 : P - pb;  // pixels of my 4 inside the image (<= 0: none)
+            mask_lines<MASK, TR>(tile, wt, c, [&](int r, const float (&m)[4], const float (&wq)[4], const float (&r1)[6]) {
+                const int l = l0 + 4 * w + r;
+                if (!FULL && (l >= L || nvalid <= 0)) return;
+                float au[4];  // u = mask * W (Watermark.cpp:169), mask = |e| / max|e| (Watermark.cpp:214)
 #pragma unroll
-            for (int j = 0; j < 4; j++) au[j] = __fmul_rn(MASK == 0 ? div_by(m[j], mx, rmx) : m[j], wq[j]);
-            for (int ch = 0; ch < a.channels; ch++) {
-                float bv[4];
-                if (a.same_base) {
-                    bv[0] = r1[1]; bv[1] = r1[2]; bv[2] = r1[3]; bv[3] = r1[4];
-                } else {
-                    const PixT* br = bas + (long long)ch * a.base_pstride + (long long)l * a.base_ld + pb;
-                    if (a.base_vec_ok && (full || pb + 3 < P)) {
-                        if constexpr (sizeof(PixT) == 4) {
-                            const float4 v = __ldg(reinterpret_cast<const float4*>(br));
-                            bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+                for (int j = 0; j < 4; j++) au[j] = __fmul_rn(MASK == 0 ? div_by(m[j], mx, rmx) : m[j], wq[j]);
+                for (int ch = 0; ch < channels; ch++) {
+                    float bv[4];
+                    if constexpr (SB) {
+                        bv[0] = r1[1]; bv[1] = r1[2]; bv[2] = r1[3]; bv[3] = r1[4];
+                    } else {
+                        const PixT* br = bas + (long long)ch * a.base_pstride + (long long)l * a.base_ld + pb;
+                        if (base_vec && (FULL || nvalid >= 4)) {
+                            if constexpr (sizeof(PixT) == 4) {
+                                const float4 v = __ldg(reinterpret_cast<const float4*>(br));
+                                bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+                            } else {
+                                const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(br));
+                                bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+                            }
                         } else {
-                            const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(br));
-                            bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+#pragma unroll
+                            for (int j = 0; j < 4; j++) bv[j] = (j < nvalid) ? (float)br[j] : 0.0f;
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) bv[j] = (pb + j < P) ? (float)br[j] : 0.0f;
                     }
-                }
-                float ov[4];
+                    float ov[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float v = __fmaf_rn(au[j], av, bv[j]);
-                    ov[j] = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);  // af::clamp(., 0, 255)
+                    for (int j = 0; j < 4; j++) ov[j] = fminf(fmaxf(__fmaf_rn(au[j], av, bv[j]), 0.0f), 255.0f);  // af::clamp
+                    OutT* orow = out + (long long)ch * a.out_pstride + (long long)l * a.out_ld + pb;
+                    store4<OutT>(orow, ov, out_vec && (FULL || nvalid >= 4), nvalid);
                 }
-                OutT* orow = out + (long long)ch * a.out_pstride + (long long)l * a.out_ld + pb;
-                if (a.out_vec_ok && (full || pb + 3 < P)) {
-                    if constexpr (sizeof(OutT) == 4) {
-                        *reinterpret_cast<float4*>(orow) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-                    } else {
-                        *reinterpret_cast<uchar4*>(orow) =
-                            make_uchar4(to_out<uint8_t>(ov[0]), to_out<uint8_t>(ov[1]), to_out<uint8_t>(ov[2]), to_out<uint8_t>(ov[3]));
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) if (pb + j < P) orow[j] = to_out<OutT>(ov[j]);
-                }
-            }
-        });
+            });
+        };
+        if (l0 + TL <= L && p0 + TP <= P) run(BoolTag<true>{}); else run(BoolTag<false>{});
     });
 }
 
@@ -912,6 +937,105 @@ struct DetectArgs {
     Scal* scal;
     ScalDbg* dbg;
 };
+
+// one tile of the detector; FULL = the tile lies completely inside the image (its 1-pixel ring may not)
+template <int MASK, bool TR, bool FULL>
+__device__ __forceinline__ void detect_tile(const float* __restrict__ zt, const float* __restrict__ wt, float* __restrict__ ut,
+                                            const float (&c)[8], int l0, int p0, int L, int P, float& fd, float& fz, float& fu)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int pb = p0 + 4 * lane;
+    const int scol = 4 * lane + HP;
+    float ez[4][4];
+    // ---- phase 1a: my 4 x 4 pixels ----
+    {
+        const float* zb = zt + (4 * w + 1) * SW;  // smem line of image line l-1 for r = 0
+        float r0[6], r1[6], r2[6];
+        load_win6(r0, zb, scol);
+        load_win6(r1, zb + SW, scol);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            load_win6(r2, zb + (r + 2) * SW, scol);
+            const float4 wv = *reinterpret_cast<const float4*>(wt + (4 * w + r + 1) * SW + scol);
+            const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+            float uu[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float e = __fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j));
+                ez[r][j] = e;
+                float m;
+                if constexpr (MASK == 0) m = fabsf(e); else m = nvf_mask<TR>(r0, r1, r2, j);
+                uu[j] = __fmul_rn(m, wq[j]);
+            }
+            *reinterpret_cast<float4*>(ut + (4 * w + r + 1) * SW + scol) = make_float4(uu[0], uu[1], uu[2], uu[3]);
+#pragma unroll
+            for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
+        }
+    }
+    // ---- phase 1b: the 1-pixel ring around the tile (in-image cells only) ----
+    for (int idx = threadIdx.x; idx < 2 * (TP + 2) + 2 * TL; idx += NT) {
+        int rl, rp;  // relative to (l0, p0)
+        if (idx < TP + 2) { rl = -1; rp = idx - 1; }
+        else if (idx < 2 * (TP + 2)) { rl = TL; rp = idx - (TP + 2) - 1; }
+        else if (idx < 2 * (TP + 2) + TL) { rl = idx - 2 * (TP + 2); rp = -1; }
+        else { rl = idx - 2 * (TP + 2) - TL; rp = TP; }
+        const int l = l0 + rl, p = p0 + rp;
+        if (l >= 0 && l < L && p >= 0 && p < P) {
+            const float* zc = zt + (rl + 2) * SW + (rp + HP);
+            float q0[3] = {zc[-SW - 1], zc[-SW], zc[-SW + 1]};
+            float q1[3] = {zc[-1], zc[0], zc[1]};
+            float q2[3] = {zc[SW - 1], zc[SW], zc[SW + 1]};
+            float m;
+            if constexpr (MASK == 0) m = fabsf(__fsub_rn(q1[1], predict<TR>(c, q0, q1, q2, 0)));
+            else m = nvf_mask<TR>(q0, q1, q2, 0);
+            ut[(rl + 1) * SW + (rp + HP)] = __fmul_rn(m, wt[(rl + 1) * SW + (rp + HP)]);
+        }
+    }
+    __syncthreads();
+    // ---- tiles on the image frame: u(p+o) = u(clamp(p+o)) for the cells just outside the image.  Only the line
+    // above/below and the column left/right of the image can be read by a valid pixel. ----
+    if (l0 == 0 || p0 == 0 || l0 + TL >= L || p0 + TP >= P) {
+        const int rl_lo = max(l0, 0) - l0, rl_hi = min(l0 + TL, L) - l0;  // in-image tile lines [rl_lo, rl_hi) (rel.)
+        const int rp_lo = 0, rp_hi = min(p0 + TP, P) - p0;
+        (void)rl_lo; (void)rp_lo;
+        for (int idx = threadIdx.x; idx < 2 * (TP + 2) + 2 * (TL + 2); idx += NT) {
+            int rl, rp;
+            if (idx < TP + 2) { rl = -1; rp = idx - 1; }                       // line above the tile
+            else if (idx < 2 * (TP + 2)) { rl = rl_hi; rp = idx - (TP + 2) - 1; }  // first line below the in-image part
+            else if (idx < 2 * (TP + 2) + (TL + 2)) { rl = idx - 2 * (TP + 2) - 1; rp = -1; }
+            else { rl = idx - 2 * (TP + 2) - (TL + 2) - 1; rp = rp_hi; }
+            const int l = l0 + rl, p = p0 + rp;
+            if (rl <= TL && rp <= TP && (l < 0 || l >= L || p < 0 || p >= P)) {
+                const int lc = clampi(l, 0, L - 1) - l0, pc = clampi(p, 0, P - 1) - p0;
+                ut[(rl + 1) * SW + (rp + HP)] = ut[(lc + 1) * SW + (pc + HP)];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- phase 2: e_u and the correlation sums ----
+    {
+        const float* ub = ut + (4 * w) * SW;
+        float r0[6], r1[6], r2[6];
+        load_win6(r0, ub, scol);
+        load_win6(r1, ub + SW, scol);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            load_win6(r2, ub + (r + 2) * SW, scol);
+            const bool lok = FULL || (l0 + 4 * w + r < L);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bool ok = FULL || (lok && pb + j < P);
+                const float eu = ok ? __fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j)) : 0.0f;
+                const float e = ok ? ez[r][j] : 0.0f;
+                fd = __fmaf_rn(eu, e, fd);
+                fz = __fmaf_rn(e, e, fz);
+                fu = __fmaf_rn(eu, eu, fu);
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
+        }
+    }
+}
 
 template <typename PixT, int MASK, bool TR, bool TMA>
 __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW,
@@ -954,7 +1078,6 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
     for (int t = blockIdx.x; t < a.ntiles; t += step, k++) {
         const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
         const int l0 = tl * TL, p0 = tp * TP;
-        const int pb = p0 + 4 * lane;
         float *zt, *wt;  // zt: (TL+4) x SW lines l0-2 ..; wt: (TL+2) x SW lines l0-1 ..
         if constexpr (TMA) {
             if (threadIdx.x == 0) {
@@ -973,92 +1096,10 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
             load_tile<float, TL + 2>(wt, a.W, P, L, P, l0 - 1, p0 - HP, a.w_vec_ok != 0);
             __syncthreads();
         }
-        const bool full = l0 + TL <= L && p0 + TP <= P;
-        const int scol = 4 * lane + HP;
-        float ez[4][4];
-        // ---- phase 1a: my 4 x 4 pixels ----
-        {
-            const float* zb = zt + (4 * w + 1) * SW;  // smem line of image line l-1 for r = 0
-            float r0[6], r1[6], r2[6];
-            load_win6(r0, zb, scol);
-            load_win6(r1, zb + SW, scol);
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                load_win6(r2, zb + (r + 2) * SW, scol);
-                const float4 wv = *reinterpret_cast<const float4*>(wt + (4 * w + r + 1) * SW + scol);
-                const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
-                float uu[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float e = __fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j));
-                    ez[r][j] = e;
-                    float m;
-                    if constexpr (MASK == 0) m = fabsf(e); else m = nvf_mask<TR>(r0, r1, r2, j);
-                    uu[j] = __fmul_rn(m, wq[j]);
-                }
-                *reinterpret_cast<float4*>(ut + (4 * w + r + 1) * SW + scol) = make_float4(uu[0], uu[1], uu[2], uu[3]);
-#pragma unroll
-                for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
-            }
-        }
-        // ---- phase 1b: the 1-pixel ring around the tile (in-image cells only) ----
-        for (int idx = threadIdx.x; idx < 2 * (TP + 2) + 2 * TL; idx += NT) {
-            int rl, rp;  // relative to (l0, p0)
-            if (idx < TP + 2) { rl = -1; rp = idx - 1; }
-            else if (idx < 2 * (TP + 2)) { rl = TL; rp = idx - (TP + 2) - 1; }
-            else if (idx < 2 * (TP + 2) + TL) { rl = idx - 2 * (TP + 2); rp = -1; }
-            else { rl = idx - 2 * (TP + 2) - TL; rp = TP; }
-            const int l = l0 + rl, p = p0 + rp;
-            if (l >= 0 && l < L && p >= 0 && p < P) {
-                const float* zc = zt + (rl + 2) * SW + (rp + HP);
-                float q0[3] = {zc[-SW - 1], zc[-SW], zc[-SW + 1]};
-                float q1[3] = {zc[-1], zc[0], zc[1]};
-                float q2[3] = {zc[SW - 1], zc[SW], zc[SW + 1]};
-                float m;
-                if constexpr (MASK == 0) m = fabsf(__fsub_rn(q1[1], predict<TR>(c, q0, q1, q2, 0)));
-                else m = nvf_mask<TR>(q0, q1, q2, 0);
-                ut[(rl + 1) * SW + (rp + HP)] = __fmul_rn(m, wt[(rl + 1) * SW + (rp + HP)]);
-            }
-        }
-        __syncthreads();
-        // ---- tiles on the image frame: replicate u into cells outside the image (sources are in-image cells) ----
-        if (l0 == 0 || p0 == 0 || l0 + TL >= L || p0 + TP >= P) {
-            for (int idx = threadIdx.x; idx < (TL + 2) * (TP + 2); idx += NT) {
-                const int rl = idx / (TP + 2) - 1, rp = idx - (rl + 1) * (TP + 2) - 1;
-                const int l = l0 + rl, p = p0 + rp;
-                if (l < 0 || l >= L || p < 0 || p >= P) {
-                    const int lc = clampi(l, 0, L - 1) - l0, pc = clampi(p, 0, P - 1) - p0;
-                    ut[(rl + 1) * SW + (rp + HP)] = ut[(lc + 1) * SW + (pc + HP)];
-                }
-            }
-            __syncthreads();
-        }
-        // ---- phase 2: e_u and the correlation sums ----
-        {
-            const float* ub = ut + (4 * w) * SW;
-            float r0[6], r1[6], r2[6];
-            load_win6(r0, ub, scol);
-            load_win6(r1, ub + SW, scol);
-            float fd = 0.0f, fz = 0.0f, fu = 0.0f;
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                load_win6(r2, ub + (r + 2) * SW, scol);
-                const int l = l0 + 4 * w + r;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (full || (l < L && pb + j < P)) {
-                        const float eu = __fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j));
-                        const float e = ez[r][j];
-                        fd = __fmaf_rn(eu, e, fd);
-                        fz = __fmaf_rn(e, e, fz);
-                        fu = __fmaf_rn(eu, eu, fu);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
-            }
-            ddot += (double)fd; dnz += (double)fz; dnu += (double)fu;
-        }
+        float fd = 0.0f, fz = 0.0f, fu = 0.0f;
+        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu);
+        else detect_tile<MASK, TR, false>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu);
+        ddot += (double)fd; dnz += (double)fz; dnu += (double)fu;
         if constexpr (TMA) __syncthreads();  // ut and the stage are rewritten from the next iteration on
     }
     __syncthreads();
