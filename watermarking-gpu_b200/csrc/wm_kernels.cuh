@@ -105,6 +105,33 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
                  : "memory");
 }
 
+// round-robin tile walk t = first, first + step, ... with (tl, tp) kept incrementally (no per-tile division)
+struct TileIter {
+    int t, tl, tp, step, step_l, step_p, tiles_p;
+    __device__ __forceinline__ TileIter(int first, int step_, int tiles_p_) : t(first), step(step_), tiles_p(tiles_p_)
+    {
+        tl = first / tiles_p_; tp = first - tl * tiles_p_;
+        step_l = step_ / tiles_p_; step_p = step_ - step_l * tiles_p_;
+    }
+    __device__ __forceinline__ void next()
+    {
+        t += step; tl += step_l; tp += step_p;
+        if (tp >= tiles_p) { tp -= tiles_p; tl++; }
+    }
+    // coordinates of the tile `ahead` steps further on (ahead is a small compile-time-ish constant)
+    __device__ __forceinline__ void peek(int ahead, int& ptl, int& ptp) const
+    {
+        ptl = tl + ahead * step_l; ptp = tp + ahead * step_p;
+        while (ptp >= tiles_p) { ptp -= tiles_p; ptl++; }
+    }
+};
+// ring position of a software pipeline: stage index and mbarrier phase parity, advanced without % or /
+template <int NST> struct StagePos {
+    int s = 0, ph = 0;
+    __device__ __forceinline__ void next() { if (++s == NST) { s = 0; ph ^= 1; } }
+    __device__ __forceinline__ int ahead(int n) const { int x = s + n; return x >= NST ? x - NST : x; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // plain tile loaders (TMA = false): rows [l_org, l_org+NROWS) x cols [p_org, p_org+SW) of the image into smem
 // as float, coordinates clamped to the image (replicate border).  p_org is a multiple of 4, so a 4-pixel chunk
@@ -534,11 +561,11 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
         const int sb = blockIdx.x, step = a.nsweep;
         constexpr int NST = TMA ? SWEEP_NST : 1;
         auto stage = [&](int s) { return reinterpret_cast<float*>(dsm + (size_t)s * SWEEP_STAGE); };
-        auto issue = [&](int t, int s) {  // thread 0 only
-            const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+        auto issue = [&](int tl, int tp, int s) {  // thread 0 only
             mbar_expect_tx(&bars[s], (TL + 2) * SW * 4);
             tma_load_3d(stage(s), &tmI, tp * TP - HP, tl * TL, b, &bars[s]);
         };
+        TileIter it(sb, step, a.tiles_p);
         if constexpr (TMA) {
             if (threadIdx.x == 0) {
                 for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
@@ -547,26 +574,29 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
             __syncthreads();
             if (threadIdx.x == 0)
                 for (int s = 0; s < NST - 1; s++)
-                    if (sb + s * step < a.ntiles) issue(sb + s * step, s);
+                    if (sb + s * step < a.ntiles) { int ptl, ptp; it.peek(s, ptl, ptp); issue(ptl, ptp, s); }
         }
         double dacc[NLAG];
         float e0[NLAG], e1[NLAG];  // even / odd pixel accumulators
 #pragma unroll
         for (int v = 0; v < NLAG; v++) { dacc[v] = 0.0; e0[v] = 0.0f; e1[v] = 0.0f; }
+        StagePos<NST> pos;
         int k = 0;
-        for (int t = sb; t < a.ntiles; t += step, k++) {
-            const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
-            const int l0 = tl * TL, p0 = tp * TP;
+        for (; it.t < a.ntiles; it.next(), k++) {
+            const int l0 = it.tl * TL, p0 = it.tp * TP;
             const float* tile;
             if constexpr (TMA) {
-                if (threadIdx.x == 0) {
-                    const int tn = t + (NST - 1) * step;
-                    if (tn < a.ntiles) { fence_proxy_async(); issue(tn, (k + NST - 1) % NST); }
+                if (threadIdx.x == 0 && it.t + (NST - 1) * step < a.ntiles) {
+                    int ptl, ptp;
+                    it.peek(NST - 1, ptl, ptp);
+                    fence_proxy_async();
+                    issue(ptl, ptp, pos.ahead(NST - 1));
                 }
-                mbar_wait(&bars[k % NST], (k / NST) & 1);
-                float* tw = stage(k % NST);
+                mbar_wait(&bars[pos.s], pos.ph);
+                float* tw = stage(pos.s);
                 if (tile_on_frame<TL + 2>(l0, p0 - HP, L, P)) { fix_border<TL + 2>(tw, l0, p0 - HP, L, P); __syncthreads(); }
                 tile = tw;
+                pos.next();
             } else {
                 __syncthreads();
                 load_tile<PixT, TL + 2>(stage(0), img, a.ld, L, P, l0, p0 - HP, a.vec_ok != 0);
@@ -580,7 +610,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
 #pragma unroll
                 for (int v = 0; v < NLAG; v++) { dacc[v] += (double)__fadd_rn(e0[v], e1[v]); e0[v] = 0.0f; e1[v] = 0.0f; }
             }
-            if constexpr (TMA) __syncthreads();  // stage k % NST may be refilled from the next iteration on
+            if constexpr (TMA) __syncthreads();  // the stage just read may be refilled from the next iteration on
         }
 #pragma unroll
         for (int v = 0; v < NLAG; v++) dacc[v] += (double)__fadd_rn(e0[v], e1[v]);
@@ -597,45 +627,66 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
         const int ncl = min(2, P), pright = max(2, P - 2), ncr = P - pright > 0 ? P - pright : 0;
         const long long n1 = (long long)ntop * P, n2 = n1 + (long long)nbot * P;
         const long long count = n2 + (long long)nmid * (ncl + ncr);
-        double facc[NFRM];
+        // One warp per ring pixel, one lane per product: lane v (< 32) owns partial v and, for v < 12, partial 32 + v,
+        // so the 44 partials never need a cross-lane reduction (only the 8 warps are summed through smem).
+        // partial t: t < 8 -> rx[t]; t >= 8 -> Rx pair (i, j), i <= j, in row-major upper-triangle order.
+        int pi[2], pj[2];
 #pragma unroll
-        for (int v = 0; v < NFRM; v++) facc[v] = 0.0;
-        for (long long idx = (long long)fb * NT + threadIdx.x; idx < count; idx += (long long)a.nsweep * NT) {
-            int l, p;
-            if (idx < n1) { l = (int)(idx / P); p = (int)(idx - (long long)l * P); }
-            else if (idx < n2) { const long long i2 = idx - n1; const int q = (int)(i2 / P); l = lbot + q; p = (int)(i2 - (long long)q * P); }
-            else { const long long i3 = idx - n2; const int q = (int)(i3 / (ncl + ncr)); const int c = (int)(i3 - (long long)q * (ncl + ncr)); l = 2 + q; p = c < ncl ? c : pright + (c - ncl); }
-            float n[8];
-            bool nc[8];  // neighbour position NOT in core
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const int dl = m < 3 ? -1 : (m < 5 ? 0 : 1);
-                const int dp = m < 3 ? m - 1 : (m == 3 ? -1 : (m == 4 ? 1 : m - 6));
-                const int ll = l + dl, pp = p + dp;
-                nc[m] = !(ll >= 1 && ll <= L - 2 && pp >= 1 && pp <= P - 2);
-                n[m] = (float)img[(long long)clampi(ll, 0, L - 1) * a.ld + clampi(pp, 0, P - 1)];
-            }
-            const float x = (float)img[(long long)l * a.ld + p];
-            const bool xc = !(l >= 1 && l <= L - 2 && p >= 1 && p <= P - 2);
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const bool use = m <= 3 ? nc[m] : xc;
-                float pr = __fmul_rn(n[m], x);
-                if constexpr (FP16) pr = round_f16(pr);
-                if (use) facc[m] += (double)pr;
-            }
-            int t = 8;
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-#pragma unroll
-                for (int j = i; j < 8; j++, t++) {
-                    float pr = __fmul_rn(n[i], n[j]);
-                    if constexpr (FP16) pr = round_f16(pr);
-                    if (nc[i]) facc[t] += (double)pr;
-                }
+        for (int q = 0; q < 2; q++) {
+            const int t = lane + 32 * q;
+            int i = 0, j = 0;
+            if (t < 8) { i = t; j = 8; }              // j = 8 stands for the centre pixel
+            else if (t < NFRM) { int r = t - 8; i = 0; while (r >= 8 - i) { r -= 8 - i; i++; } j = i + r; }
+            pi[q] = i; pj[q] = j;
         }
-        block_sum<NFRM>(facc, red);
-        if (threadIdx.x < NFRM) part[(size_t)fb * NTOT + NLAG + threadIdx.x] = red[threadIdx.x];
+        double f0 = 0.0, f1 = 0.0;
+        // chunks of NT ring pixels: thread t stages pixel t's 3x3 window (clamped) + its not-in-core bits in smem
+        // (all loads of a chunk in flight together), then each warp walks 32 of the staged pixels
+        float* win = reinterpret_cast<float*>(dsm);            // [NT][9]  (the tile stages are idle by now)
+        unsigned* ncm = reinterpret_cast<unsigned*>(win + NT * 9);  // [NT]
+        for (long long c0 = (long long)fb * NT; c0 < count; c0 += (long long)a.nsweep * NT) {
+            const long long idx = c0 + threadIdx.x;
+            __syncthreads();
+            if (idx < count) {
+                int l, p;
+                if (idx < n1) { l = (int)(idx / P); p = (int)(idx - (long long)l * P); }
+                else if (idx < n2) { const long long i2 = idx - n1; const int q = (int)(i2 / P); l = lbot + q; p = (int)(i2 - (long long)q * P); }
+                else { const long long i3 = idx - n2; const int q = (int)(i3 / (ncl + ncr)); const int c = (int)(i3 - (long long)q * (ncl + ncr)); l = 2 + q; p = c < ncl ? c : pright + (c - ncl); }
+                unsigned m = 0;
+#pragma unroll
+                for (int k = 0; k < 9; k++) {  // raster order, k = 4 is the centre
+                    const int ll = l + k / 3 - 1, pp = p + k % 3 - 1;
+                    if (!(ll >= 1 && ll <= L - 2 && pp >= 1 && pp <= P - 2)) m |= 1u << k;
+                    win[threadIdx.x * 9 + k] = (float)img[(long long)clampi(ll, 0, L - 1) * a.ld + clampi(pp, 0, P - 1)];
+                }
+                ncm[threadIdx.x] = m;
+            }
+            __syncthreads();
+            const int nhere = (int)min((long long)NT, count - c0);
+            for (int px = w; px < nhere; px += NT / 32) {
+                const unsigned ncmask = ncm[px];
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int i = pi[q], j = pj[q];
+                    const int li = i < 4 ? i : i + 1, lj = j == 8 ? 4 : (j < 4 ? j : j + 1);  // neighbour index -> window slot
+                    float pr = __fmul_rn(win[px * 9 + li], win[px * 9 + lj]);
+                    if constexpr (FP16) pr = round_f16(pr);
+                    // rx[i], i <= 3 and every Rx pair: counted when p + o_i is not a core pixel; rx[i], i >= 4: when p is not
+                    const bool use = (j == 8 && i >= 4) ? ((ncmask >> 4) & 1) : ((ncmask >> li) & 1);
+                    if (lane + 32 * q < NFRM && use) { if (q == 0) f0 += (double)pr; else f1 += (double)pr; }
+                }
+            }
+        }
+        __syncthreads();
+        red[w * NFRM + lane] = f0;
+        if (lane < NFRM - 32) red[w * NFRM + 32 + lane] = f1;
+        __syncthreads();
+        if (threadIdx.x < NFRM) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < NT / 32; k++) sacc += red[k * NFRM + threadIdx.x];
+            part[(size_t)fb * NTOT + NLAG + threadIdx.x] = sacc;
+        }
     }
 
     // ---- second stage + solve in the last block ----
@@ -681,12 +732,12 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
     const int b = blockIdx.y, step = gridDim.x;
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     auto stage = [&](int s) { return reinterpret_cast<float*>(dsm + (size_t)s * EMBED_STAGE); };
-    auto issue = [&](int t, int s) {  // thread 0 only
-        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+    auto issue = [&](int tl, int tp, int s) {  // thread 0 only
         mbar_expect_tx(&bars[s], (TL + 2) * SW * 4 + SZ_WT);
         tma_load_3d(stage(s), tmI, tp * TP - HP, tl * TL - 1, b, &bars[s]);
         tma_load_3d(reinterpret_cast<unsigned char*>(stage(s)) + SZ_I34, tmW, tp * TP, tl * TL, 0, &bars[s]);
     };
+    TileIter it(blockIdx.x, step, a.tiles_p);
     if constexpr (TMA) {
         if (threadIdx.x == 0) {
             for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
@@ -695,20 +746,22 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
         __syncthreads();
         if (threadIdx.x == 0)
             for (int s = 0; s < NST - 1; s++)
-                if ((int)blockIdx.x + s * step < a.ntiles) issue(blockIdx.x + s * step, s);
+                if ((int)blockIdx.x + s * step < a.ntiles) { int ptl, ptp; it.peek(s, ptl, ptp); issue(ptl, ptp, s); }
     }
-    int k = 0;
-    for (int t = blockIdx.x; t < a.ntiles; t += step, k++) {
-        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
-        const int l0 = tl * TL, p0 = tp * TP;
+    StagePos<NST> pos;
+    for (; it.t < a.ntiles; it.next()) {
+        const int l0 = it.tl * TL, p0 = it.tp * TP;
         float* tile;
         if constexpr (TMA) {
-            if (threadIdx.x == 0) {
-                const int tn = t + (NST - 1) * step;
-                if (tn < a.ntiles) { fence_proxy_async(); issue(tn, (k + NST - 1) % NST); }
+            if (threadIdx.x == 0 && it.t + (NST - 1) * step < a.ntiles) {
+                int ptl, ptp;
+                it.peek(NST - 1, ptl, ptp);
+                fence_proxy_async();
+                issue(ptl, ptp, pos.ahead(NST - 1));
             }
-            mbar_wait(&bars[k % NST], (k / NST) & 1);
-            tile = stage(k % NST);
+            mbar_wait(&bars[pos.s], pos.ph);
+            tile = stage(pos.s);
+            pos.next();
             if (tile_on_frame<TL + 2>(l0 - 1, p0 - HP, a.L, a.P)) { fix_border<TL + 2>(tile, l0 - 1, p0 - HP, a.L, a.P); __syncthreads(); }
         } else {
             tile = stage(0);
@@ -941,7 +994,8 @@ struct DetectArgs {
 // one tile of the detector; FULL = the tile lies completely inside the image (its 1-pixel ring may not)
 template <int MASK, bool TR, bool FULL>
 __device__ __forceinline__ void detect_tile(const float* __restrict__ zt, const float* __restrict__ wt, float* __restrict__ ut,
-                                            const float (&c)[8], int l0, int p0, int L, int P, float& fd, float& fz, float& fu)
+                                            const float (&c)[8], const int (&ring_l)[2], const int (&ring_p)[2], int l0, int p0,
+                                            int L, int P, float& fd, float& fz, float& fu)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int pb = p0 + 4 * lane;
@@ -973,14 +1027,11 @@ __device__ __forceinline__ void detect_tile(const float* __restrict__ zt, const 
         }
     }
     // ---- phase 1b: the 1-pixel ring around the tile (in-image cells only) ----
-    for (int idx = threadIdx.x; idx < 2 * (TP + 2) + 2 * TL; idx += NT) {
-        int rl, rp;  // relative to (l0, p0)
-        if (idx < TP + 2) { rl = -1; rp = idx - 1; }
-        else if (idx < 2 * (TP + 2)) { rl = TL; rp = idx - (TP + 2) - 1; }
-        else if (idx < 2 * (TP + 2) + TL) { rl = idx - 2 * (TP + 2); rp = -1; }
-        else { rl = idx - 2 * (TP + 2) - TL; rp = TP; }
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int rl = ring_l[q], rp = ring_p[q];
         const int l = l0 + rl, p = p0 + rp;
-        if (l >= 0 && l < L && p >= 0 && p < P) {
+        if (rl <= TL && l >= 0 && l < L && p >= 0 && p < P) {
             const float* zc = zt + (rl + 2) * SW + (rp + HP);
             float q0[3] = {zc[-SW - 1], zc[-SW], zc[-SW + 1]};
             float q1[3] = {zc[-1], zc[0], zc[1]};
@@ -1057,12 +1108,12 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
 #pragma unroll
     for (int k = 0; k < 8; k++) c[k] = sc->coef[k];
     auto stage = [&](int s) { return reinterpret_cast<float*>(dsm + (size_t)s * DETECT_STAGE); };
-    auto issue = [&](int t, int s) {  // thread 0 only
-        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+    auto issue = [&](int tl, int tp, int s) {  // thread 0 only
         mbar_expect_tx(&bars[s], (TL + 4) * SW * 4 + (TL + 2) * SW * 4);
         tma_load_3d(stage(s), &tmZ, tp * TP - HP, tl * TL - 2, b, &bars[s]);
         tma_load_3d(reinterpret_cast<unsigned char*>(stage(s)) + SZ_I36, &tmW, tp * TP - HP, tl * TL - 1, 0, &bars[s]);
     };
+    TileIter it(blockIdx.x, step, a.tiles_p);
     if constexpr (TMA) {
         if (threadIdx.x == 0) {
             for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
@@ -1071,22 +1122,36 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
         __syncthreads();
         if (threadIdx.x == 0)
             for (int s = 0; s < NST - 1; s++)
-                if ((int)blockIdx.x + s * step < a.ntiles) issue(blockIdx.x + s * step, s);
+                if ((int)blockIdx.x + s * step < a.ntiles) { int ptl, ptp; it.peek(s, ptl, ptp); issue(ptl, ptp, s); }
+    }
+    // my cells of the 1-pixel ring around a tile (relative to the tile origin), fixed for the whole kernel
+    int ring_l[2], ring_p[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int idx = threadIdx.x + q * NT;
+        int rl = TL + 8, rp = 0;  // sentinel: no cell
+        if (idx < TP + 2) { rl = -1; rp = idx - 1; }
+        else if (idx < 2 * (TP + 2)) { rl = TL; rp = idx - (TP + 2) - 1; }
+        else if (idx < 2 * (TP + 2) + TL) { rl = idx - 2 * (TP + 2); rp = -1; }
+        else if (idx < 2 * (TP + 2) + 2 * TL) { rl = idx - 2 * (TP + 2) - TL; rp = TP; }
+        ring_l[q] = rl; ring_p[q] = rp;
     }
     double ddot = 0.0, dnz = 0.0, dnu = 0.0;
-    int k = 0;
-    for (int t = blockIdx.x; t < a.ntiles; t += step, k++) {
-        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
-        const int l0 = tl * TL, p0 = tp * TP;
+    StagePos<NST> pos;
+    for (; it.t < a.ntiles; it.next()) {
+        const int l0 = it.tl * TL, p0 = it.tp * TP;
         float *zt, *wt;  // zt: (TL+4) x SW lines l0-2 ..; wt: (TL+2) x SW lines l0-1 ..
         if constexpr (TMA) {
-            if (threadIdx.x == 0) {
-                const int tn = t + (NST - 1) * step;
-                if (tn < a.ntiles) { fence_proxy_async(); issue(tn, (k + NST - 1) % NST); }
+            if (threadIdx.x == 0 && it.t + (NST - 1) * step < a.ntiles) {
+                int ptl, ptp;
+                it.peek(NST - 1, ptl, ptp);
+                fence_proxy_async();
+                issue(ptl, ptp, pos.ahead(NST - 1));
             }
-            mbar_wait(&bars[k % NST], (k / NST) & 1);
-            zt = stage(k % NST);
+            mbar_wait(&bars[pos.s], pos.ph);
+            zt = stage(pos.s);
             wt = zt + SZ_I36 / 4;
+            pos.next();
             if (tile_on_frame<TL + 4>(l0 - 2, p0 - HP, L, P)) { fix_border<TL + 4>(zt, l0 - 2, p0 - HP, L, P); __syncthreads(); }
         } else {
             zt = stage(0);
@@ -1097,8 +1162,8 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
             __syncthreads();
         }
         float fd = 0.0f, fz = 0.0f, fu = 0.0f;
-        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu);
-        else detect_tile<MASK, TR, false>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu);
+        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true>(zt, wt, ut, c, ring_l, ring_p, l0, p0, L, P, fd, fz, fu);
+        else detect_tile<MASK, TR, false>(zt, wt, ut, c, ring_l, ring_p, l0, p0, L, P, fd, fz, fu);
         ddot += (double)fd; dnz += (double)fz; dnu += (double)fu;
         if constexpr (TMA) __syncthreads();  // ut and the stage are rewritten from the next iteration on
     }
