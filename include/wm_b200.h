@@ -88,9 +88,10 @@ int wm_detect(wm_ctx *ctx, const wm_image *img, int mask_type, float *corr_host)
 /* ---- batched / pipelined form (BASELINE config 5; the video driver's inner loop) ----
  * `batch` equal-size images, image b at data + b*batch_stride elements (in/base/out each).
  * One launch sequence covers the whole batch; results land in a_host/corr_host/status_host[batch]
- * (status may be NULL).  Asynchronous on `slot` (0..wm_num_slots-1, each its own stream + workspace):
- * results are valid after wm_sync(ctx, slot). */
+ * (status may be NULL).  Asynchronous on `slot` (0..wm_num_slots-1, each its own stream + workspace): calls on one
+ * slot queue up in stream order (no host wait between them); results are valid after wm_sync(ctx, slot). */
 int wm_num_slots(const wm_ctx *ctx);
+void *wm_get_stream(const wm_ctx *ctx, int slot); /* the slot's cudaStream_t: order your own copies on it */
 int wm_embed_batch(wm_ctx *ctx, int slot, const wm_image *in_gray, const wm_image *base, wm_image *out,
                    int64_t in_stride, int64_t base_stride, int64_t out_stride, int batch, int mask_type,
                    float *a_host, int *status_host);

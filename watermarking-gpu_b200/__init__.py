@@ -29,7 +29,7 @@ VIDEO_EMBED, VIDEO_DETECT = 0, 1
 # every symbol include/wm_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "wm_create", "wm_create_from_file", "wm_clone", "wm_reinitialize", "wm_reinitialize_from_file", "wm_destroy",
-    "wm_set_option", "wm_last_error", "wm_strength_factor", "wm_embed", "wm_detect", "wm_num_slots",
+    "wm_set_option", "wm_last_error", "wm_strength_factor", "wm_embed", "wm_detect", "wm_num_slots", "wm_get_stream",
     "wm_embed_batch", "wm_detect_batch", "wm_sync", "wm_embed_host", "wm_detect_host", "wm_debug_get",
     "wm_debug_set_coeffs", "wm_debug_plane", "wm_get_kernel_times", "wm_launch_count", "wm_process_frames",
     "wm_dev_alloc", "wm_dev_free", "wm_dev_upload", "wm_dev_download", "wm_host_alloc_pinned",
@@ -91,6 +91,8 @@ def lib():
     L.wm_embed.argtypes = [vp, imp, imp, imp, i32, fp]
     L.wm_detect.argtypes = [vp, imp, i32, fp]
     L.wm_num_slots.argtypes = [vp]
+    L.wm_get_stream.argtypes = [vp, i32]
+    L.wm_get_stream.restype = vp
     L.wm_embed_batch.argtypes = [vp, i32, imp, imp, imp, i64, i64, i64, i32, i32, fp, ip]
     L.wm_detect_batch.argtypes = [vp, i32, imp, i64, i32, i32, fp, ip]
     L.wm_sync.argtypes = [vp, i32]
@@ -332,6 +334,10 @@ class Watermark:
     @property
     def num_slots(self):
         return lib().wm_num_slots(self._h)
+
+    def stream(self, slot):
+        """cudaStream_t (as int) of a slot, e.g. for torch.cuda.ExternalStream: order your own copies on it."""
+        return lib().wm_get_stream(self._h, slot)
 
     # -- parity access ----------------------------------------------------------------------------
     def debug(self, what):

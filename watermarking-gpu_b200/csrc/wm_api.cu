@@ -49,11 +49,10 @@ struct Slot {
     Scal* scal = nullptr;
     ScalDbg* dbg = nullptr;
     Scal* scal_host = nullptr;  // pinned
-    // pending result delivery
-    int pending = 0;  // 0 none, 1 embed, 2 detect
-    int pend_batch = 0;
-    float* pend_scalar = nullptr;
-    int* pend_status = nullptr;
+    // results in flight on this slot's stream, delivered in order by finish_slot (several ops may be queued)
+    struct Pending { int kind; int batch; float* scalar; int* status; size_t off; int64_t sstride; };  // kind 1 embed, 2 detect
+    std::vector<Pending> queue;
+    size_t host_cap = 0, host_used = 0;  // pinned result ring, in Scal units
     // staging for the host-buffer API / video driver
     void* stage_in = nullptr; size_t stage_in_cap = 0;
     void* stage_base = nullptr; size_t stage_base_cap = 0;
@@ -126,8 +125,15 @@ bool vec_ok(const void* p, long long ld, long long bstride, long long pstride, i
     return ((uintptr_t)p % al == 0) && (ld % 4 == 0) && (bstride % 4 == 0) && (pstride % 4 == 0);
 }
 
+int finish_slot(wm_ctx* ctx, Slot& s);
+
 int ensure_slot(wm_ctx* ctx, Slot& s, int batch, int gx_max, int nsweep, int nframe)
 {
+    const size_t need_part = (size_t)batch * ((size_t)nsweep * NTOT + (size_t)gx_max * 3);
+    if ((batch > s.batch_cap || need_part > s.part_cap) && !s.queue.empty()) {
+        const int r = finish_slot(ctx, s);  // buffers in use by queued work are about to be replaced
+        if (r < 0) return r;
+    }
     if (batch > s.batch_cap) {
         if (s.counters) cudaFree(s.counters);
         if (s.scal) cudaFree(s.scal);
@@ -140,10 +146,12 @@ int ensure_slot(wm_ctx* ctx, Slot& s, int batch, int gx_max, int nsweep, int nfr
         CU(cudaMemsetAsync(s.scal, 0, sizeof(Scal) * batch, s.stream));
         CU(cudaMalloc(&s.dbg, sizeof(ScalDbg) * batch));
         CU(cudaMemsetAsync(s.dbg, 0, sizeof(ScalDbg) * batch, s.stream));
-        CU(cudaMallocHost(&s.scal_host, sizeof(Scal) * batch));
+        s.host_cap = (size_t)std::max(batch * 4, 64);
+        s.host_used = 0;
+        CU(cudaMallocHost(&s.scal_host, sizeof(Scal) * s.host_cap));
         s.batch_cap = batch;
     }
-    const size_t need = (size_t)batch * ((size_t)nsweep * NTOT + (size_t)gx_max * 3);
+    const size_t need = need_part;
     (void)nframe;
     if (need > s.part_cap) {
         if (s.part) cudaFree(s.part);
@@ -350,6 +358,19 @@ void launch_detect(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream
     else launch_detect_t<uint8_t, false>(mask, tr, grid, st, tmZ, tmW, a);
 }
 
+// copy the op's per-image scalars into the slot's pinned ring (in stream order) and queue their delivery
+int push_result(wm_ctx* ctx, Slot& s, int kind, int batch)
+{
+    if (s.host_used + (size_t)batch > s.host_cap || s.queue.size() >= 32) {
+        const int r = finish_slot(ctx, s);  // ring full: deliver what is queued (the kernels of this op are already enqueued)
+        if (r < 0) return r;
+    }
+    CU(cudaMemcpyAsync(s.scal_host + s.host_used, s.scal, sizeof(Scal) * batch, cudaMemcpyDeviceToHost, s.stream));
+    s.queue.push_back({kind, batch, nullptr, nullptr, s.host_used, 1});
+    s.host_used += (size_t)batch;
+    return WM_OK;
+}
+
 // enqueue the Rx sweep (+ solve), or the injection of debug coefficients
 int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int batch, const Geo& g, const Plan& pl)
 {
@@ -445,10 +466,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
         launch_apply(vi.dtype, vo.dtype, mask, vi.transposed, tma, dim3(pl.gx_stats, batch), s.stream, tmI, tmW, ea);
     }
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(s.scal_host, s.scal, sizeof(Scal) * batch, cudaMemcpyDeviceToHost, s.stream));
-    s.pending = 1;
-    s.pend_batch = batch;
-    return WM_OK;
+    return push_result(ctx, s, 1, batch);
 }
 
 int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, int batch, int mask)
@@ -488,33 +506,30 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
         launch_detect(v.dtype, mask, v.transposed, tma, dim3(pl.gx_detect, batch), s.stream, tmZ, tmW, da);
     }
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(s.scal_host, s.scal, sizeof(Scal) * batch, cudaMemcpyDeviceToHost, s.stream));
-    s.pending = 2;
-    s.pend_batch = batch;
-    return WM_OK;
+    return push_result(ctx, s, 2, batch);
 }
 
-// wait for a slot and deliver its scalars; returns the first non-zero status of the batch (or error)
+// wait for a slot and deliver the scalars of every queued op; returns the first non-zero status (or error)
 int finish_slot(wm_ctx* ctx, Slot& s)
 {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(s.stream));
     drain_timers(ctx, s);
     int rc = WM_OK;
-    if (s.pending) {
-        for (int b = 0; b < s.pend_batch; b++) {
-            const Scal& h = s.scal_host[b];
-            if (s.pend_scalar) {
-                if (s.pending == 1) { if (h.status != WM_SINGULAR) s.pend_scalar[b] = h.a; }  // untouched when unsolvable (Watermark.cpp:164-165)
-                else s.pend_scalar[b] = h.status == 0 ? h.corr : 0.0f;                        // Watermark.cpp:246-247
+    for (const Slot::Pending& q : s.queue) {
+        for (int b = 0; b < q.batch; b++) {
+            const Scal& h = s.scal_host[q.off + b];
+            if (q.scalar) {
+                float* dst = q.scalar + (int64_t)b * q.sstride;
+                if (q.kind == 1) { if (h.status != WM_SINGULAR) *dst = h.a; }  // untouched when unsolvable (Watermark.cpp:164-165)
+                else *dst = h.status == 0 ? h.corr : 0.0f;                    // Watermark.cpp:246-247
             }
-            if (s.pend_status) s.pend_status[b] = h.status;
+            if (q.status) q.status[b] = h.status;
             if (h.status != 0 && rc == WM_OK) rc = h.status;
         }
     }
-    s.pending = 0;
-    s.pend_scalar = nullptr;
-    s.pend_status = nullptr;
+    s.queue.clear();
+    s.host_used = 0;
     return rc;
 }
 
@@ -705,6 +720,7 @@ int wm_set_option(wm_ctx* ctx, int option, int value)
 const char* wm_last_error(const wm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 float wm_strength_factor(const wm_ctx* ctx) { return ctx ? ctx->strength : 0.0f; }
 int wm_num_slots(const wm_ctx*) { return NSLOTS; }
+void* wm_get_stream(const wm_ctx* ctx, int slot) { return (ctx && slot >= 0 && slot < NSLOTS) ? (void*)ctx->slots[slot].stream : nullptr; }
 
 int wm_sync(wm_ctx* ctx, int slot)
 {
@@ -724,11 +740,10 @@ int wm_embed_batch(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* ba
 {
     if (!ctx) return WM_ERR_ARG;
     if (slot < 0 || slot >= NSLOTS) return fail(ctx, WM_ERR_ARG, "bad slot");
-    if (ctx->slots[slot].pending) { const int r = finish_slot(ctx, ctx->slots[slot]); if (r < 0) return r; }
     const int rc = do_embed(ctx, slot, in, base, out, in_stride, base_stride, out_stride, batch, mask);
     if (rc) return rc;
-    ctx->slots[slot].pend_scalar = a_host;
-    ctx->slots[slot].pend_status = status_host;
+    ctx->slots[slot].queue.back().scalar = a_host;
+    ctx->slots[slot].queue.back().status = status_host;
     return WM_OK;
 }
 
@@ -736,11 +751,10 @@ int wm_detect_batch(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stri
 {
     if (!ctx) return WM_ERR_ARG;
     if (slot < 0 || slot >= NSLOTS) return fail(ctx, WM_ERR_ARG, "bad slot");
-    if (ctx->slots[slot].pending) { const int r = finish_slot(ctx, ctx->slots[slot]); if (r < 0) return r; }
     const int rc = do_detect(ctx, slot, img, img_stride, batch, mask);
     if (rc) return rc;
-    ctx->slots[slot].pend_scalar = corr_host;
-    ctx->slots[slot].pend_status = status_host;
+    ctx->slots[slot].queue.back().scalar = corr_host;
+    ctx->slots[slot].queue.back().status = status_host;
     return WM_OK;
 }
 
@@ -774,7 +788,7 @@ int wm_embed_host(wm_ctx* ctx, const wm_image* in, const wm_image* base, wm_imag
     if (!ctx || !in || !out || !in->data || !out->data) return WM_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     Slot& s = ctx->slots[0];
-    if (s.pending) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+    if (!s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
     const wm_image* b = base ? base : in;
     const size_t nin = image_bytes(in, nullptr), nb = image_bytes(b, nullptr), nout = image_bytes(out, nullptr);
     int rc;
@@ -792,7 +806,7 @@ int wm_embed_host(wm_ctx* ctx, const wm_image* in, const wm_image* base, wm_imag
     dout.data = s.stage_out;
     rc = do_embed(ctx, 0, &din, &dbase, &dout, 0, 0, 0, 1, mask);
     if (rc) return rc;
-    s.pend_scalar = a_host;
+    s.queue.back().scalar = a_host;
     CU(cudaMemcpyAsync(out->data, s.stage_out, nout, cudaMemcpyDeviceToHost, s.stream));
     return finish_slot(ctx, s);
 }
@@ -802,7 +816,7 @@ int wm_detect_host(wm_ctx* ctx, const wm_image* img, int mask, float* corr_host)
     if (!ctx || !img || !img->data) return WM_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     Slot& s = ctx->slots[0];
-    if (s.pending) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+    if (!s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
     const size_t n = image_bytes(img, nullptr);
     int rc;
     if ((rc = ensure_stage(ctx, &s.stage_in, &s.stage_in_cap, n))) return rc;
@@ -811,7 +825,7 @@ int wm_detect_host(wm_ctx* ctx, const wm_image* img, int mask, float* corr_host)
     d.data = s.stage_in;
     rc = do_detect(ctx, 0, &d, 0, 1, mask);
     if (rc) return rc;
-    s.pend_scalar = corr_host;
+    s.queue.back().scalar = corr_host;
     return finish_slot(ctx, s);
 }
 
@@ -856,7 +870,7 @@ int wm_debug_plane(wm_ctx* ctx, const wm_image* img, int what, float* dst_dev)
     if ((rc = make_view(ctx, img, &v, false))) return rc;
     CU(cudaSetDevice(ctx->device));
     Slot& s = ctx->slots[0];
-    if (s.pending) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+    if (!s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
     const Geo g = geo(v.L, v.P);
     const Plan pl = plan(ctx, g, 1);
     if ((rc = ensure_slot(ctx, s, 1, std::max(pl.gx_stats, pl.gx_detect), pl.nsweep, pl.nframe))) return rc;
@@ -910,50 +924,66 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
     CU(cudaSetDevice(ctx->device));
     int rc;
     for (int i = 0; i < NSLOTS; i++)
-        if (ctx->slots[i].pending) { const int r = finish_slot(ctx, ctx->slots[i]); if (r < 0) return r; }
+        if (!ctx->slots[i].queue.empty()) { const int r = finish_slot(ctx, ctx->slots[i]); if (r < 0) return r; }
     const float nanv = nanf("");
+    const int64_t K = v->watermark_interval;
+    const int64_t i0 = (K - first_index % K) % K;  // first gated frame: (first_index + i) % K == 0 (main.cpp:346,395: global index)
+    const int64_t ngated = i0 < n_frames ? (n_frames - i0 + K - 1) / K : 0;
+    const cudaMemcpyKind through = v->frames_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToHost;
+    // frames between the gated ones: copied through without the row padding (main.cpp:362-366), no scalar
     for (int64_t i = 0; i < n_frames; i++) {
-        const int64_t gidx = first_index + i;
-        const bool gated = (gidx % v->watermark_interval) == 0;  // main.cpp:346,395 (global frame index)
-        const int si = (int)(i % NSLOTS);
+        if ((first_index + i) % K == 0) continue;
+        if (scalars) scalars[i] = nanv;
+        if (mode == WM_VIDEO_EMBED)
+            CU(cudaMemcpy2DAsync(out + i * ostride, Wd, frames + i * fstride, linesize, Wd, H, through, ctx->slots[i % NSLOTS].stream));
+    }
+    // gated frames: equally spaced in memory, so a run of them is ONE batched launch sequence (image index in
+    // blockIdx.y); runs go round-robin over the slots so copies, kernels and the per-frame solves of different runs overlap
+    const int64_t fbytes = H * Wd;
+    int64_t B = v->frames_on_device ? std::max<int64_t>(1, std::min<int64_t>(32, (64LL << 20) / fbytes)) : 4;
+    for (int64_t g = 0, run = 0; g < ngated; g += B, run++) {
+        const int nb = (int)std::min<int64_t>(B, ngated - g);
+        const int si = (int)(run % NSLOTS);
         Slot& s = ctx->slots[si];
-        if (s.pending) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
-        const uint8_t* src = frames + i * fstride;
-        uint8_t* dst = out ? out + i * ostride : nullptr;
-        if (!gated) {
-            if (mode == WM_VIDEO_EMBED) {  // copy-through, dropping the row padding (main.cpp:362-366)
-                CU(cudaMemcpy2DAsync(dst, Wd, src, linesize, Wd, H,
-                                     v->frames_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToHost, s.stream));
-                if (scalars) scalars[i] = nanv;
-            } else if (scalars) scalars[i] = nanv;
-            continue;
-        }
+        const int64_t i = i0 + g * K;
         wm_image fin;
         memset(&fin, 0, sizeof fin);
         fin.rows = H; fin.cols = Wd; fin.channels = 1; fin.layout = WM_ROW_MAJOR; fin.dtype = WM_U8;
+        int64_t in_stride;
         if (v->frames_on_device) {
-            fin.data = (void*)src; fin.ld = linesize;  // strided reads: no repack pass needed
+            fin.data = (void*)(frames + i * fstride); fin.ld = linesize;  // strided reads: no repack pass needed
+            in_stride = K * fstride;
         } else {
-            if ((rc = ensure_stage(ctx, &s.stage_in, &s.stage_in_cap, (size_t)(H * Wd)))) return rc;
-            CU(cudaMemcpy2DAsync(s.stage_in, Wd, src, linesize, Wd, H, cudaMemcpyHostToDevice, s.stream));  // repack on the fly
+            if (fbytes * nb > (int64_t)s.stage_in_cap && !s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+            if ((rc = ensure_stage(ctx, &s.stage_in, &s.stage_in_cap, (size_t)(fbytes * B)))) return rc;
+            for (int j = 0; j < nb; j++)  // H2D, dropping the row padding on the fly (main.cpp:348-353)
+                CU(cudaMemcpy2DAsync((uint8_t*)s.stage_in + j * fbytes, Wd, frames + (i + j * K) * fstride, linesize, Wd, H,
+                                     cudaMemcpyHostToDevice, s.stream));
             fin.data = s.stage_in; fin.ld = Wd;
+            in_stride = fbytes;
         }
         if (mode == WM_VIDEO_EMBED) {
             wm_image fout = fin;
             fout.ld = Wd;
-            if (v->frames_on_device) fout.data = dst;
+            int64_t out_stride;
+            if (v->frames_on_device) { fout.data = out + i * ostride; out_stride = K * ostride; }
             else {
-                if ((rc = ensure_stage(ctx, &s.stage_out, &s.stage_out_cap, (size_t)(H * Wd)))) return rc;
-                fout.data = s.stage_out;
+                if (fbytes * nb > (int64_t)s.stage_out_cap && !s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+                if ((rc = ensure_stage(ctx, &s.stage_out, &s.stage_out_cap, (size_t)(fbytes * B)))) return rc;
+                fout.data = s.stage_out; out_stride = fbytes;
             }
-            rc = do_embed(ctx, si, &fin, &fin, &fout, 0, 0, 0, 1, WM_MASK_ME);  // main.cpp:356,380
+            rc = do_embed(ctx, si, &fin, &fin, &fout, in_stride, in_stride, out_stride, nb, WM_MASK_ME);  // main.cpp:356,380
             if (rc) return rc;
-            if (!v->frames_on_device) CU(cudaMemcpyAsync(dst, s.stage_out, (size_t)(H * Wd), cudaMemcpyDeviceToHost, s.stream));
+            if (!v->frames_on_device)
+                for (int j = 0; j < nb; j++)
+                    CU(cudaMemcpyAsync(out + (i + j * K) * ostride, (uint8_t*)s.stage_out + j * fbytes, (size_t)fbytes,
+                                       cudaMemcpyDeviceToHost, s.stream));
         } else {
-            rc = do_detect(ctx, si, &fin, 0, 1, WM_MASK_ME);  // main.cpp:406
+            rc = do_detect(ctx, si, &fin, in_stride, nb, WM_MASK_ME);  // main.cpp:406
             if (rc) return rc;
         }
-        s.pend_scalar = scalars ? scalars + i : nullptr;
+        s.queue.back().scalar = scalars ? scalars + i : nullptr;
+        s.queue.back().sstride = K;
     }
     for (int i = 0; i < NSLOTS; i++) { const int r = finish_slot(ctx, ctx->slots[i]); if (r < 0) return r; }
     return n_frames;

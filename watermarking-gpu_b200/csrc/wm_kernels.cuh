@@ -31,6 +31,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace wm {
 
 constexpr int TP = 128;          // tile width  (contiguous pixels)
@@ -186,6 +188,87 @@ __device__ __forceinline__ void load_w_tile(float* __restrict__ wt, const float*
         *reinterpret_cast<float4*>(wt + r * TP + 4 * c) = v;
     }
 }
+
+// Register-prefetched variant of the plain loaders: issue() starts the global loads of a tile into registers (before the
+// current tile is computed), commit() converts and stores them to smem one iteration later, so the load latency hides
+// behind a whole tile of arithmetic.  Chunks that cannot be vector-loaded (frame, odd alignment) are read in commit().
+template <typename PixT, int NROWS>
+struct TilePrefetch {
+    static constexpr int CH = SW / 4, NCH = (NROWS * CH + NT - 1) / NT;
+    using Raw = typename std::conditional<sizeof(PixT) == 4, float4, uchar4>::type;
+    Raw v[NCH];
+    unsigned ok;
+    int l_org, p_org;
+    __device__ __forceinline__ void issue(const PixT* __restrict__ img, long long ld, int L, int P, int l_org_, int p_org_, bool vec_ok)
+    {
+        ok = 0; l_org = l_org_; p_org = p_org_;
+#pragma unroll
+        for (int k = 0; k < NCH; k++) {
+            const int idx = threadIdx.x + k * NT;
+            if (idx < NROWS * CH) {
+                const int r = idx / CH, c = idx - r * CH;
+                const int l = clampi(l_org + r, 0, L - 1), p = p_org + 4 * c;
+                if (vec_ok && p >= 0 && p + 3 < P) {
+                    v[k] = __ldg(reinterpret_cast<const Raw*>(img + (long long)l * ld + p));
+                    ok |= 1u << k;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void commit(float* __restrict__ tile, const PixT* __restrict__ img, long long ld, int L, int P)
+    {
+#pragma unroll
+        for (int k = 0; k < NCH; k++) {
+            const int idx = threadIdx.x + k * NT;
+            if (idx < NROWS * CH) {
+                float4 f;
+                if ((ok >> k) & 1) {
+                    if constexpr (sizeof(PixT) == 4) f = *reinterpret_cast<const float4*>(&v[k]);
+                    else f = make_float4((float)v[k].x, (float)v[k].y, (float)v[k].z, (float)v[k].w);
+                } else {
+                    const int r = idx / CH, c = idx - r * CH;
+                    const PixT* row = img + (long long)clampi(l_org + r, 0, L - 1) * ld;
+                    const int p = p_org + 4 * c;
+                    f.x = (float)row[clampi(p, 0, P - 1)];
+                    f.y = (float)row[clampi(p + 1, 0, P - 1)];
+                    f.z = (float)row[clampi(p + 2, 0, P - 1)];
+                    f.w = (float)row[clampi(p + 3, 0, P - 1)];
+                }
+                *reinterpret_cast<float4*>(tile + 4 * idx) = f;  // rows are dense: chunk idx sits at float 4*idx
+            }
+        }
+    }
+};
+// W tile without halo (TL x TP at (l0, p0)), prefetched the same way; cells outside the image are never used
+struct WTilePrefetch {
+    static constexpr int NCH = TL * (TP / 4) / NT;  // 4
+    float4 v[NCH];
+    __device__ __forceinline__ void issue(const float* __restrict__ W, int L, int P, int l0, int p0, bool vec_ok)
+    {
+#pragma unroll
+        for (int k = 0; k < NCH; k++) {
+            const int idx = threadIdx.x + k * NT;
+            const int l = l0 + (idx >> 5), p = p0 + 4 * (idx & 31);
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (l < L && p < P) {
+                const float* wr = W + (long long)l * P + p;
+                if (vec_ok && p + 3 < P) f = __ldg(reinterpret_cast<const float4*>(wr));
+                else {
+                    f.x = wr[0];
+                    if (p + 1 < P) f.y = wr[1];
+                    if (p + 2 < P) f.z = wr[2];
+                    if (p + 3 < P) f.w = wr[3];
+                }
+            }
+            v[k] = f;
+        }
+    }
+    __device__ __forceinline__ void commit(float* __restrict__ wt)
+    {
+#pragma unroll
+        for (int k = 0; k < NCH; k++) *reinterpret_cast<float4*>(wt + 4 * (threadIdx.x + k * NT)) = v[k];
+    }
+};
 
 // TMA tiles arrive zero-filled outside the image: overwrite those cells with the replicated edge value.
 // Sources are in-image cells, targets out-of-image cells, so one pass needs no intermediate barrier.
@@ -385,13 +468,21 @@ __device__ __forceinline__ float nvf_mask(const float* r0, const float* r1, cons
     return div_safe(var, __fadd_rn(1.0f, var));
 }
 
-// 6-float window (pixels p-1 .. p+4 of one smem line) for a thread's 4 pixels; sc = smem column of pixel 0
+// 6-float window (pixels p-1 .. p+4 of one smem line) for a thread's 4 pixels; sc = smem column of pixel 0.
+// The two halo pixels come from the neighbouring lanes' vectors (shuffles) instead of two scalar LDS whose 16-byte
+// lane stride makes them 4-way bank conflicted; only lanes 0 and 31 read their halo from smem (one LDS for both).
+// Must be called by all 32 lanes of a warp.
 __device__ __forceinline__ void load_win6(float (&w)[6], const float* line, int sc)
 {
-    w[0] = line[sc - 1];
+    const int lane = threadIdx.x & 31;
     const float4 v = *reinterpret_cast<const float4*>(line + sc);
-    w[1] = v.x; w[2] = v.y; w[3] = v.z; w[4] = v.w;
-    w[5] = line[sc + 4];
+    float l = __shfl_up_sync(0xffffffffu, v.w, 1);
+    float r = __shfl_down_sync(0xffffffffu, v.x, 1);
+    if (lane == 0 || lane == 31) {
+        const float h = line[sc + (lane == 0 ? -1 : 4)];
+        if (lane == 0) l = h; else r = h;
+    }
+    w[0] = l; w[1] = v.x; w[2] = v.y; w[3] = v.z; w[4] = v.w; w[5] = r;
 }
 
 // ================================================================================================
@@ -581,6 +672,8 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
 #pragma unroll
         for (int v = 0; v < NLAG; v++) { dacc[v] = 0.0; e0[v] = 0.0f; e1[v] = 0.0f; }
         StagePos<NST> pos;
+        TilePrefetch<PixT, TL + 2> pre;
+        if constexpr (!TMA) { if (it.t < a.ntiles) pre.issue(img, a.ld, L, P, it.tl * TL, it.tp * TP - HP, a.vec_ok != 0); }
         int k = 0;
         for (; it.t < a.ntiles; it.next(), k++) {
             const int l0 = it.tl * TL, p0 = it.tp * TP;
@@ -599,8 +692,9 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
                 pos.next();
             } else {
                 __syncthreads();
-                load_tile<PixT, TL + 2>(stage(0), img, a.ld, L, P, l0, p0 - HP, a.vec_ok != 0);
+                pre.commit(stage(0), img, a.ld, L, P);
                 __syncthreads();
+                if (it.t + step < a.ntiles) { int ptl, ptp; it.peek(1, ptl, ptp); pre.issue(img, a.ld, L, P, ptl * TL, ptp * TP - HP, a.vec_ok != 0); }
                 tile = stage(0);
             }
             const bool full = l0 >= 1 && l0 + TL <= L - 1 && p0 >= 1 && p0 + TP <= P - 1;
@@ -749,6 +843,14 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
                 if ((int)blockIdx.x + s * step < a.ntiles) { int ptl, ptp; it.peek(s, ptl, ptp); issue(ptl, ptp, s); }
     }
     StagePos<NST> pos;
+    TilePrefetch<PixT, TL + 2> pre;
+    WTilePrefetch wpre;
+    if constexpr (!TMA) {
+        if (it.t < a.ntiles) {
+            pre.issue(img, a.ld, a.L, a.P, it.tl * TL - 1, it.tp * TP - HP, a.vec_ok != 0);
+            wpre.issue(a.W, a.L, a.P, it.tl * TL, it.tp * TP, a.w_vec_ok != 0);
+        }
+    }
     for (; it.t < a.ntiles; it.next()) {
         const int l0 = it.tl * TL, p0 = it.tp * TP;
         float* tile;
@@ -766,9 +868,15 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
         } else {
             tile = stage(0);
             __syncthreads();
-            load_tile<PixT, TL + 2>(tile, img, a.ld, a.L, a.P, l0 - 1, p0 - HP, a.vec_ok != 0);
-            load_w_tile(tile + SZ_I34 / 4, a.W, a.L, a.P, l0, p0, a.w_vec_ok != 0);
+            pre.commit(tile, img, a.ld, a.L, a.P);
+            wpre.commit(tile + SZ_I34 / 4);
             __syncthreads();
+            if (it.t + step < a.ntiles) {
+                int ptl, ptp;
+                it.peek(1, ptl, ptp);
+                pre.issue(img, a.ld, a.L, a.P, ptl * TL - 1, ptp * TP - HP, a.vec_ok != 0);
+                wpre.issue(a.W, a.L, a.P, ptl * TL, ptp * TP, a.w_vec_ok != 0);
+            }
         }
         body(tile, tile + SZ_I34 / 4, l0, p0);
         if constexpr (TMA) __syncthreads();
@@ -1138,6 +1246,14 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
     }
     double ddot = 0.0, dnz = 0.0, dnu = 0.0;
     StagePos<NST> pos;
+    TilePrefetch<PixT, TL + 4> zpre;
+    TilePrefetch<float, TL + 2> wpre;
+    if constexpr (!TMA) {
+        if (it.t < a.ntiles) {
+            zpre.issue(img, a.ld, L, P, it.tl * TL - 2, it.tp * TP - HP, a.vec_ok != 0);
+            wpre.issue(a.W, P, L, P, it.tl * TL - 1, it.tp * TP - HP, a.w_vec_ok != 0);
+        }
+    }
     for (; it.t < a.ntiles; it.next()) {
         const int l0 = it.tl * TL, p0 = it.tp * TP;
         float *zt, *wt;  // zt: (TL+4) x SW lines l0-2 ..; wt: (TL+2) x SW lines l0-1 ..
@@ -1157,9 +1273,15 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
             zt = stage(0);
             wt = zt + SZ_I36 / 4;
             __syncthreads();
-            load_tile<PixT, TL + 4>(zt, img, a.ld, L, P, l0 - 2, p0 - HP, a.vec_ok != 0);
-            load_tile<float, TL + 2>(wt, a.W, P, L, P, l0 - 1, p0 - HP, a.w_vec_ok != 0);
+            zpre.commit(zt, img, a.ld, L, P);
+            wpre.commit(wt, a.W, P, L, P);
             __syncthreads();
+            if (it.t + step < a.ntiles) {
+                int ptl, ptp;
+                it.peek(1, ptl, ptp);
+                zpre.issue(img, a.ld, L, P, ptl * TL - 2, ptp * TP - HP, a.vec_ok != 0);
+                wpre.issue(a.W, P, L, P, ptl * TL - 1, ptp * TP - HP, a.w_vec_ok != 0);
+            }
         }
         float fd = 0.0f, fz = 0.0f, fu = 0.0f;
         if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true>(zt, wt, ut, c, ring_l, ring_p, l0, p0, L, P, fd, fz, fu);
