@@ -367,7 +367,7 @@ def main():
     for name, (n, tot_ms) in ktimes.items():
         if n == 0:
             continue
-        per_launch_px = npx * (nfr if kind == "image" else 1)
+        per_launch_px = npx * nfr * args.steps * {"rx_sweep": (3 if kind == "image" else 2), "embed_apply": 2 if kind == "image" else 1, "detect_apply": 2 if kind == "image" else 1}.get(name, 1) / n  # pixels one launch covers
         alg = ALG_BYTES[dtype][name] * per_launch_px
         avg_ms = tot_ms / n
         kern.append({"kernel": name, "launches": n, "avg_ms": avg_ms, "total_ms": tot_ms,

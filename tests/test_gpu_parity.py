@@ -483,3 +483,40 @@ def test_tma_and_plain_paths_agree(wmb, oracle, rows, cols):
         assert abs(res[(1, 1, wmb.ME)][0] - o["a"]) / o["a"] <= 1e-3
         assert np.abs(res[(1, 1, wmb.ME)][1] - o["out"]).max() <= 1e-4 * 255
     wm.close()
+
+
+@pytest.mark.parametrize("rows,cols,ls", [(64, 64, 64), (96, 160, 192), (270, 480, 480), (130, 264, 272)])
+def test_u8_tma_and_plain_paths_agree(wmb, oracle, rows, cols, ls):
+    """u8 frames resident on the device: TMA byte tiles + conversion pass vs the register-prefetched plain loader."""
+    n = 5
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    frames = np.zeros((n, rows, ls), np.uint8)
+    for i in range(n):
+        frames[i, :, :cols] = util.natural_image(rows, cols, seed=500 + i, integer=True)
+        frames[i, :, cols:] = 9
+    L = wmb.lib()
+    dfr = L.wm_dev_alloc(wm._h, frames.nbytes)
+    dout = L.wm_dev_alloc(wm._h, n * rows * cols)
+    L.wm_dev_upload(wm._h, dfr, frames.ctypes.data, frames.nbytes)
+    ctx = wmb.VideoProcessingContext(wm, rows, cols, 1, linesize=ls, frames_on_device=True)
+    ctx_o = wmb.VideoProcessingContext(wm, rows, cols, 1, linesize=cols, frames_on_device=True)
+    res = {}
+    for tma in (1, 0):
+        wm.set_option(wmb.OPT_USE_TMA, tma)
+        a = np.zeros(n, np.float32)
+        c = np.zeros(n, np.float32)
+        wmb.process_frames(ctx, wmb.VIDEO_EMBED, dfr, dout, 0, n, a)
+        out = np.zeros((n, rows, cols), np.uint8)
+        L.wm_dev_download(wm._h, out.ctypes.data, dout, out.nbytes)
+        wmb.process_frames(ctx_o, wmb.VIDEO_DETECT, dout, None, 0, n, c)
+        res[tma] = (a, out, c)
+    report("u8 tma_vs_plain %dx%d ls=%d a=%s corr=%s" % (rows, cols, ls, res[1][0][:2], res[1][2][:2]))
+    assert np.array_equal(res[1][0], res[0][0]) and np.array_equal(res[1][1], res[0][1]) and np.array_equal(res[1][2], res[0][2])
+    st, oo, oa = oracle.embed_frame_u8(frames[2], W, 40.0, oracle.ME, width=cols)
+    st2, oc = oracle.detect_frame_u8(oo, W, oracle.ME)
+    assert np.abs(res[1][1][2].astype(int) - oo.astype(int)).max() <= 1
+    assert abs(res[1][0][2] - oa) / oa <= 1e-3 and abs(res[1][2][2] - oc) / abs(oc) <= 1e-3
+    L.wm_dev_free(wm._h, dfr)
+    L.wm_dev_free(wm._h, dout)
+    wm.close()

@@ -267,23 +267,27 @@ EncodeTiledFn encode_fn()
     }();
     return fn;
 }
-// f32 tensor (pixel, line, image) with a (boxP x boxL x 1) box; out-of-bounds elements are zero-filled
-bool make_tmap(CUtensorMap* tm, const void* ptr, int P, int L, int B, long long ld, long long bstride, int boxP, int boxL)
+// f32 / u8 tensor (pixel, line, image) with a (boxP x boxL x 1) box; out-of-bounds elements are zero-filled.
+// boxP is given in f32 terms (SW or TP); u8 image boxes are U8_ROW (144) pixels wide so that the row is 16-byte sized.
+bool make_tmap(CUtensorMap* tm, int dtype, const void* ptr, int P, int L, int B, long long ld, long long bstride, int boxP, int boxL)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
+    const int es = dtype == WM_F32 ? 4 : 1;
     const cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)L, (cuuint64_t)std::max(B, 1)};
     const long long bs = (B > 1 && bstride > 0) ? bstride : (long long)L * ld;
-    const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)bs * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)boxP, (cuuint32_t)boxL, 1};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * es, (cuuint64_t)bs * es};
+    const cuuint32_t box[3] = {(cuuint32_t)(dtype == WM_F32 ? boxP : U8_ROW), (cuuint32_t)boxL, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return fn(tm, dtype == WM_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), dims,
+              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 bool tma_ok(const wm_ctx* ctx, const View& v, long long bstride, int batch)
 {
-    return ctx->opt_tma && v.dtype == WM_F32 && ((uintptr_t)v.ptr % 16 == 0) && (v.ld % 4 == 0) && (v.P % 4 == 0) &&
-           (batch == 1 || bstride % 4 == 0) && encode_fn() != nullptr;
+    const long long al = v.dtype == WM_F32 ? 4 : 16;  // strides must be multiples of 16 bytes
+    return ctx->opt_tma && ((uintptr_t)v.ptr % 16 == 0) && (v.ld % al == 0) && (v.P % 4 == 0) &&
+           (batch == 1 || bstride % al == 0) && encode_fn() != nullptr;
 }
 
 // ---- kernel dispatch over (pixel type, out type, mask, transposed, TMA) ----
@@ -304,30 +308,31 @@ void set_smem(K kernel, int bytes)
 void launch_sweep(int dtype, bool fp16, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const SweepArgs& a)
 {
     if (dtype == WM_F32) {
-        if (tma) { if (fp16) WM_LAUNCH((k_sweep<float, true, true>), sweep_smem(true), tmI, a); else WM_LAUNCH((k_sweep<float, false, true>), sweep_smem(true), tmI, a); }
-        else { if (fp16) WM_LAUNCH((k_sweep<float, true, false>), sweep_smem(false), tmI, a); else WM_LAUNCH((k_sweep<float, false, false>), sweep_smem(false), tmI, a); }
+        if (tma) { if (fp16) WM_LAUNCH((k_sweep<float, true, true>), sweep_smem(true, false), tmI, a); else WM_LAUNCH((k_sweep<float, false, true>), sweep_smem(true, false), tmI, a); }
+        else { if (fp16) WM_LAUNCH((k_sweep<float, true, false>), sweep_smem(false, false), tmI, a); else WM_LAUNCH((k_sweep<float, false, false>), sweep_smem(false, false), tmI, a); }
     } else {
-        if (fp16) WM_LAUNCH((k_sweep<uint8_t, true, false>), sweep_smem(false), tmI, a); else WM_LAUNCH((k_sweep<uint8_t, false, false>), sweep_smem(false), tmI, a);
+        if (tma) { if (fp16) WM_LAUNCH((k_sweep<uint8_t, true, true>), sweep_smem(true, true), tmI, a); else WM_LAUNCH((k_sweep<uint8_t, false, true>), sweep_smem(true, true), tmI, a); }
+        else { if (fp16) WM_LAUNCH((k_sweep<uint8_t, true, false>), sweep_smem(false, true), tmI, a); else WM_LAUNCH((k_sweep<uint8_t, false, false>), sweep_smem(false, true), tmI, a); }
     }
 }
 
 template <typename PixT, bool TMA>
 void launch_stats_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
 {
-    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_stats<PixT, 0, true, TMA>), embed_smem(TMA), tmI, tmW, a); else WM_LAUNCH((k_stats<PixT, 0, false, TMA>), embed_smem(TMA), tmI, tmW, a); }
-    else { if (tr) WM_LAUNCH((k_stats<PixT, 1, true, TMA>), embed_smem(TMA), tmI, tmW, a); else WM_LAUNCH((k_stats<PixT, 1, false, TMA>), embed_smem(TMA), tmI, tmW, a); }
+    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_stats<PixT, 0, true, TMA>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_stats<PixT, 0, false, TMA>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
+    else { if (tr) WM_LAUNCH((k_stats<PixT, 1, true, TMA>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_stats<PixT, 1, false, TMA>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
 }
 void launch_stats(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
 {
     if (dtype == WM_F32) { if (tma) launch_stats_t<float, true>(mask, tr, grid, st, tmI, tmW, a); else launch_stats_t<float, false>(mask, tr, grid, st, tmI, tmW, a); }
-    else launch_stats_t<uint8_t, false>(mask, tr, grid, st, tmI, tmW, a);
+    else { if (tma) launch_stats_t<uint8_t, true>(mask, tr, grid, st, tmI, tmW, a); else launch_stats_t<uint8_t, false>(mask, tr, grid, st, tmI, tmW, a); }
 }
 
 template <typename PixT, typename OutT, bool TMA, bool SB>
 void launch_apply_s(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
 {
-    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 0, true, TMA, SB>), embed_smem(TMA), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 0, false, TMA, SB>), embed_smem(TMA), tmI, tmW, a); }
-    else { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 1, true, TMA, SB>), embed_smem(TMA), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 1, false, TMA, SB>), embed_smem(TMA), tmI, tmW, a); }
+    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 0, true, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 0, false, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
+    else { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 1, true, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 1, false, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
 }
 template <typename PixT, typename OutT, bool TMA>
 void launch_apply_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
@@ -342,20 +347,21 @@ void launch_apply(int in_dtype, int out_dtype, int mask, bool tr, bool tma, dim3
         if (out_dtype == WM_F32) { if (tma) launch_apply_t<float, float, true>(mask, tr, grid, st, tmI, tmW, a); else launch_apply_t<float, float, false>(mask, tr, grid, st, tmI, tmW, a); }
         else { if (tma) launch_apply_t<float, uint8_t, true>(mask, tr, grid, st, tmI, tmW, a); else launch_apply_t<float, uint8_t, false>(mask, tr, grid, st, tmI, tmW, a); }
     } else {
-        if (out_dtype == WM_F32) launch_apply_t<uint8_t, float, false>(mask, tr, grid, st, tmI, tmW, a); else launch_apply_t<uint8_t, uint8_t, false>(mask, tr, grid, st, tmI, tmW, a);
+        if (out_dtype == WM_F32) { if (tma) launch_apply_t<uint8_t, float, true>(mask, tr, grid, st, tmI, tmW, a); else launch_apply_t<uint8_t, float, false>(mask, tr, grid, st, tmI, tmW, a); }
+        else { if (tma) launch_apply_t<uint8_t, uint8_t, true>(mask, tr, grid, st, tmI, tmW, a); else launch_apply_t<uint8_t, uint8_t, false>(mask, tr, grid, st, tmI, tmW, a); }
     }
 }
 
 template <typename PixT, bool TMA>
 void launch_detect_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
 {
-    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_detect<PixT, 0, true, TMA>), detect_smem(TMA), tmZ, tmW, a); else WM_LAUNCH((k_detect<PixT, 0, false, TMA>), detect_smem(TMA), tmZ, tmW, a); }
-    else { if (tr) WM_LAUNCH((k_detect<PixT, 1, true, TMA>), detect_smem(TMA), tmZ, tmW, a); else WM_LAUNCH((k_detect<PixT, 1, false, TMA>), detect_smem(TMA), tmZ, tmW, a); }
+    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_detect<PixT, 0, true, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); else WM_LAUNCH((k_detect<PixT, 0, false, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); }
+    else { if (tr) WM_LAUNCH((k_detect<PixT, 1, true, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); else WM_LAUNCH((k_detect<PixT, 1, false, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); }
 }
 void launch_detect(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
 {
     if (dtype == WM_F32) { if (tma) launch_detect_t<float, true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_t<float, false>(mask, tr, grid, st, tmZ, tmW, a); }
-    else launch_detect_t<uint8_t, false>(mask, tr, grid, st, tmZ, tmW, a);
+    else { if (tma) launch_detect_t<uint8_t, true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_t<uint8_t, false>(mask, tr, grid, st, tmZ, tmW, a); }
 }
 
 // copy the op's per-image scalars into the slot's pinned ring (in stream order) and queue their delivery
@@ -396,7 +402,7 @@ int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int ba
     CUtensorMap tmI;
     memset(&tmI, 0, sizeof tmI);
     bool tma = tma_ok(ctx, v, bstride, batch);
-    if (tma) tma = make_tmap(&tmI, v.ptr, g.P, g.L, batch, v.ld, bstride, SW, TL + 2);
+    if (tma) tma = make_tmap(&tmI, v.dtype, v.ptr, g.P, g.L, batch, v.ld, bstride, SW, TL + 2);
     {
         KTimer t(ctx, s, WM_K_SWEEP);
         launch_sweep(v.dtype, ctx->opt_fp16 != 0, tma, dim3(pl.nsweep + pl.nframe, batch), s.stream, tmI, a);
@@ -454,8 +460,8 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     memset(&tmI, 0, sizeof tmI);
     memset(&tmW, 0, sizeof tmW);
     bool tma = tma_ok(ctx, vi, in_stride, batch);
-    if (tma) tma = make_tmap(&tmI, vi.ptr, g.P, g.L, batch, vi.ld, in_stride, SW, TL + 2) &&
-                   make_tmap(&tmW, W, g.P, g.L, 1, g.P, 0, TP, TL);
+    if (tma) tma = make_tmap(&tmI, vi.dtype, vi.ptr, g.P, g.L, batch, vi.ld, in_stride, SW, TL + 2) &&
+                   make_tmap(&tmW, WM_F32, W, g.P, g.L, 1, g.P, 0, TP, TL);
     {
         KTimer t(ctx, s, mask == WM_MASK_ME ? WM_K_ME_STATS : WM_K_NVF_STATS);
         launch_stats(vi.dtype, mask, vi.transposed, tma, dim3(pl.gx_stats, batch), s.stream, tmI, tmW, ea);
@@ -499,8 +505,8 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     memset(&tmZ, 0, sizeof tmZ);
     memset(&tmW, 0, sizeof tmW);
     bool tma = tma_ok(ctx, v, img_stride, batch);
-    if (tma) tma = make_tmap(&tmZ, v.ptr, g.P, g.L, batch, v.ld, img_stride, SW, TL + 4) &&
-                   make_tmap(&tmW, W, g.P, g.L, 1, g.P, 0, SW, TL + 2);
+    if (tma) tma = make_tmap(&tmZ, v.dtype, v.ptr, g.P, g.L, batch, v.ld, img_stride, SW, TL + 4) &&
+                   make_tmap(&tmW, WM_F32, W, g.P, g.L, 1, g.P, 0, SW, TL + 2);
     {
         KTimer t(ctx, s, WM_K_DETECT);
         launch_detect(v.dtype, mask, v.transposed, tma, dim3(pl.gx_detect, batch), s.stream, tmZ, tmW, da);

@@ -44,18 +44,28 @@ constexpr int NLAG = 13;         // distinct lags of the upper triangle of Rx
 constexpr int NFRM = 44;         // frame partials: 8 rx + 36 Rx (upper triangle)
 constexpr int NTOT = NLAG + NFRM;
 
-constexpr int align128(int x) { return (x + 127) & ~127; }
+__host__ __device__ constexpr int align128(int x) { return (x + 127) & ~127; }
 // shared-memory stage layouts (bytes)
 constexpr int SZ_I34 = align128((TL + 2) * SW * 4);  // image tile with 1 (or 0+2) halo lines
 constexpr int SZ_I36 = align128((TL + 4) * SW * 4);  // image tile with 2 halo lines (detect)
 constexpr int SZ_WT = TL * TP * 4;                   // W tile, no halo
-constexpr int SWEEP_STAGE = SZ_I34;
-constexpr int EMBED_STAGE = SZ_I34 + SZ_WT;
-constexpr int DETECT_STAGE = SZ_I36 + SZ_I34;        // Z (halo 2) + W (halo 1)
+// u8 frames through TMA: the box starts 16 pixels left of the tile so that its first byte is 16-byte aligned in global
+// memory like the f32 boxes are (p0 is a multiple of 128), and is 160 bytes wide (pixels p0-16 .. p0+143; 136 used from
+// offset U8_OFF); it lands as bytes and a conversion pass widens it into the f32 work tile the arithmetic reads
+constexpr int U8_ROW = 160, U8_LEFT = 16, U8_OFF = U8_LEFT - HP;
+constexpr int U8_I34 = align128((TL + 2) * U8_ROW);
+constexpr int U8_I36 = align128((TL + 4) * U8_ROW);
 constexpr int SWEEP_NST = 3, EMBED_NST = 3, DETECT_NST = 2;
-constexpr int sweep_smem(bool tma) { return (tma ? SWEEP_NST : 1) * SWEEP_STAGE; }
-constexpr int embed_smem(bool tma) { return (tma ? EMBED_NST : 1) * EMBED_STAGE; }
-constexpr int detect_smem(bool tma) { return (tma ? DETECT_NST : 1) * DETECT_STAGE + SZ_I34; }  // + u tile
+// dynamic shared memory per kernel: [NST stages][work tiles]; with f32 TMA the stage IS the work tile
+__host__ __device__ constexpr int sweep_stage(bool u8) { return u8 ? U8_I34 : SZ_I34; }
+__host__ __device__ constexpr int embed_stage(bool u8) { return (u8 ? U8_I34 : SZ_I34) + SZ_WT; }
+__host__ __device__ constexpr int detect_stage(bool u8) { return (u8 ? U8_I36 : SZ_I36) + SZ_I34; }  // Z (halo 2) + W (halo 1)
+constexpr int sweep_smem(bool tma, bool u8) { return tma ? SWEEP_NST * sweep_stage(u8) + (u8 ? SZ_I34 : 0) : SZ_I34; }
+constexpr int embed_smem(bool tma, bool u8) { return tma ? EMBED_NST * embed_stage(u8) + (u8 ? SZ_I34 : 0) : SZ_I34 + SZ_WT; }
+constexpr int detect_smem(bool tma, bool u8)  // + u tile
+{
+    return (tma ? DETECT_NST * detect_stage(u8) + (u8 ? SZ_I36 : 0) : SZ_I36 + SZ_I34) + SZ_I34;
+}
 
 // per-image scalars living in device memory (one per batch entry), mirrored to pinned host memory
 struct Scal {
@@ -189,6 +199,21 @@ __device__ __forceinline__ void load_w_tile(float* __restrict__ wt, const float*
     }
 }
 
+// global loads pinned in program order (asm volatile): ptxas otherwise sinks read-only loads down to their first use,
+// i.e. past the barriers and the tile arithmetic they are meant to overlap with
+__device__ __forceinline__ float4 ld_pinned(const float4* p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uchar4 ld_pinned(const uchar4* p)
+{
+    unsigned u;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(u) : "l"(p) : "memory");
+    return *reinterpret_cast<uchar4*>(&u);
+}
+
 // Register-prefetched variant of the plain loaders: issue() starts the global loads of a tile into registers (before the
 // current tile is computed), commit() converts and stores them to smem one iteration later, so the load latency hides
 // behind a whole tile of arithmetic.  Chunks that cannot be vector-loaded (frame, odd alignment) are read in commit().
@@ -209,7 +234,7 @@ struct TilePrefetch {
                 const int r = idx / CH, c = idx - r * CH;
                 const int l = clampi(l_org + r, 0, L - 1), p = p_org + 4 * c;
                 if (vec_ok && p >= 0 && p + 3 < P) {
-                    v[k] = __ldg(reinterpret_cast<const Raw*>(img + (long long)l * ld + p));
+                    v[k] = ld_pinned(reinterpret_cast<const Raw*>(img + (long long)l * ld + p));
                     ok |= 1u << k;
                 }
             }
@@ -252,7 +277,7 @@ struct WTilePrefetch {
             float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
             if (l < L && p < P) {
                 const float* wr = W + (long long)l * P + p;
-                if (vec_ok && p + 3 < P) f = __ldg(reinterpret_cast<const float4*>(wr));
+                if (vec_ok && p + 3 < P) f = ld_pinned(reinterpret_cast<const float4*>(wr));
                 else {
                     f.x = wr[0];
                     if (p + 1 < P) f.y = wr[1];
@@ -269,6 +294,18 @@ struct WTilePrefetch {
         for (int k = 0; k < NCH; k++) *reinterpret_cast<float4*>(wt + 4 * (threadIdx.x + k * NT)) = v[k];
     }
 };
+
+// u8 TMA stage (rows of U8_ROW bytes) -> f32 work tile (rows of SW floats)
+template <int NROWS>
+__device__ __forceinline__ void convert_u8_tile(const unsigned char* __restrict__ src, float* __restrict__ dst)
+{
+    constexpr int CH = SW / 4;
+    for (int idx = threadIdx.x; idx < NROWS * CH; idx += NT) {
+        const int r = idx / CH, c = idx - r * CH;
+        const uchar4 u = *reinterpret_cast<const uchar4*>(src + r * U8_ROW + U8_OFF + 4 * c);
+        *reinterpret_cast<float4*>(dst + 4 * idx) = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+    }
+}
 
 // TMA tiles arrive zero-filled outside the image: overwrite those cells with the replicated edge value.
 // Sources are in-image cells, targets out-of-image cells, so one pass needs no intermediate barrier.
@@ -638,10 +675,10 @@ __device__ __forceinline__ void sweep_tile(const float* __restrict__ tile, int l
 template <typename PixT, bool FP16, bool TMA>
 __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtensorMap tmI, const SweepArgs a)
 {
-    static_assert(!TMA || sizeof(PixT) == 4, "TMA path is f32 only");
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * NFRM];
     __shared__ __align__(8) uint64_t bars[SWEEP_NST];
+    constexpr bool U8T = TMA && sizeof(PixT) == 1;
     const int b = blockIdx.y;
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     const int L = a.L, P = a.P;
@@ -651,10 +688,12 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
     {
         const int sb = blockIdx.x, step = a.nsweep;
         constexpr int NST = TMA ? SWEEP_NST : 1;
-        auto stage = [&](int s) { return reinterpret_cast<float*>(dsm + (size_t)s * SWEEP_STAGE); };
+        constexpr int STG = sweep_stage(U8T);
+        auto stage = [&](int s) { return dsm + (size_t)s * STG; };
+        float* const work = reinterpret_cast<float*>(dsm + (TMA ? (size_t)NST * STG : 0));  // u8 TMA / plain path
         auto issue = [&](int tl, int tp, int s) {  // thread 0 only
-            mbar_expect_tx(&bars[s], (TL + 2) * SW * 4);
-            tma_load_3d(stage(s), &tmI, tp * TP - HP, tl * TL, b, &bars[s]);
+            mbar_expect_tx(&bars[s], U8T ? (TL + 2) * U8_ROW : (TL + 2) * SW * 4);
+            tma_load_3d(stage(s), &tmI, tp * TP - (U8T ? U8_LEFT : HP), tl * TL, b, &bars[s]);
         };
         TileIter it(sb, step, a.tiles_p);
         if constexpr (TMA) {
@@ -686,16 +725,18 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
                     issue(ptl, ptp, pos.ahead(NST - 1));
                 }
                 mbar_wait(&bars[pos.s], pos.ph);
-                float* tw = stage(pos.s);
+                float* tw;
+                if constexpr (U8T) { tw = work; convert_u8_tile<TL + 2>(stage(pos.s), tw); __syncthreads(); }
+                else tw = reinterpret_cast<float*>(stage(pos.s));
                 if (tile_on_frame<TL + 2>(l0, p0 - HP, L, P)) { fix_border<TL + 2>(tw, l0, p0 - HP, L, P); __syncthreads(); }
                 tile = tw;
                 pos.next();
             } else {
                 __syncthreads();
-                pre.commit(stage(0), img, a.ld, L, P);
+                pre.commit(work, img, a.ld, L, P);
                 __syncthreads();
                 if (it.t + step < a.ntiles) { int ptl, ptp; it.peek(1, ptl, ptp); pre.issue(img, a.ld, L, P, ptl * TL, ptp * TP - HP, a.vec_ok != 0); }
-                tile = stage(0);
+                tile = work;
             }
             const bool full = l0 >= 1 && l0 + TL <= L - 1 && p0 >= 1 && p0 + TP <= P - 1;
             if (full) sweep_tile<FP16, true>(tile, l0, p0, L, P, e0, e1);
@@ -823,13 +864,16 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
                                                 unsigned char* dsm, uint64_t* bars, Body body)
 {
     constexpr int NST = TMA ? EMBED_NST : 1;
+    constexpr bool U8T = TMA && sizeof(PixT) == 1;
+    constexpr int STG = embed_stage(U8T), IPART = U8T ? U8_I34 : SZ_I34;
     const int b = blockIdx.y, step = gridDim.x;
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
-    auto stage = [&](int s) { return reinterpret_cast<float*>(dsm + (size_t)s * EMBED_STAGE); };
+    auto stage = [&](int s) { return dsm + (size_t)s * STG; };
+    float* const work = reinterpret_cast<float*>(dsm + (size_t)NST * STG);  // u8 TMA only
     auto issue = [&](int tl, int tp, int s) {  // thread 0 only
-        mbar_expect_tx(&bars[s], (TL + 2) * SW * 4 + SZ_WT);
-        tma_load_3d(stage(s), tmI, tp * TP - HP, tl * TL - 1, b, &bars[s]);
-        tma_load_3d(reinterpret_cast<unsigned char*>(stage(s)) + SZ_I34, tmW, tp * TP, tl * TL, 0, &bars[s]);
+        mbar_expect_tx(&bars[s], (U8T ? (TL + 2) * U8_ROW : (TL + 2) * SW * 4) + SZ_WT);
+        tma_load_3d(stage(s), tmI, tp * TP - (U8T ? U8_LEFT : HP), tl * TL - 1, b, &bars[s]);
+        tma_load_3d(stage(s) + IPART, tmW, tp * TP, tl * TL, 0, &bars[s]);
     };
     TileIter it(blockIdx.x, step, a.tiles_p);
     if constexpr (TMA) {
@@ -853,7 +897,7 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
     }
     for (; it.t < a.ntiles; it.next()) {
         const int l0 = it.tl * TL, p0 = it.tp * TP;
-        float* tile;
+        float *tile, *wtile;
         if constexpr (TMA) {
             if (threadIdx.x == 0 && it.t + (NST - 1) * step < a.ntiles) {
                 int ptl, ptp;
@@ -862,14 +906,17 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
                 issue(ptl, ptp, pos.ahead(NST - 1));
             }
             mbar_wait(&bars[pos.s], pos.ph);
-            tile = stage(pos.s);
+            wtile = reinterpret_cast<float*>(stage(pos.s) + IPART);
+            if constexpr (U8T) { tile = work; convert_u8_tile<TL + 2>(stage(pos.s), tile); __syncthreads(); }
+            else tile = reinterpret_cast<float*>(stage(pos.s));
             pos.next();
             if (tile_on_frame<TL + 2>(l0 - 1, p0 - HP, a.L, a.P)) { fix_border<TL + 2>(tile, l0 - 1, p0 - HP, a.L, a.P); __syncthreads(); }
         } else {
-            tile = stage(0);
+            tile = reinterpret_cast<float*>(dsm);
+            wtile = tile + SZ_I34 / 4;
             __syncthreads();
             pre.commit(tile, img, a.ld, a.L, a.P);
-            wpre.commit(tile + SZ_I34 / 4);
+            wpre.commit(wtile);
             __syncthreads();
             if (it.t + step < a.ntiles) {
                 int ptl, ptp;
@@ -878,7 +925,7 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
                 wpre.issue(a.W, a.L, a.P, ptl * TL, ptp * TP, a.w_vec_ok != 0);
             }
         }
-        body(tile, tile + SZ_I34 / 4, l0, p0);
+        body(tile, wtile, l0, p0);
         if constexpr (TMA) __syncthreads();
     }
 }
@@ -918,7 +965,6 @@ template <typename PixT, int MASK, bool TR, bool TMA>
 __global__ void __launch_bounds__(NT, 2) k_stats(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
                                                  const EmbedArgs a)
 {
-    static_assert(!TMA || sizeof(PixT) == 4, "TMA path is f32 only");
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * 2];
     __shared__ __align__(8) uint64_t bars[EMBED_NST];
@@ -1020,7 +1066,6 @@ template <typename PixT, typename OutT, int MASK, bool TR, bool TMA, bool SB>
 __global__ void __launch_bounds__(NT, 2) k_apply(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
                                                  const EmbedArgs a)
 {
-    static_assert(!TMA || sizeof(PixT) == 4, "TMA path is f32 only");
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ __align__(8) uint64_t bars[EMBED_NST];
     const int b = blockIdx.y;
@@ -1200,12 +1245,14 @@ template <typename PixT, int MASK, bool TR, bool TMA>
 __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW,
                                                   const DetectArgs a)
 {
-    static_assert(!TMA || sizeof(PixT) == 4, "TMA path is f32 only");
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * 3];
     __shared__ __align__(8) uint64_t bars[DETECT_NST];
     constexpr int NST = TMA ? DETECT_NST : 1;
-    float* ut = reinterpret_cast<float*>(dsm + (size_t)NST * DETECT_STAGE);  // (TL+2) x SW, lines l0-1 .. l0+TL
+    constexpr bool U8T = TMA && sizeof(PixT) == 1;
+    constexpr int STG = TMA ? detect_stage(U8T) : SZ_I36 + SZ_I34, ZPART = U8T ? U8_I36 : SZ_I36;
+    float* const zwork = reinterpret_cast<float*>(dsm + (size_t)NST * STG);                        // u8 TMA only
+    float* const ut = reinterpret_cast<float*>(dsm + (size_t)NST * STG + (U8T ? SZ_I36 : 0));      // (TL+2) x SW, lines l0-1 .. l0+TL
     const int b = blockIdx.y;
     Scal* sc = a.scal + b;
     if (sc->status != 0) return;  // singular: corr = 0 was written by the sweep
@@ -1215,11 +1262,11 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
     float c[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) c[k] = sc->coef[k];
-    auto stage = [&](int s) { return reinterpret_cast<float*>(dsm + (size_t)s * DETECT_STAGE); };
+    auto stage = [&](int s) { return dsm + (size_t)s * STG; };
     auto issue = [&](int tl, int tp, int s) {  // thread 0 only
-        mbar_expect_tx(&bars[s], (TL + 4) * SW * 4 + (TL + 2) * SW * 4);
-        tma_load_3d(stage(s), &tmZ, tp * TP - HP, tl * TL - 2, b, &bars[s]);
-        tma_load_3d(reinterpret_cast<unsigned char*>(stage(s)) + SZ_I36, &tmW, tp * TP - HP, tl * TL - 1, 0, &bars[s]);
+        mbar_expect_tx(&bars[s], (U8T ? (TL + 4) * U8_ROW : (TL + 4) * SW * 4) + (TL + 2) * SW * 4);
+        tma_load_3d(stage(s), &tmZ, tp * TP - (U8T ? U8_LEFT : HP), tl * TL - 2, b, &bars[s]);
+        tma_load_3d(stage(s) + ZPART, &tmW, tp * TP - HP, tl * TL - 1, 0, &bars[s]);
     };
     TileIter it(blockIdx.x, step, a.tiles_p);
     if constexpr (TMA) {
@@ -1265,12 +1312,13 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
                 issue(ptl, ptp, pos.ahead(NST - 1));
             }
             mbar_wait(&bars[pos.s], pos.ph);
-            zt = stage(pos.s);
-            wt = zt + SZ_I36 / 4;
+            wt = reinterpret_cast<float*>(stage(pos.s) + ZPART);
+            if constexpr (U8T) { zt = zwork; convert_u8_tile<TL + 4>(stage(pos.s), zt); __syncthreads(); }
+            else zt = reinterpret_cast<float*>(stage(pos.s));
             pos.next();
             if (tile_on_frame<TL + 4>(l0 - 2, p0 - HP, L, P)) { fix_border<TL + 4>(zt, l0 - 2, p0 - HP, L, P); __syncthreads(); }
         } else {
-            zt = stage(0);
+            zt = reinterpret_cast<float*>(dsm);
             wt = zt + SZ_I36 / 4;
             __syncthreads();
             zpre.commit(zt, img, a.ld, L, P);
