@@ -13,6 +13,6 @@ for line in sys.stdin:
     nf = d["config"]["frames_per_step"]
     print(round(d["value"]), d["unit"], "ms/step", round(d["ms_per_step"], 3), "frac", round(d["step_frac_of_peak"], 3), d["clocks"])
     for k in d["kernels"]:
-        per = k["total_ms"] * 1000 / d["steps"] / nf
-        print("   %-13s launches %4d  avg %8.1f us  %6.2f us/frame/step  %6.0f GB/s" % (k["kernel"], k["launches"], k["avg_ms"] * 1000, per, k["achieved_gbs"]))
+        print("   %-13s launches %4d  avg %8.1f us  %6.0f GB/s (%.0f%% of peak)" % (
+            k["kernel"], k["launches"], k["avg_ms"] * 1000, k["achieved_gbs"], 100 * k["achieved_gbs"] / d["roofline"]["peak"]))
     print("   roofline", d["roofline"]["kernel"], round(d["roofline"]["frac"], 3), "| e2e", d["e2e"] and round(d["e2e"]["value"]), "| launches", d["gpu_launches"], "| cpu", d["cpu_baseline"] and round(d["cpu_baseline"]["value"], 1))

@@ -69,7 +69,7 @@ struct wm_ctx {
     float psnr = 0.f, strength = 0.f;
     std::shared_ptr<WShared> w;
     Slot slots[NSLOTS];
-    int opt_fp16 = 1, opt_timing = 0, opt_tma = 1;
+    int opt_fp16 = 1, opt_timing = 0, opt_tma = 1, opt_serial = 0;
     bool inject_coef = false;
     float injected[8];
     std::string err;
@@ -719,6 +719,7 @@ int wm_set_option(wm_ctx* ctx, int option, int value)
     case WM_OPT_FP16_PRODUCTS: ctx->opt_fp16 = value != 0; return WM_OK;
     case WM_OPT_KERNEL_TIMING: ctx->opt_timing = value != 0; return WM_OK;
     case WM_OPT_USE_TMA: ctx->opt_tma = value != 0; return WM_OK;
+    case WM_OPT_SERIAL_SLOTS: ctx->opt_serial = value != 0; return WM_OK;
     default: return fail(ctx, WM_ERR_ARG, "unknown option");
     }
 }
@@ -949,7 +950,7 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
     int64_t B = v->frames_on_device ? std::max<int64_t>(1, std::min<int64_t>(32, (64LL << 20) / fbytes)) : 4;
     for (int64_t g = 0, run = 0; g < ngated; g += B, run++) {
         const int nb = (int)std::min<int64_t>(B, ngated - g);
-        const int si = (int)(run % NSLOTS);
+        const int si = ctx->opt_serial ? 0 : (int)(run % NSLOTS);
         Slot& s = ctx->slots[si];
         const int64_t i = i0 + g * K;
         wm_image fin;

@@ -55,12 +55,12 @@ constexpr int SZ_WT = TL * TP * 4;                   // W tile, no halo
 constexpr int U8_ROW = 160, U8_LEFT = 16, U8_OFF = U8_LEFT - HP;
 constexpr int U8_I34 = align128((TL + 2) * U8_ROW);
 constexpr int U8_I36 = align128((TL + 4) * U8_ROW);
-constexpr int SWEEP_NST = 3, EMBED_NST = 3, DETECT_NST = 2;
+constexpr int SWEEP_NST = 3, SWEEP_NST_U8 = 4, EMBED_NST = 3, DETECT_NST = 2;
 // dynamic shared memory per kernel: [NST stages][work tiles]; with f32 TMA the stage IS the work tile
 __host__ __device__ constexpr int sweep_stage(bool u8) { return u8 ? U8_I34 : SZ_I34; }
 __host__ __device__ constexpr int embed_stage(bool u8) { return (u8 ? U8_I34 : SZ_I34) + SZ_WT; }
 __host__ __device__ constexpr int detect_stage(bool u8) { return (u8 ? U8_I36 : SZ_I36) + SZ_I34; }  // Z (halo 2) + W (halo 1)
-constexpr int sweep_smem(bool tma, bool u8) { return tma ? SWEEP_NST * sweep_stage(u8) + (u8 ? SZ_I34 : 0) : SZ_I34; }
+constexpr int sweep_smem(bool tma, bool u8) { return tma ? (u8 ? SWEEP_NST_U8 * sweep_stage(true) + SZ_I34 : SWEEP_NST * sweep_stage(false)) : SZ_I34; }
 constexpr int embed_smem(bool tma, bool u8) { return tma ? EMBED_NST * embed_stage(u8) + (u8 ? SZ_I34 : 0) : SZ_I34 + SZ_WT; }
 constexpr int detect_smem(bool tma, bool u8)  // + u tile
 {
@@ -307,6 +307,27 @@ __device__ __forceinline__ void convert_u8_tile(const unsigned char* __restrict_
     }
 }
 
+// u8 TMA stage -> fp16 work tile (rows of SW halves).  Integers 0..255 are exact in fp16: byte b becomes the half with
+// bits 0x6400 | b (= 1024 + b, ulp 1 there), then 1024 is subtracted — two full-rate instructions per pixel pair.
+template <int NROWS>
+__device__ __forceinline__ void convert_u8_tile_h(const unsigned char* __restrict__ src, __half* __restrict__ dst)
+{
+    constexpr int CH = SW / 4;
+    const __half2 k1024 = __floats2half2_rn(1024.0f, 1024.0f);
+    for (int idx = threadIdx.x; idx < NROWS * CH; idx += NT) {
+        const int r = idx / CH, c = idx - r * CH;
+        const unsigned u = *reinterpret_cast<const unsigned*>(src + r * U8_ROW + U8_OFF + 4 * c);
+        unsigned lo = __byte_perm(u, 0x64646464u, 0x4140);  // (0x64, b1, 0x64, b0)
+        unsigned hi = __byte_perm(u, 0x64646464u, 0x4342);  // (0x64, b3, 0x64, b2)
+        const __half2 h0 = __hsub2(*reinterpret_cast<__half2*>(&lo), k1024);
+        const __half2 h1 = __hsub2(*reinterpret_cast<__half2*>(&hi), k1024);
+        uint2 o;
+        o.x = *reinterpret_cast<const unsigned*>(&h0);
+        o.y = *reinterpret_cast<const unsigned*>(&h1);
+        *reinterpret_cast<uint2*>(dst + 4 * idx) = o;
+    }
+}
+
 // TMA tiles arrive zero-filled outside the image: overwrite those cells with the replicated edge value.
 // Sources are in-image cells, targets out-of-image cells, so one pass needs no intermediate barrier.
 template <int NROWS>
@@ -314,8 +335,8 @@ __device__ __forceinline__ bool tile_on_frame(int l_org, int p_org, int L, int P
 {
     return l_org < 0 || l_org + NROWS > L || p_org < 0 || p_org + SW > P;
 }
-template <int NROWS>
-__device__ __forceinline__ void fix_border(float* tile, int l_org, int p_org, int L, int P)
+template <int NROWS, typename T>
+__device__ __forceinline__ void fix_border(T* tile, int l_org, int p_org, int L, int P)
 {
     // Only cells within 2 of the image are ever read by a valid pixel's window, so at most 2 lines above, 2 below,
     // 2 columns left and 2 right are patched; every source is an in-image cell of this tile.
@@ -672,12 +693,70 @@ __device__ __forceinline__ void sweep_tile(const float* __restrict__ tile, int l
     }
 }
 
+// u8 frames, fp16-rounded products: pixels 0..255 are exact in fp16 and their products exact in f32, so one HMUL2 gives
+// two products already rounded the way the reference rounds them (RN16(RN32(a*b)) == RN16(a*b)); FHADD accumulates.
+// tile: fp16, rows of SW halves, same column convention as the f32 tiles.
+__device__ __forceinline__ void acc2_h2(float& a0, float& a1, unsigned x2, unsigned y2)
+{
+    asm("{\n\t.reg .b32 h;\n\t.reg .b16 lo, hi;\n\t"
+        "mul.rn.f16x2 h, %2, %3;\n\t"
+        "mov.b32 {lo, hi}, h;\n\t"
+        "add.rn.f32.f16 %0, lo, %0;\n\t"
+        "add.rn.f32.f16 %1, hi, %1;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "r"(x2), "r"(y2));
+}
+template <bool FULL>
+__device__ __forceinline__ void sweep_tile_h2(const __half* __restrict__ tile, int l0, int p0, int L, int P,
+                                              float (&e0)[NLAG], float (&e1)[NLAG])
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // window of 8 pixels (p-2 .. p+5) = 4 aligned pairs h[0..3] = (-2,-1) (0,1) (2,3) (4,5) + 3 odd pairs s[0..2] = (-1,0) (1,2) (3,4)
+    const __half* base = tile + (4 * w) * SW + 4 * lane + 2;
+    const int pb = p0 + 4 * lane;
+    unsigned m01 = 0xffffffffu, m23 = 0xffffffffu;  // validity masks of my pixel pairs (all-ones halves)
+    if (!FULL) {
+        m01 = ((pb >= 1 && pb <= P - 2) ? 0x0000ffffu : 0u) | ((pb + 1 >= 1 && pb + 1 <= P - 2) ? 0xffff0000u : 0u);
+        m23 = ((pb + 2 >= 1 && pb + 2 <= P - 2) ? 0x0000ffffu : 0u) | ((pb + 3 >= 1 && pb + 3 <= P - 2) ? 0xffff0000u : 0u);
+    }
+    struct Row { unsigned h[4], s[3]; };
+    auto loadrow = [](Row& r, const __half* q) {
+        r.h[0] = *reinterpret_cast<const unsigned*>(q);
+        const uint2 mid = *reinterpret_cast<const uint2*>(q + 2);
+        r.h[1] = mid.x; r.h[2] = mid.y;
+        r.h[3] = *reinterpret_cast<const unsigned*>(q + 6);
+#pragma unroll
+        for (int i = 0; i < 3; i++) r.s[i] = __byte_perm(r.h[i], r.h[i + 1], 0x5432);  // (hi of h[i], lo of h[i+1])
+    };
+    Row A, B, C;
+    loadrow(A, base);
+    loadrow(B, base + SW);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        loadrow(C, base + (r + 2) * SW);
+        unsigned x01 = A.h[1], x23 = A.h[2];
+        if (!FULL) {
+            const int l = l0 + 4 * w + r;
+            const bool vl = (l >= 1) && (l <= L - 2);
+            x01 = vl ? (x01 & m01) : 0u;
+            x23 = vl ? (x23 & m23) : 0u;
+        }
+        // lag (dl, dp): partner pair of (0,1) is (dp, 1+dp); of (2,3) it is (2+dp, 3+dp)
+#define WM_LAGH(v, R, P01, P23) acc2_h2(e0[v], e1[v], x01, R.P01); acc2_h2(e0[v], e1[v], x23, R.P23);
+        WM_LAGH(0, A, h[1], h[2]) WM_LAGH(1, A, s[1], s[2]) WM_LAGH(2, A, h[2], h[3])
+        WM_LAGH(3, B, h[0], h[1]) WM_LAGH(4, B, s[0], s[1]) WM_LAGH(5, B, h[1], h[2]) WM_LAGH(6, B, s[1], s[2]) WM_LAGH(7, B, h[2], h[3])
+        WM_LAGH(8, C, h[0], h[1]) WM_LAGH(9, C, s[0], s[1]) WM_LAGH(10, C, h[1], h[2]) WM_LAGH(11, C, s[1], s[2]) WM_LAGH(12, C, h[2], h[3])
+#undef WM_LAGH
+        A = B; B = C;
+    }
+}
+
 template <typename PixT, bool FP16, bool TMA>
 __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtensorMap tmI, const SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * NFRM];
-    __shared__ __align__(8) uint64_t bars[SWEEP_NST];
+    __shared__ __align__(8) uint64_t bars[SWEEP_NST_U8];
     constexpr bool U8T = TMA && sizeof(PixT) == 1;
     const int b = blockIdx.y;
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
@@ -687,7 +766,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
 
     {
         const int sb = blockIdx.x, step = a.nsweep;
-        constexpr int NST = TMA ? SWEEP_NST : 1;
+        constexpr int NST = TMA ? (U8T ? SWEEP_NST_U8 : SWEEP_NST) : 1;
         constexpr int STG = sweep_stage(U8T);
         auto stage = [&](int s) { return dsm + (size_t)s * STG; };
         float* const work = reinterpret_cast<float*>(dsm + (TMA ? (size_t)NST * STG : 0));  // u8 TMA / plain path
@@ -711,9 +790,51 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
 #pragma unroll
         for (int v = 0; v < NLAG; v++) { dacc[v] = 0.0; e0[v] = 0.0f; e1[v] = 0.0f; }
         StagePos<NST> pos;
+        int k = 0;
+        if constexpr (U8T && FP16) {
+            // u8 frames: fp16 work tiles + packed-half products.  Software pipeline with ONE barrier per tile: while tile k
+            // is computed from work tile k&1, tile k+1 (already landed) is widened into the other work tile; the TMA
+            // of tile k+NST-1 is issued at the top, so loads, conversion and arithmetic of three different tiles overlap.
+            __half* const wk0 = reinterpret_cast<__half*>(work);
+            __half* const wk1 = wk0 + (TL + 2) * SW;  // 2 x 9248 B fit the SZ_I34 work area
+            if (it.t < a.ntiles) {  // prologue: tile 0
+                mbar_wait(&bars[pos.s], pos.ph);
+                convert_u8_tile_h<TL + 2>(stage(pos.s), wk0);
+                pos.next();
+                __syncthreads();
+                if (tile_on_frame<TL + 2>(it.tl * TL, it.tp * TP - HP, L, P)) { fix_border<TL + 2>(wk0, it.tl * TL, it.tp * TP - HP, L, P); __syncthreads(); }
+            }
+            for (; it.t < a.ntiles; it.next(), k++) {
+                const int l0 = it.tl * TL, p0 = it.tp * TP;
+                __half* const cur = (k & 1) ? wk1 : wk0;
+                __half* const nxt = (k & 1) ? wk0 : wk1;
+                const bool has_next = it.t + step < a.ntiles;
+                int ntl = 0, ntp = 0;
+                if (threadIdx.x == 0 && it.t + (NST - 1) * step < a.ntiles) {
+                    int ptl, ptp;
+                    it.peek(NST - 1, ptl, ptp);
+                    fence_proxy_async();
+                    issue(ptl, ptp, pos.ahead(NST - 2));  // pos is one tile ahead of k
+                }
+                if (has_next) {
+                    it.peek(1, ntl, ntp);
+                    mbar_wait(&bars[pos.s], pos.ph);
+                    convert_u8_tile_h<TL + 2>(stage(pos.s), nxt);
+                    pos.next();
+                }
+                const bool full = l0 >= 1 && l0 + TL <= L - 1 && p0 >= 1 && p0 + TP <= P - 1;
+                if (full) sweep_tile_h2<true>(cur, l0, p0, L, P, e0, e1);
+                else sweep_tile_h2<false>(cur, l0, p0, L, P, e0, e1);
+                if ((k & 3) == 3) {
+#pragma unroll
+                    for (int v = 0; v < NLAG; v++) { dacc[v] += (double)__fadd_rn(e0[v], e1[v]); e0[v] = 0.0f; e1[v] = 0.0f; }
+                }
+                __syncthreads();  // nxt complete, cur free, the stage just converted may be refilled
+                if (has_next && tile_on_frame<TL + 2>(ntl * TL, ntp * TP - HP, L, P)) { fix_border<TL + 2>(nxt, ntl * TL, ntp * TP - HP, L, P); __syncthreads(); }
+            }
+        } else {
         TilePrefetch<PixT, TL + 2> pre;
         if constexpr (!TMA) { if (it.t < a.ntiles) pre.issue(img, a.ld, L, P, it.tl * TL, it.tp * TP - HP, a.vec_ok != 0); }
-        int k = 0;
         for (; it.t < a.ntiles; it.next(), k++) {
             const int l0 = it.tl * TL, p0 = it.tp * TP;
             const float* tile;
@@ -746,6 +867,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
                 for (int v = 0; v < NLAG; v++) { dacc[v] += (double)__fadd_rn(e0[v], e1[v]); e0[v] = 0.0f; e1[v] = 0.0f; }
             }
             if constexpr (TMA) __syncthreads();  // the stage just read may be refilled from the next iteration on
+        }
         }
 #pragma unroll
         for (int v = 0; v < NLAG; v++) dacc[v] += (double)__fadd_rn(e0[v], e1[v]);
