@@ -520,3 +520,58 @@ def test_u8_tma_and_plain_paths_agree(wmb, oracle, rows, cols, ls):
     L.wm_dev_free(wm._h, dfr)
     L.wm_dev_free(wm._h, dout)
     wm.close()
+
+
+def test_many_small_images_one_launch(wmb, oracle):
+    """BASELINE config 5 in miniature: hundreds of small images in ONE launch sequence (one CTA per image, which also
+    switches the frame-ring code to its thread-per-pixel mode)."""
+    rows, cols, B = 96, 160, 320
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    rng = np.random.default_rng(3)
+    base = [util.natural_image(rows, cols, seed=600 + k) for k in range(8)]
+    imgs = np.stack([np.clip(base[b % 8] + rng.uniform(-1, 1, (rows, cols)).astype(np.float32) * (b // 8), 0, 255) for b in range(B)]).astype(np.float32)
+    L = wmb.lib()
+    din = L.wm_dev_alloc(wm._h, imgs.nbytes)
+    dout = L.wm_dev_alloc(wm._h, imgs.nbytes)
+    L.wm_dev_upload(wm._h, din, imgs.ctypes.data, imgs.nbytes)
+    n = rows * cols
+    di = wmb.image_desc(din, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+    do = wmb.image_desc(dout, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+    a = np.zeros(B, np.float32)
+    c = np.zeros(B, np.float32)
+    st = np.zeros(B, np.int32)
+    wm.embed_batch(0, di, di, do, n, n, n, B, wmb.ME, a, st)
+    wm.detect_batch(0, do, n, B, wmb.ME, c, st)
+    wm.sync(0)
+    outs = np.zeros_like(imgs)
+    L.wm_dev_download(wm._h, outs.ctypes.data, dout, outs.nbytes)
+    for b in (0, 7, 100, B - 1):
+        o = oracle.embed(imgs[b], W, 40.0, wmb.ME)
+        od = oracle.detect(o["out"], W, wmb.ME)
+        report("many_small b=%d a rel=%.3g dpix=%.3g corr rel=%.3g" % (
+            b, abs(a[b] - o["a"]) / o["a"], np.abs(outs[b] - o["out"]).max(), abs(c[b] - od["corr"]) / abs(od["corr"])))
+        assert abs(a[b] - o["a"]) / o["a"] <= 1e-3
+        assert np.abs(outs[b] - o["out"]).max() <= 1e-4 * 255
+        assert abs(c[b] - od["corr"]) / abs(od["corr"]) <= 1e-3
+    # the same images one by one (few-pixels-per-block ring mode) give bit-identical scalars
+    for b in (3, 200):
+        d1 = wmb.DeviceArray.from_numpy(wm, imgs[b], wmb.ROW_MAJOR)
+        o1, a1, _ = wm.makeWatermark(d1, d1, wmb.ME)
+        assert a1 == a[b] and np.array_equal(o1.numpy(), outs[b])
+    # u8 frames through the same batched path: Rx exact => pixels identical to the oracle
+    y = np.rint(imgs).astype(np.uint8)
+    dy = L.wm_dev_alloc(wm._h, y.nbytes)
+    dyo = L.wm_dev_alloc(wm._h, y.nbytes)
+    L.wm_dev_upload(wm._h, dy, y.ctypes.data, y.nbytes)
+    ctx = wmb.VideoProcessingContext(wm, rows, cols, 1, linesize=cols, frames_on_device=True)
+    a8 = np.zeros(B, np.float32)
+    wmb.process_frames(ctx, wmb.VIDEO_EMBED, dy, dyo, 0, B, a8)
+    yo = np.zeros_like(y)
+    L.wm_dev_download(wm._h, yo.ctypes.data, dyo, yo.nbytes)
+    for b in (0, 150, B - 1):
+        st8, oo, oa = oracle.embed_frame_u8(y[b], W, 40.0, oracle.ME)
+        assert np.abs(yo[b].astype(int) - oo.astype(int)).max() <= 1 and abs(a8[b] - oa) / oa <= 1e-3
+    for ptr in (din, dout, dy, dyo):
+        L.wm_dev_free(wm._h, ptr)
+    wm.close()

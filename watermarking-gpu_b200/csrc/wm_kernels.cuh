@@ -395,6 +395,26 @@ __device__ __forceinline__ void block_sum(const double (&v)[NV], double* red)
     __syncthreads();
 }
 
+// same for f32 partials (widened one at a time, so no second register array is live)
+template <int NV>
+__device__ __forceinline__ void block_sum_f32(const float (&v)[NV], double* red)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const double s = warp_sum((double)v[i]);
+        if (lane == 0) red[w * NV + i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < NT / 32; k++) s += red[k * NV + threadIdx.x];
+        red[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
 // last-block election (threadFenceReduction pattern); counter wraps back to 0 by itself
 __device__ __forceinline__ bool last_block(unsigned* counter, unsigned nblocks)
 {
@@ -896,11 +916,21 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
             else if (t < NFRM) { int r = t - 8; i = 0; while (r >= 8 - i) { r -= 8 - i; i++; } j = i + r; }
             pi[q] = i; pj[q] = j;
         }
-        double f0 = 0.0, f1 = 0.0;
         // chunks of NT ring pixels: thread t stages pixel t's 3x3 window (clamped) + its not-in-core bits in smem
-        // (all loads of a chunk in flight together), then each warp walks 32 of the staged pixels
+        // (all loads of a chunk in flight together).  Then either
+        //   (a) few ring pixels per block (single image, ~300 CTAs): each WARP walks staged pixels, one lane per product —
+        //       lane v owns partial v (and 32+v), so no cross-lane reduction at all (latency matters here), or
+        //   (b) many ring pixels per block (batched images, few CTAs each): each THREAD takes one staged pixel and all its
+        //       44 products in registers (32x fewer warp instructions per pixel), one block reduction at the end.
         float* win = reinterpret_cast<float*>(dsm);            // [NT][9]  (the tile stages are idle by now)
         unsigned* ncm = reinterpret_cast<unsigned*>(win + NT * 9);  // [NT]
+        const bool per_thread = count > (long long)a.nsweep * 512;
+        double f0 = 0.0, f1 = 0.0;
+        float tacc[NFRM];
+#pragma unroll
+        for (int v = 0; v < NFRM; v++) tacc[v] = 0.0f;
+        int chunks = 0;
+        double ftot = 0.0;  // mode (b): thread t < NFRM keeps the block total of partial t
         for (long long c0 = (long long)fb * NT; c0 < count; c0 += (long long)a.nsweep * NT) {
             const long long idx = c0 + threadIdx.x;
             __syncthreads();
@@ -920,29 +950,71 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
             }
             __syncthreads();
             const int nhere = (int)min((long long)NT, count - c0);
-            for (int px = w; px < nhere; px += NT / 32) {
-                const unsigned ncmask = ncm[px];
+            if (!per_thread) {
+                for (int px = w; px < nhere; px += NT / 32) {
+                    const unsigned ncmask = ncm[px];
 #pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int i = pi[q], j = pj[q];
-                    const int li = i < 4 ? i : i + 1, lj = j == 8 ? 4 : (j < 4 ? j : j + 1);  // neighbour index -> window slot
-                    float pr = __fmul_rn(win[px * 9 + li], win[px * 9 + lj]);
-                    if constexpr (FP16) pr = round_f16(pr);
-                    // rx[i], i <= 3 and every Rx pair: counted when p + o_i is not a core pixel; rx[i], i >= 4: when p is not
-                    const bool use = (j == 8 && i >= 4) ? ((ncmask >> 4) & 1) : ((ncmask >> li) & 1);
-                    if (lane + 32 * q < NFRM && use) { if (q == 0) f0 += (double)pr; else f1 += (double)pr; }
+                    for (int q = 0; q < 2; q++) {
+                        const int i = pi[q], j = pj[q];
+                        const int li = i < 4 ? i : i + 1, lj = j == 8 ? 4 : (j < 4 ? j : j + 1);  // neighbour index -> window slot
+                        float pr = __fmul_rn(win[px * 9 + li], win[px * 9 + lj]);
+                        if constexpr (FP16) pr = round_f16(pr);
+                        // rx[i], i <= 3 and every Rx pair: counted when p + o_i is not a core pixel; rx[i], i >= 4: when p is not
+                        const bool use = (j == 8 && i >= 4) ? ((ncmask >> 4) & 1) : ((ncmask >> li) & 1);
+                        if (lane + 32 * q < NFRM && use) { if (q == 0) f0 += (double)pr; else f1 += (double)pr; }
+                    }
                 }
+            } else if ((int)threadIdx.x < nhere) {
+                const unsigned ncmask = ncm[threadIdx.x];
+                float n[8], nm[8];  // neighbours, and neighbours zeroed unless "p + o_i not in core"
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    const int sl = m < 4 ? m : m + 1;
+                    n[m] = win[threadIdx.x * 9 + sl];
+                    nm[m] = ((ncmask >> sl) & 1) ? n[m] : 0.0f;
+                }
+                const float x = win[threadIdx.x * 9 + 4];
+                const float xm = ((ncmask >> 4) & 1) ? x : 0.0f;
+                // a masked-out operand makes the product 0, which rounds to 0: same sum as skipping the term
+                float pr[NFRM];
+#pragma unroll
+                for (int m = 0; m < 8; m++) pr[m] = m <= 3 ? __fmul_rn(nm[m], x) : __fmul_rn(n[m], xm);
+                {
+                    int t = 8;
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+#pragma unroll
+                        for (int j = i; j < 8; j++, t++) pr[t] = __fmul_rn(nm[i], n[j]);
+                }
+#pragma unroll
+                for (int t = 0; t < NFRM; t += 2) {
+                    if constexpr (FP16) acc2_f16(tacc[t], tacc[t + 1], pr[t], pr[t + 1]);
+                    else { tacc[t] = __fadd_rn(tacc[t], pr[t]); tacc[t + 1] = __fadd_rn(tacc[t + 1], pr[t + 1]); }
+                }
+            }
+            if (per_thread && ++chunks == 64) {  // block-uniform: keeps the f32 partials exact for integer pixels (64 * 65504 < 2^24)
+                __syncthreads();
+                block_sum_f32<NFRM>(tacc, red);
+                if (threadIdx.x < NFRM) ftot += red[threadIdx.x];
+#pragma unroll
+                for (int v = 0; v < NFRM; v++) tacc[v] = 0.0f;
+                chunks = 0;
             }
         }
         __syncthreads();
-        red[w * NFRM + lane] = f0;
-        if (lane < NFRM - 32) red[w * NFRM + 32 + lane] = f1;
-        __syncthreads();
-        if (threadIdx.x < NFRM) {
-            double sacc = 0.0;
+        if (per_thread) {
+            block_sum_f32<NFRM>(tacc, red);
+            if (threadIdx.x < NFRM) part[(size_t)fb * NTOT + NLAG + threadIdx.x] = ftot + red[threadIdx.x];
+        } else {
+            red[w * NFRM + lane] = f0;
+            if (lane < NFRM - 32) red[w * NFRM + 32 + lane] = f1;
+            __syncthreads();
+            if (threadIdx.x < NFRM) {
+                double sacc = 0.0;
 #pragma unroll
-            for (int k = 0; k < NT / 32; k++) sacc += red[k * NFRM + threadIdx.x];
-            part[(size_t)fb * NTOT + NLAG + threadIdx.x] = sacc;
+                for (int k = 0; k < NT / 32; k++) sacc += red[k * NFRM + threadIdx.x];
+                part[(size_t)fb * NTOT + NLAG + threadIdx.x] = sacc;
+            }
         }
     }
 
