@@ -397,10 +397,13 @@ def main():
         roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dom["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": dom["alg_bytes_per_launch"], "avg_launch_ms": dom["avg_ms"]}
-        tr = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the ncu --set full capture
+        tr = os.path.join(ROOT, "profiles", "traffic.json")  # DRAM bytes per frame from the ncu --set full capture
         if os.path.exists(tr):
             try:
-                roof["traffic"] = json.load(open(tr)).get(wl, {}).get(dom["kernel"])
+                per_frame = json.load(open(tr)).get(wl, {}).get("per_frame", {}).get(dom["kernel"])
+                if per_frame is not None:
+                    roof["traffic"] = per_frame * dom["alg_bytes_per_launch"] / (ALG_BYTES[dtype][dom["kernel"]] * npx)
+                    roof["traffic_source"] = "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per frame x frames per launch)"
             except Exception:
                 pass
     # whole-step effective bandwidth on the compulsory bytes of embed+detect pairs

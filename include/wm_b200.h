@@ -62,7 +62,8 @@ enum {
     WM_OPT_FP16_PRODUCTS = 1, /* 1 (default): Rx/rx products rounded to fp16 as kernels/me_p3.hpp:10-20 does; 0: f32 */
     WM_OPT_KERNEL_TIMING = 2, /* 1: bracket every kernel with CUDA events (wm_get_kernel_times) */
     WM_OPT_USE_TMA = 3,       /* 1 (default): TMA tile loads when the shape allows; 0: always the plain loader */
-    WM_OPT_SERIAL_SLOTS = 4   /* 1: the video driver uses one slot (kernels do not overlap: per-kernel timing) */
+    WM_OPT_SERIAL_SLOTS = 4,  /* 1: the video driver uses one slot (kernels do not overlap: per-kernel timing) */
+    WM_OPT_CUDA_GRAPHS = 5    /* 1 (default): wm_embed / wm_detect replay a captured CUDA graph when called again with the same arguments */
 };
 
 /* ---- lifetime: Watermark ctor / copy-ctor / reinitialize / dtor (Watermark.cpp:21-85) ---- */
