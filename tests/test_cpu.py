@@ -219,3 +219,28 @@ def test_two_rank_sharding_gloo():
     assert tmax == 2.0
     exp = [float(i) if i % 3 == 0 else float("nan") for i in range(13)]
     assert all((np.isnan(a) and np.isnan(b)) or a == b for a, b in zip(vals, exp))
+
+
+# ---------------------------------------------------------------------------------------------------
+# watermark generator: reproduces the stream of the committed .dat files
+# ---------------------------------------------------------------------------------------------------
+def test_common_random_matrix_reproduces_committed_file(wmb, tmp_path):
+    import subprocess
+    exe = wmb.build().build_generator()
+    out = tmp_path / "w.dat"
+    r = subprocess.run([exe, "512", "512", "28390211", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0 and "Successfully wrote 262144 random floats" in r.stdout
+    a = np.fromfile(out, np.float32)
+    b = util.load_w512().ravel()
+    assert a.size == b.size
+    ulp = np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 2 and np.abs(a - b).max() <= 5e-7          # MSVC evaluates the polar transform in double
+    # all committed files are prefixes of one stream: a smaller request is a prefix of a larger one
+    out2 = tmp_path / "w2.dat"
+    subprocess.run([exe, "64", "64", "28390211", str(out2)], check=True, capture_output=True)
+    assert np.array_equal(np.fromfile(out2, np.float32), a[:4096])
+    # argument validation (CommonRandomMatrix/main.cpp:17-32)
+    assert subprocess.run([exe, "0", "64", "1", str(out2)], capture_output=True).returncode != 0
+    assert subprocess.run([exe, "64"], capture_output=True).returncode != 0
+    # the file loads through the library's own size check (Watermark.cpp:70-71) when a GPU is present
+    assert abs(float(a.mean())) < 0.01 and abs(float(a.std()) - 1.0) < 0.01

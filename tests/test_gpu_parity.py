@@ -408,7 +408,8 @@ def test_argument_errors(wmb, tmp_path):
 # ---------------------------------------------------------------------------------------------------
 # full-size, size-independent properties (BASELINE configs 2-4)
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,cols", [(1080, 1920), (2160, 3840)])
+# 1078x1918 and 2160x3872 are the reference's own odd-size samples (not divisible by 16 / by 64)
+@pytest.mark.parametrize("rows,cols", [(1080, 1920), (1078, 1918), (2160, 3840), (2160, 3872)])
 def test_full_size_properties(wmb, oracle, rows, cols):
     img = util.natural_image(rows, cols, seed=42)
     W = util.normal_w(rows, cols)
@@ -574,4 +575,30 @@ def test_many_small_images_one_launch(wmb, oracle):
         assert np.abs(yo[b].astype(int) - oo.astype(int)).max() <= 1 and abs(a8[b] - oa) / oa <= 1e-3
     for ptr in (din, dout, dy, dyo):
         L.wm_dev_free(wm._h, ptr)
+    wm.close()
+
+
+def test_8k_image(wmb, oracle):
+    """BASELINE config 4: one 7680x4320 image (133 MB f32) — the reduction and the fused passes at HBM scale."""
+    rows, cols = 4320, 7680
+    img = util.natural_image(rows, cols, seed=8)
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    sf = wm.strength_factor
+    d = wmb.DeviceArray.from_numpy(wm, img, wmb.COL_MAJOR)
+    for mask in (wmb.ME, wmb.NVF):
+        out, a, st = wm.makeWatermark(d, d, mask)
+        got = out.numpy()
+        mse = float(np.mean((got.astype(np.float64) - img) ** 2))
+        cm, _ = wm.detectWatermark(out, mask)
+        cc, _ = wm.detectWatermark(d, mask)
+        report("8k mask=%d a=%.7g mse/sf^2=%.6f corr marked=%.6f clean=%.6f" % (mask, a, mse / sf ** 2, cm, cc))
+        assert st == 0 and 0.9 <= mse / sf ** 2 <= 1.0 + 1e-4
+        assert cm > 0.2 and abs(cc) < 0.05
+    # Rx of the 8K image against the oracle (33 Mpx of fp16-rounded products: the sums must still agree to 1e-6)
+    wm.detectWatermark(d, wmb.ME)
+    Rx = wm.debug(wmb.DBG_RX)
+    oRx, _ = oracle.rx(img, oracle.FAITHFUL)
+    report("8k Rx rel=%.3g" % util.rel(Rx, oRx))
+    assert util.rel(Rx, oRx) <= 1e-6
     wm.close()

@@ -57,6 +57,21 @@ def build_facade_test(force=False):
     return exe
 
 
+def build_generator(force=False):
+    """tools/CommonRandomMatrix: the watermark-file generator (host-only C++)."""
+    src = os.path.join(ROOT, "tools", "CommonRandomMatrix", "generate_w.cpp")
+    exe = os.path.join(ROOT, "tools", "CommonRandomMatrix", "CommonRandomMatrix")
+    if not os.path.exists(src):
+        return None
+    if not force and os.path.exists(exe) and os.path.getmtime(exe) >= os.path.getmtime(src):
+        return exe
+    r = subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-o", exe, src], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_facade_test(force="--force" in sys.argv))
+    print(build_generator(force="--force" in sys.argv))
