@@ -11,14 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwm_b200.so")
-SOURCES = [os.path.join(CSRC, "wm_api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "wm_kernels.cuh"), os.path.join(ROOT, "include", "wm_b200.h")]
+SOURCES = [os.path.join(CSRC, f) for f in ("wm_api.cu", "wm_k_sweep.cu", "wm_k_stats.cu", "wm_k_apply.cu", "wm_k_detect.cu")]
+DEPS = SOURCES + [os.path.join(CSRC, "wm_kernels.cuh"), os.path.join(CSRC, "wm_launch.h"), os.path.join(ROOT, "include", "wm_b200.h")]
+OBJDIR = os.path.join(HERE, "build")
 
 NVCC = os.environ.get("WM_NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
-]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ccbin", "/usr/bin/g++",
+         "-Xcompiler", "-fPIC"]
+LINK_FLAGS = ["-shared", "-cudart", "static"]
 
 
 def stale():
@@ -31,12 +31,27 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    # one translation unit per kernel family, compiled in parallel, then linked into the shared library
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJDIR, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    if verbose:
+        for _, err in results:
+            sys.stderr.write(err)
+    cmd = [NVCC] + FLAGS + LINK_FLAGS + ["-o", LIB] + [o for o, _ in results]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc link failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     return LIB
 
 

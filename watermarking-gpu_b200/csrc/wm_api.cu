@@ -3,8 +3,8 @@
 // Mirrors the reference's Watermark object (Watermark_GPU/Watermark.{hpp,cpp}): a ctx owns W, the strength
 // factor and per-slot workspaces (the reference owns one staging texture => one object per concurrent caller;
 // here each slot has its own stream + workspace so one ctx can pipeline frames).  There is no CPU fallback.
-#include "wm_kernels.cuh"
 #include "../../include/wm_b200.h"
+#include "wm_launch.h"
 
 #include <algorithm>
 #include <cmath>
@@ -195,8 +195,7 @@ const float* w_for(wm_ctx* ctx, bool transposed, cudaStream_t st, int* rc)
             *rc = fail(ctx, WM_ERR_CUDA, "cudaMalloc(W col-major)");
             return nullptr;
         }
-        const dim3 blk(32, 8), grd((unsigned)((ctx->cols + 31) / 32), (unsigned)((ctx->rows + 31) / 32));
-        k_transpose<<<grd, blk, 0, st>>>(w.row_major, w.col_major, (int)ctx->rows, (int)ctx->cols);
+        launch_transpose(w.row_major, w.col_major, (int)ctx->rows, (int)ctx->cols, st);
         cudaStreamSynchronize(st);  // other slots/clones may use it right away
     }
     return w.col_major;
@@ -299,80 +298,6 @@ bool tma_ok(const wm_ctx* ctx, const View& v, long long bstride, int batch)
     const long long al = v.dtype == WM_F32 ? 4 : 16;  // strides must be multiples of 16 bytes
     return ctx->opt_tma && ((uintptr_t)v.ptr % 16 == 0) && (v.ld % al == 0) && (v.P % 4 == 0) &&
            (batch == 1 || bstride % al == 0) && encode_fn() != nullptr;
-}
-
-// ---- kernel dispatch over (pixel type, out type, mask, transposed, TMA) ----
-template <typename K>
-void set_smem(K kernel, int bytes)
-{
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-}
-#define WM_LAUNCH(KERNEL, SMEM, ...)                                   \
-    do {                                                               \
-        static bool done_[64] = {false};                               \
-        int dev_ = 0;                                                  \
-        cudaGetDevice(&dev_);                                          \
-        if (!done_[dev_ & 63]) { set_smem(KERNEL, SMEM); done_[dev_ & 63] = true; } \
-        KERNEL<<<grid, NT, SMEM, st>>>(__VA_ARGS__);                   \
-    } while (0)
-
-void launch_sweep(int dtype, bool fp16, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const SweepArgs& a)
-{
-    if (dtype == WM_F32) {
-        if (tma) { if (fp16) WM_LAUNCH((k_sweep<float, true, true>), sweep_smem(true, false), tmI, a); else WM_LAUNCH((k_sweep<float, false, true>), sweep_smem(true, false), tmI, a); }
-        else { if (fp16) WM_LAUNCH((k_sweep<float, true, false>), sweep_smem(false, false), tmI, a); else WM_LAUNCH((k_sweep<float, false, false>), sweep_smem(false, false), tmI, a); }
-    } else {
-        if (tma) { if (fp16) WM_LAUNCH((k_sweep<uint8_t, true, true>), sweep_smem(true, true), tmI, a); else WM_LAUNCH((k_sweep<uint8_t, false, true>), sweep_smem(true, true), tmI, a); }
-        else { if (fp16) WM_LAUNCH((k_sweep<uint8_t, true, false>), sweep_smem(false, true), tmI, a); else WM_LAUNCH((k_sweep<uint8_t, false, false>), sweep_smem(false, true), tmI, a); }
-    }
-}
-
-template <typename PixT, bool TMA>
-void launch_stats_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
-{
-    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_stats<PixT, 0, true, TMA>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_stats<PixT, 0, false, TMA>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
-    else { if (tr) WM_LAUNCH((k_stats<PixT, 1, true, TMA>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_stats<PixT, 1, false, TMA>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
-}
-void launch_stats(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
-{
-    if (dtype == WM_F32) { if (tma) launch_stats_t<float, true>(mask, tr, grid, st, tmI, tmW, a); else launch_stats_t<float, false>(mask, tr, grid, st, tmI, tmW, a); }
-    else { if (tma) launch_stats_t<uint8_t, true>(mask, tr, grid, st, tmI, tmW, a); else launch_stats_t<uint8_t, false>(mask, tr, grid, st, tmI, tmW, a); }
-}
-
-template <typename PixT, typename OutT, bool TMA, bool SB>
-void launch_apply_s(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
-{
-    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 0, true, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 0, false, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
-    else { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 1, true, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 1, false, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
-}
-template <typename PixT, typename OutT, bool TMA>
-void launch_apply_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
-{
-    if (a.same_base) launch_apply_s<PixT, OutT, TMA, true>(mask, tr, grid, st, tmI, tmW, a);
-    else launch_apply_s<PixT, OutT, TMA, false>(mask, tr, grid, st, tmI, tmW, a);
-}
-void launch_apply(int in_dtype, int out_dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI,
-                  const CUtensorMap& tmW, const EmbedArgs& a)
-{
-    if (in_dtype == WM_F32) {
-        if (out_dtype == WM_F32) { if (tma) launch_apply_t<float, float, true>(mask, tr, grid, st, tmI, tmW, a); else launch_apply_t<float, float, false>(mask, tr, grid, st, tmI, tmW, a); }
-        else { if (tma) launch_apply_t<float, uint8_t, true>(mask, tr, grid, st, tmI, tmW, a); else launch_apply_t<float, uint8_t, false>(mask, tr, grid, st, tmI, tmW, a); }
-    } else {
-        if (out_dtype == WM_F32) { if (tma) launch_apply_t<uint8_t, float, true>(mask, tr, grid, st, tmI, tmW, a); else launch_apply_t<uint8_t, float, false>(mask, tr, grid, st, tmI, tmW, a); }
-        else { if (tma) launch_apply_t<uint8_t, uint8_t, true>(mask, tr, grid, st, tmI, tmW, a); else launch_apply_t<uint8_t, uint8_t, false>(mask, tr, grid, st, tmI, tmW, a); }
-    }
-}
-
-template <typename PixT, bool TMA>
-void launch_detect_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
-{
-    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_detect<PixT, 0, true, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); else WM_LAUNCH((k_detect<PixT, 0, false, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); }
-    else { if (tr) WM_LAUNCH((k_detect<PixT, 1, true, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); else WM_LAUNCH((k_detect<PixT, 1, false, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); }
-}
-void launch_detect(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
-{
-    if (dtype == WM_F32) { if (tma) launch_detect_t<float, true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_t<float, false>(mask, tr, grid, st, tmZ, tmW, a); }
-    else { if (tma) launch_detect_t<uint8_t, true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_t<uint8_t, false>(mask, tr, grid, st, tmZ, tmW, a); }
 }
 
 // copy the op's per-image scalars into the slot's pinned ring (in stream order) and queue their delivery
@@ -974,11 +899,7 @@ int wm_debug_plane(wm_ctx* ctx, const wm_image* img, int what, float* dst_dev)
     pa.scal = s.scal;
     pa.dst = dst_dev;
     const dim3 grid(std::min(g.ntiles, 3 * ctx->sms));
-#define WM_PLANE(PIX)                                                                                             \
-    if (what == WM_DBG_ERRSEQ) { if (v.transposed) k_plane<PIX, 0, true><<<grid, NT, 0, s.stream>>>(pa); else k_plane<PIX, 0, false><<<grid, NT, 0, s.stream>>>(pa); } \
-    else { if (v.transposed) k_plane<PIX, 1, true><<<grid, NT, 0, s.stream>>>(pa); else k_plane<PIX, 1, false><<<grid, NT, 0, s.stream>>>(pa); }
-    if (v.dtype == WM_F32) { WM_PLANE(float) } else { WM_PLANE(uint8_t) }
-#undef WM_PLANE
+    launch_plane(v.dtype, what == WM_DBG_ERRSEQ, v.transposed, grid, s.stream, pa);
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s.stream));

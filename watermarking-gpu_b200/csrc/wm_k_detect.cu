@@ -1,0 +1,33 @@
+// wm_k_detect.cu — instantiations + dispatch of one kernel family (see wm_launch.h)
+#include "wm_launch.h"
+
+namespace wm {
+
+template <typename PixT, bool TMA>
+void launch_detect_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
+{
+    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_detect<PixT, 0, true, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); else WM_LAUNCH((k_detect<PixT, 0, false, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); }
+    else { if (tr) WM_LAUNCH((k_detect<PixT, 1, true, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); else WM_LAUNCH((k_detect<PixT, 1, false, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); }
+}
+void launch_detect(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
+{
+    if (dtype == WM_F32) { if (tma) launch_detect_t<float, true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_t<float, false>(mask, tr, grid, st, tmZ, tmW, a); }
+    else { if (tma) launch_detect_t<uint8_t, true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_t<uint8_t, false>(mask, tr, grid, st, tmZ, tmW, a); }
+}
+
+void launch_plane(int dtype, int what_errseq, bool tr, dim3 grid, cudaStream_t st, const PlaneArgs& a)
+{
+#define WM_PLANE(PIX)                                                                                             \
+    if (what_errseq) { if (tr) k_plane<PIX, 0, true><<<grid, NT, 0, st>>>(a); else k_plane<PIX, 0, false><<<grid, NT, 0, st>>>(a); } \
+    else { if (tr) k_plane<PIX, 1, true><<<grid, NT, 0, st>>>(a); else k_plane<PIX, 1, false><<<grid, NT, 0, st>>>(a); }
+    if (dtype == WM_F32) { WM_PLANE(float) } else { WM_PLANE(uint8_t) }
+#undef WM_PLANE
+}
+
+void launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t st)
+{
+    const dim3 blk(32, 8), grd((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    k_transpose<<<grd, blk, 0, st>>>(src, dst, rows, cols);
+}
+
+}  // namespace wm

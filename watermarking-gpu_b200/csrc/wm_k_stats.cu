@@ -1,0 +1,18 @@
+// wm_k_stats.cu — instantiations + dispatch of one kernel family (see wm_launch.h)
+#include "wm_launch.h"
+
+namespace wm {
+
+template <typename PixT, bool TMA>
+void launch_stats_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
+{
+    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_stats<PixT, 0, true, TMA>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_stats<PixT, 0, false, TMA>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
+    else { if (tr) WM_LAUNCH((k_stats<PixT, 1, true, TMA>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_stats<PixT, 1, false, TMA>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
+}
+void launch_stats(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
+{
+    if (dtype == WM_F32) { if (tma) launch_stats_t<float, true>(mask, tr, grid, st, tmI, tmW, a); else launch_stats_t<float, false>(mask, tr, grid, st, tmI, tmW, a); }
+    else { if (tma) launch_stats_t<uint8_t, true>(mask, tr, grid, st, tmI, tmW, a); else launch_stats_t<uint8_t, false>(mask, tr, grid, st, tmI, tmW, a); }
+}
+
+}  // namespace wm

@@ -587,7 +587,7 @@ struct SweepArgs {
 
 __device__ __forceinline__ int lag_index(int dl, int dp) { return dl == 0 ? dp : (dl == 1 ? 5 + dp : 10 + dp); }
 
-__device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* sc, ScalDbg* dbg, int transposed, double* M /* smem [8][9] */)
+static __device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* sc, ScalDbg* dbg, int transposed, double* M /* smem [8][9] */)
 {
     // internal (line, pixel) raster order of the 8 neighbours
     const int DLc[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
@@ -1599,7 +1599,7 @@ __global__ void __launch_bounds__(NT, 3) k_plane(const PlaneArgs a)
 }
 
 // dense transpose (rows x cols row-major -> col-major), used once per ctx for W
-__global__ void k_transpose(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols)
+static __global__ void k_transpose(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols)
 {
     __shared__ float t[32][33];
     const int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;

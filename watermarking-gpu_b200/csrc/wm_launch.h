@@ -1,0 +1,28 @@
+// wm_launch.h — launch dispatchers, one translation unit per kernel family so the build compiles them in parallel.
+#pragma once
+#include "wm_kernels.cuh"
+
+namespace wm {
+void launch_sweep(int dtype, bool fp16, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const SweepArgs& a);
+void launch_stats(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a);
+void launch_apply(int in_dtype, int out_dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI,
+                  const CUtensorMap& tmW, const EmbedArgs& a);
+void launch_detect(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a);
+void launch_plane(int dtype, int what_errseq, bool tr, dim3 grid, cudaStream_t st, const PlaneArgs& a);
+void launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t st);
+}  // namespace wm
+
+// dtype / mask codes shared with include/wm_b200.h
+#ifndef WM_B200_H
+enum { WM_MASK_ME = 0, WM_MASK_NVF = 1 };
+enum { WM_F32 = 0, WM_U8 = 1 };
+#endif
+
+#define WM_LAUNCH(KERNEL, SMEM, ...)                                   \
+    do {                                                               \
+        static bool done_[64] = {false};                               \
+        int dev_ = 0;                                                  \
+        cudaGetDevice(&dev_);                                          \
+        if (!done_[dev_ & 63]) { cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); done_[dev_ & 63] = true; } \
+        KERNEL<<<grid, NT, SMEM, st>>>(__VA_ARGS__);                   \
+    } while (0)
