@@ -212,18 +212,20 @@ Geo geo(int L, int P)
     return g;
 }
 
-struct Plan { int nsweep, nframe, gx_stats, gx_detect; };
-// Grids are sized so that every launch is at most ONE wave of 2 resident CTAs per SM (persistent tile loops):
-// a partial second wave would leave most SMs idle for a whole tile-loop's duration.
+struct Plan { int nsweep, nframe, gx_stats, gx_detect, nblk_base, nblk_extra; };
+// Every launch is at most ONE wave of 2 resident CTAs per SM (persistent tile loops; a partial second wave would leave
+// most SMs idle for a whole tile loop).  The wave is split over the images of a batch as evenly as possible: image b
+// gets nblk_base + (b < nblk_extra) CTAs, gridDim.x is the larger of the two and the surplus CTAs exit at once.
 Plan plan(const wm_ctx* ctx, const Geo& g, int batch)
 {
     Plan p;
-    const int cap = 2 * ctx->sms;              // resident CTAs per launch
-    const int per = std::max(1, cap / batch);  // CTAs per image
-    p.nframe = 0;                              // the frame ring is shared by the sweep blocks
-    p.nsweep = std::max(1, std::min(g.ntiles, per));
-    p.gx_stats = p.nsweep;
-    p.gx_detect = p.nsweep;
+    const int cap = 2 * ctx->sms;  // resident CTAs per launch
+    int base = cap / batch, extra = cap % batch;
+    if (base < 1) { base = 1; extra = 0; }
+    if (base >= g.ntiles) { base = g.ntiles; extra = 0; }
+    p.nblk_base = base; p.nblk_extra = extra;
+    p.nframe = 0;  // the frame ring is shared by the sweep blocks
+    p.nsweep = p.gx_stats = p.gx_detect = base + (extra > 0 ? 1 : 0);
     return p;
 }
 
@@ -330,6 +332,7 @@ int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int ba
     a.img = v.ptr; a.ld = v.ld; a.bstride = bstride;
     a.L = g.L; a.P = g.P; a.tiles_p = g.tiles_p; a.ntiles = g.ntiles;
     a.nsweep = pl.nsweep; a.nframe = pl.nframe;
+    a.nblk_base = pl.nblk_base; a.nblk_extra = pl.nblk_extra;
     a.vec_ok = vec_ok(v.ptr, v.ld, bstride, 0, v.dtype);
     a.transposed = v.transposed;
     a.part = s.part;
@@ -383,6 +386,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     ea.vec_ok = vec_ok(vi.ptr, vi.ld, in_stride, 0, vi.dtype);
     ea.w_vec_ok = (g.P % 4 == 0);
     ea.strength = ctx->strength;
+    ea.nblk_base = pl.nblk_base; ea.nblk_extra = pl.nblk_extra;
     ea.part = s.part + stats_part_offset(pl, batch);
     ea.counter = s.counters + s.batch_cap;
     ea.scal = s.scal; ea.dbg = s.dbg;
@@ -434,6 +438,7 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     da.L = g.L; da.P = g.P; da.tiles_p = g.tiles_p; da.ntiles = g.ntiles;
     da.vec_ok = vec_ok(v.ptr, v.ld, img_stride, 0, v.dtype);
     da.w_vec_ok = (g.P % 4 == 0);
+    da.nblk_base = pl.nblk_base; da.nblk_extra = pl.nblk_extra;
     da.part = s.part + stats_part_offset(pl, batch);
     da.counter = s.counters + 2 * s.batch_cap;
     da.scal = s.scal; da.dbg = s.dbg;

@@ -84,6 +84,9 @@ struct ScalDbg {
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+// CTAs working on image b of a batch: the launch's one wave of resident CTAs is split as evenly as possible, the first
+// `extra` images get one more (gridDim.x = base + (extra > 0); the surplus CTAs of the other images exit at once)
+__device__ __forceinline__ int blocks_of_image(int base, int extra, int b) { return base + (b < extra ? 1 : 0); }
 
 // ------------------------------------------------------------------------------------------------
 // TMA / mbarrier primitives (PTX; SASS: UTMALDG, SYNCS)
@@ -577,7 +580,8 @@ struct SweepArgs {
     const void* img;
     long long ld, bstride;  // elements
     int L, P, tiles_p, ntiles;
-    int nsweep, nframe;  // nframe unused (kept 0): the ring is shared by the sweep blocks
+    int nsweep, nframe;  // nsweep = gridDim.x (partial stride); nframe unused (kept 0): the ring is shared by the sweep blocks
+    int nblk_base, nblk_extra;  // CTAs per image = nblk_base + (image < nblk_extra)
     int vec_ok, transposed;
     double* part;        // [batch][nsweep][NTOT]
     unsigned* counter;   // [batch]
@@ -783,9 +787,11 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
     const int L = a.L, P = a.P;
     double* part = a.part + (size_t)b * (size_t)a.nsweep * NTOT;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nblk = blocks_of_image(a.nblk_base, a.nblk_extra, b);
+    if ((int)blockIdx.x >= nblk) return;
 
     {
-        const int sb = blockIdx.x, step = a.nsweep;
+        const int sb = blockIdx.x, step = nblk;
         constexpr int NST = TMA ? (U8T ? SWEEP_NST_U8 : SWEEP_NST) : 1;
         constexpr int STG = sweep_stage(U8T);
         auto stage = [&](int s) { return dsm + (size_t)s * STG; };
@@ -924,14 +930,14 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
         //       44 products in registers (32x fewer warp instructions per pixel), one block reduction at the end.
         float* win = reinterpret_cast<float*>(dsm);            // [NT][9]  (the tile stages are idle by now)
         unsigned* ncm = reinterpret_cast<unsigned*>(win + NT * 9);  // [NT]
-        const bool per_thread = count > (long long)a.nsweep * 512;
+        const bool per_thread = count > (long long)nblk * 512;
         double f0 = 0.0, f1 = 0.0;
         float tacc[NFRM];
 #pragma unroll
         for (int v = 0; v < NFRM; v++) tacc[v] = 0.0f;
         int chunks = 0;
         double ftot = 0.0;  // mode (b): thread t < NFRM keeps the block total of partial t
-        for (long long c0 = (long long)fb * NT; c0 < count; c0 += (long long)a.nsweep * NT) {
+        for (long long c0 = (long long)fb * NT; c0 < count; c0 += (long long)nblk * NT) {
             const long long idx = c0 + threadIdx.x;
             __syncthreads();
             if (idx < count) {
@@ -1019,11 +1025,11 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
     }
 
     // ---- second stage + solve in the last block ----
-    if (!last_block(a.counter + b, gridDim.x)) return;
+    if (!last_block(a.counter + b, nblk)) return;
     __shared__ double tot[NTOT];
     __shared__ double M[72];
     for (int v = w; v < NTOT; v += NT / 32) {
-        const double s = column_sum(part, a.nsweep, NTOT, v);
+        const double s = column_sum(part, nblk, NTOT, v);
         if (lane == 0) tot[v] = s;
     }
     __syncthreads();
@@ -1039,6 +1045,7 @@ struct EmbedArgs {
     const float* W;  // dense L x P in the image's layout
     int L, P, tiles_p, ntiles;
     int vec_ok, w_vec_ok;
+    int nblk_base, nblk_extra;  // CTAs per image = nblk_base + (image < nblk_extra)
     float strength;
     double* part;       // [batch][gridDim.x][2]       (stats)
     unsigned* counter;  // [batch]                     (stats)
@@ -1060,7 +1067,8 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
     constexpr int NST = TMA ? EMBED_NST : 1;
     constexpr bool U8T = TMA && sizeof(PixT) == 1;
     constexpr int STG = embed_stage(U8T), IPART = U8T ? U8_I34 : SZ_I34;
-    const int b = blockIdx.y, step = gridDim.x;
+    const int b = blockIdx.y, step = blocks_of_image(a.nblk_base, a.nblk_extra, b);
+    if ((int)blockIdx.x >= step) return;  // surplus CTA of this image (block-uniform, before any barrier)
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     auto stage = [&](int s) { return dsm + (size_t)s * STG; };
     float* const work = reinterpret_cast<float*>(dsm + (size_t)NST * STG);  // u8 TMA only
@@ -1172,6 +1180,8 @@ __global__ void __launch_bounds__(NT, 2) k_stats(const __grid_constant__ CUtenso
     for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
     double dsum = 0.0;
     float emax = 0.0f;
+    const int nblk = blocks_of_image(a.nblk_base, a.nblk_extra, b);
+    if ((int)blockIdx.x >= nblk) return;
     embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&](const float* tile, const float* wt, int l0, int p0) {
         const int pb = p0 + 4 * lane;
         float fs = 0.0f;
@@ -1204,11 +1214,11 @@ __global__ void __launch_bounds__(NT, 2) k_stats(const __grid_constant__ CUtenso
             part[0] = ss; part[1] = mm;
         }
     }
-    if (!last_block(a.counter + b, gridDim.x)) return;
+    if (!last_block(a.counter + b, nblk)) return;
     if (w == 0) {
         const double* part = a.part + (size_t)b * gridDim.x * 2;
-        const double S2 = column_sum(part, gridDim.x, 2, 0);
-        const float mx = column_max(part, gridDim.x, 2, 1);
+        const double S2 = column_sum(part, nblk, 2, 0);
+        const float mx = column_max(part, nblk, 2, 1);
         if (lane == 0) {
             double nrm = sqrt(S2);
             if (MASK == 0) nrm = nrm / (double)mx;
@@ -1237,7 +1247,7 @@ __device__ __forceinline__ void copy_base_through(const EmbedArgs& a)
     OutT* out = reinterpret_cast<OutT*>(a.out) + (long long)b * a.out_bstride;
     const long long n = (long long)a.L * a.P;
     for (int ch = 0; ch < a.channels; ch++)
-        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)blocks_of_image(a.nblk_base, a.nblk_extra, b) * NT) {
             const int l = (int)(i / a.P), p = (int)(i - (long long)l * a.P);
             out[(long long)ch * a.out_pstride + (long long)l * a.out_ld + p] =
                 to_out<OutT>((float)bas[(long long)ch * a.base_pstride + (long long)l * a.base_ld + p]);
@@ -1264,6 +1274,7 @@ __global__ void __launch_bounds__(NT, 2) k_apply(const __grid_constant__ CUtenso
     __shared__ __align__(8) uint64_t bars[EMBED_NST];
     const int b = blockIdx.y;
     const Scal* sc = a.scal + b;
+    if ((int)blockIdx.x >= blocks_of_image(a.nblk_base, a.nblk_extra, b)) return;
     if (sc->status != 0) { copy_base_through<PixT, OutT>(a); return; }
     const PixT* bas = reinterpret_cast<const PixT*>(a.base) + (long long)b * a.base_bstride;
     OutT* out = reinterpret_cast<OutT*>(a.out) + (long long)b * a.out_bstride;
@@ -1332,6 +1343,7 @@ struct DetectArgs {
     const float* W;
     int L, P, tiles_p, ntiles;
     int vec_ok, w_vec_ok;
+    int nblk_base, nblk_extra;  // CTAs per image = nblk_base + (image < nblk_extra)
     double* part;       // [batch][gridDim.x][3]
     unsigned* counter;
     Scal* scal;
@@ -1452,7 +1464,8 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
     if (sc->status != 0) return;  // singular: corr = 0 was written by the sweep
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     const int L = a.L, P = a.P;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, step = gridDim.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, step = blocks_of_image(a.nblk_base, a.nblk_extra, b);
+    if ((int)blockIdx.x >= step) return;
     float c[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) c[k] = sc->coef[k];
@@ -1535,9 +1548,9 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
     const double v3[3] = {ddot, dnz, dnu};
     block_sum<3>(v3, red);
     if (threadIdx.x < 3) a.part[((size_t)b * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = red[threadIdx.x];
-    if (!last_block(a.counter + b, gridDim.x)) return;
+    if (!last_block(a.counter + b, step)) return;
     if (w < 3) {
-        const double s = column_sum(a.part + (size_t)b * gridDim.x * 3, gridDim.x, 3, w);
+        const double s = column_sum(a.part + (size_t)b * gridDim.x * 3, step, 3, w);
         if (lane == 0) red[w] = s;
     }
     __syncthreads();
