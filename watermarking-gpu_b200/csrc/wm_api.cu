@@ -212,20 +212,25 @@ Geo geo(int L, int P)
     return g;
 }
 
-struct Plan { int nsweep, nframe, gx_stats, gx_detect, nblk_base, nblk_extra; };
-// Every launch is at most ONE wave of 2 resident CTAs per SM (persistent tile loops; a partial second wave would leave
-// most SMs idle for a whole tile loop).  The wave is split over the images of a batch as evenly as possible: image b
-// gets nblk_base + (b < nblk_extra) CTAs, gridDim.x is the larger of the two and the surplus CTAs exit at once.
+struct Plan { int nsweep, nframe, gx_stats, gx_detect, nblk_base, nblk_extra, eblk_base, eblk_extra; };
+// Every launch is at most ONE wave of resident CTAs (persistent tile loops; a partial second wave would leave most SMs
+// idle for a whole tile loop): 2 per SM for the sweep and the detector, EMBED_CTAS_PER_SM for stats / apply.  The wave
+// is split over the images of a batch as evenly as possible: image b gets base + (b < extra) CTAs, gridDim.x is the
+// larger of the two and the surplus CTAs exit at once.
+void split_wave(int cap, int batch, int ntiles, int* base, int* extra)
+{
+    *base = cap / batch; *extra = cap % batch;
+    if (*base < 1) { *base = 1; *extra = 0; }
+    if (*base >= ntiles) { *base = ntiles; *extra = 0; }
+}
 Plan plan(const wm_ctx* ctx, const Geo& g, int batch)
 {
     Plan p;
-    const int cap = 2 * ctx->sms;  // resident CTAs per launch
-    int base = cap / batch, extra = cap % batch;
-    if (base < 1) { base = 1; extra = 0; }
-    if (base >= g.ntiles) { base = g.ntiles; extra = 0; }
-    p.nblk_base = base; p.nblk_extra = extra;
+    split_wave(2 * ctx->sms, batch, g.ntiles, &p.nblk_base, &p.nblk_extra);
+    split_wave(EMBED_CTAS_PER_SM * ctx->sms, batch, g.ntiles, &p.eblk_base, &p.eblk_extra);
     p.nframe = 0;  // the frame ring is shared by the sweep blocks
-    p.nsweep = p.gx_stats = p.gx_detect = base + (extra > 0 ? 1 : 0);
+    p.nsweep = p.gx_detect = p.nblk_base + (p.nblk_extra > 0 ? 1 : 0);
+    p.gx_stats = p.eblk_base + (p.eblk_extra > 0 ? 1 : 0);
     return p;
 }
 
@@ -386,7 +391,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     ea.vec_ok = vec_ok(vi.ptr, vi.ld, in_stride, 0, vi.dtype);
     ea.w_vec_ok = (g.P % 4 == 0);
     ea.strength = ctx->strength;
-    ea.nblk_base = pl.nblk_base; ea.nblk_extra = pl.nblk_extra;
+    ea.nblk_base = pl.eblk_base; ea.nblk_extra = pl.eblk_extra;
     ea.part = s.part + stats_part_offset(pl, batch);
     ea.counter = s.counters + s.batch_cap;
     ea.scal = s.scal; ea.dbg = s.dbg;

@@ -55,7 +55,8 @@ constexpr int SZ_WT = TL * TP * 4;                   // W tile, no halo
 constexpr int U8_ROW = 160, U8_LEFT = 16, U8_OFF = U8_LEFT - HP;
 constexpr int U8_I34 = align128((TL + 2) * U8_ROW);
 constexpr int U8_I36 = align128((TL + 4) * U8_ROW);
-constexpr int SWEEP_NST = 3, SWEEP_NST_U8 = 4, EMBED_NST = 3, DETECT_NST = 2;
+constexpr int SWEEP_NST = 3, SWEEP_NST_U8 = 4, EMBED_NST = 2, DETECT_NST = 2;
+constexpr int EMBED_CTAS_PER_SM = 3;  // stats / apply: 2 stages of 35 KB -> three CTAs (24 warps) per SM
 // dynamic shared memory per kernel: [NST stages][work tiles]; with f32 TMA the stage IS the work tile
 __host__ __device__ constexpr int sweep_stage(bool u8) { return u8 ? U8_I34 : SZ_I34; }
 __host__ __device__ constexpr int embed_stage(bool u8) { return (u8 ? U8_I34 : SZ_I34) + SZ_WT; }
@@ -1164,7 +1165,7 @@ template <bool V> struct BoolTag { static constexpr bool value = V; };
 // ---- k_stats: MASK = ME: sum (|e| W)^2 and max|e| (the max cancels out of a.mask.W — SURVEY.md §0 — so no
 // separate max pass); MASK = NVF: sum (nvf W)^2.  Last block: a = strength / (||mask.W|| / sqrt(N)) (Watermark.cpp:170)
 template <typename PixT, int MASK, bool TR, bool TMA>
-__global__ void __launch_bounds__(NT, 2) k_stats(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
+__global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
                                                  const EmbedArgs a)
 {
     extern __shared__ __align__(128) unsigned char dsm[];
@@ -1267,7 +1268,7 @@ __device__ __forceinline__ void store4(OutT* orow, const float (&ov)[4], bool ve
 }
 
 template <typename PixT, typename OutT, int MASK, bool TR, bool TMA, bool SB>
-__global__ void __launch_bounds__(NT, 2) k_apply(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
+__global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
                                                  const EmbedArgs a)
 {
     extern __shared__ __align__(128) unsigned char dsm[];
