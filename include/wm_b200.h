@@ -106,6 +106,9 @@ int wm_embed_host(wm_ctx *ctx, const wm_image *in_gray_host, const wm_image *bas
                   int mask_type, float *a_host);
 int wm_detect_host(wm_ctx *ctx, const wm_image *img_host, int mask_type, float *corr_host);
 
+/* ---- af::rgb2gray(rgb, wr, wg, wb) of the reference's image flow (main.cpp:142-154,196-197): planar f32 RGB -> gray ---- */
+int wm_rgb2gray(wm_ctx *ctx, const wm_image *rgb, wm_image *gray, float wr, float wg, float wb);
+
 /* ---- parity access to the class's private intermediates (Watermark.hpp:52-58) ----
  * Valid after the last synchronous wm_embed / wm_detect.  dst is HOST memory.
  *   WM_DBG_RX     64 doubles  Rx (reference neighbour order, full symmetric)      Watermark.cpp:148

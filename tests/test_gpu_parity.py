@@ -602,3 +602,66 @@ def test_8k_image(wmb, oracle):
     report("8k Rx rel=%.3g" % util.rel(Rx, oRx))
     assert util.rel(Rx, oRx) <= 1e-6
     wm.close()
+
+
+def test_rgb2gray_and_image_flow(wmb, oracle):
+    """The reference's testForImage flow on the device: RGB -> gray (main.cpp:154), embed into the RGB image
+    (main.cpp:178,190), gray of the watermarked RGB (main.cpp:196-197), detect (main.cpp:208,219)."""
+    rgb = util.load_512_rgb()
+    W = util.load_w512()
+    wm = _mk(wmb, 512, 512, util.W512_PATH)
+    for layout in LAYOUTS:
+        drgb = wmb.DeviceArray.from_numpy(wm, rgb, layout)
+        dg = wm.rgb2gray(drgb)
+        g = dg.numpy()
+        og = oracle.rgb2gray(rgb)
+        assert np.array_equal(g, og)
+        for mask in (wmb.NVF, wmb.ME):
+            out, a, st = wm.makeWatermark(dg, drgb, mask)
+            gw = wm.rgb2gray(out)
+            corr, st2 = wm.detectWatermark(gw, mask)
+            o = oracle.embed(og, W, 40.0, mask, base=rgb)
+            od = oracle.detect(oracle.rgb2gray(o["out"]), W, mask)
+            report("image_flow layout=%d mask=%d a=%.6f/%.6f corr=%.6f/%.6f" % (layout, mask, a, o["a"], corr, od["corr"]))
+            assert st == 0 and st2 == 0
+            assert abs(a - o["a"]) / o["a"] <= 1e-3 and abs(corr - od["corr"]) / abs(od["corr"]) <= 1e-3
+    wm.close()
+
+
+def test_clones_on_threads(wmb, oracle):
+    """One object per concurrent caller (Watermark.cpp:30-34: copies own their workspace): clones used from several host
+    threads at once give the same answers as a single caller."""
+    import threading
+    rows, cols = 256, 384
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    imgs = [util.natural_image(rows, cols, seed=700 + k) for k in range(4)]
+    ref = []
+    for im in imgs:
+        d = wmb.DeviceArray.from_numpy(wm, im, wmb.COL_MAJOR)
+        out, a, _ = wm.makeWatermark(d, d, wmb.ME)
+        c, _ = wm.detectWatermark(out, wmb.ME)
+        ref.append((a, c))
+    got = [None] * 4
+    errs = []
+
+    def work(k):
+        try:
+            w2 = wm.clone()
+            d = wmb.DeviceArray.from_numpy(w2, imgs[k], wmb.COL_MAJOR)
+            for _ in range(20):
+                out, a, _ = w2.makeWatermark(d, d, wmb.ME)
+                c, _ = w2.detectWatermark(out, wmb.ME)
+            got[k] = (a, c)
+            w2.close()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    assert got == ref
+    wm.close()

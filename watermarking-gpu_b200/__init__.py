@@ -30,7 +30,7 @@ VIDEO_EMBED, VIDEO_DETECT = 0, 1
 EXPORTS = [
     "wm_create", "wm_create_from_file", "wm_clone", "wm_reinitialize", "wm_reinitialize_from_file", "wm_destroy",
     "wm_set_option", "wm_last_error", "wm_strength_factor", "wm_embed", "wm_detect", "wm_num_slots", "wm_get_stream",
-    "wm_embed_batch", "wm_detect_batch", "wm_sync", "wm_embed_host", "wm_detect_host", "wm_debug_get",
+    "wm_embed_batch", "wm_detect_batch", "wm_sync", "wm_embed_host", "wm_detect_host", "wm_rgb2gray", "wm_debug_get",
     "wm_debug_set_coeffs", "wm_debug_plane", "wm_get_kernel_times", "wm_launch_count", "wm_process_frames",
     "wm_dev_alloc", "wm_dev_free", "wm_dev_upload", "wm_dev_download", "wm_host_alloc_pinned",
     "wm_host_free_pinned", "wm_device_count", "wm_version",
@@ -98,6 +98,7 @@ def lib():
     L.wm_sync.argtypes = [vp, i32]
     L.wm_embed_host.argtypes = [vp, imp, imp, imp, i32, fp]
     L.wm_detect_host.argtypes = [vp, imp, i32, fp]
+    L.wm_rgb2gray.argtypes = [vp, imp, imp, C.c_float, C.c_float, C.c_float]
     L.wm_debug_get.argtypes = [vp, i32, vp]
     L.wm_debug_set_coeffs.argtypes = [vp, fp]
     L.wm_debug_plane.argtypes = [vp, imp, i32, vp]
@@ -291,6 +292,13 @@ class Watermark:
         d = watermarked_image.desc()
         rc = self._check(lib().wm_detect(self._h, C.byref(d), mask_type, C.byref(corr)))
         return corr.value, rc
+
+    def rgb2gray(self, rgb, weights=(0.299, 0.587, 0.114)):
+        """af::rgb2gray with the reference's weights (main.cpp:142-154): RGB DeviceArray -> gray DeviceArray."""
+        gray = DeviceArray(self, rgb.rows, rgb.cols, rgb.layout, F32, 1)
+        di, do = rgb.desc(), gray.desc()
+        self._check(lib().wm_rgb2gray(self._h, C.byref(di), C.byref(do), *[C.c_float(w) for w in weights]))
+        return gray
 
     # -- hot path, host (numpy) arrays: H2D + compute + D2H inside the call -------------------------
     def _host_desc(self, arr, layout):

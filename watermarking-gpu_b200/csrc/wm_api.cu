@@ -854,6 +854,25 @@ int wm_detect_host(wm_ctx* ctx, const wm_image* img, int mask, float* corr_host)
     return finish_slot(ctx, s);
 }
 
+int wm_rgb2gray(wm_ctx* ctx, const wm_image* rgb, wm_image* gray, float wr, float wg, float wb)
+{
+    if (!ctx) return WM_ERR_ARG;
+    View vi, vo;
+    int rc;
+    if ((rc = make_view(ctx, rgb, &vi, true))) return rc;
+    if ((rc = make_view(ctx, gray, &vo, false))) return rc;
+    if (vi.channels != 3 || vi.dtype != WM_F32 || vo.dtype != WM_F32 || vi.transposed != vo.transposed)
+        return fail(ctx, WM_ERR_ARG, "rgb2gray needs a 3-channel f32 input and a 1-channel f32 output of the same layout");
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slots[0];
+    const float* p0 = (const float*)vi.ptr;
+    launch_rgb2gray(p0, p0 + vi.pstride, p0 + 2 * vi.pstride, (float*)vo.ptr, vi.ld, vo.ld, vi.L, vi.P, wr, wg, wb, 4 * ctx->sms, s.stream);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s.stream));
+    return WM_OK;
+}
+
 int wm_debug_get(wm_ctx* ctx, int what, void* dst)
 {
     if (!ctx || !dst) return WM_ERR_ARG;

@@ -24,6 +24,12 @@ void launch_plane(int dtype, int what_errseq, bool tr, dim3 grid, cudaStream_t s
 #undef WM_PLANE
 }
 
+void launch_rgb2gray(const float* r, const float* g, const float* b, float* gray, long long ld_in, long long ld_out, int L, int P,
+                     float wr, float wg, float wb, int blocks, cudaStream_t st)
+{
+    k_rgb2gray<<<blocks, 256, 0, st>>>(r, g, b, gray, ld_in, ld_out, L, P, wr, wg, wb);
+}
+
 void launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t st)
 {
     const dim3 blk(32, 8), grd((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));

@@ -1612,6 +1612,18 @@ __global__ void __launch_bounds__(NT, 3) k_plane(const PlaneArgs a)
     }
 }
 
+// af::rgb2gray(rgb, 0.299, 0.587, 0.114) on planar f32 (main.cpp:142-154,196-197): element-wise, each op rounded
+static __global__ void k_rgb2gray(const float* __restrict__ r, const float* __restrict__ g, const float* __restrict__ b,
+                                  float* __restrict__ gray, long long ld_in, long long ld_out, int L, int P, float wr, float wg, float wb)
+{
+    const long long n = (long long)L * P;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(i / P), p = (int)(i - (long long)l * P);
+        const long long si = (long long)l * ld_in + p;
+        gray[(long long)l * ld_out + p] = __fadd_rn(__fadd_rn(__fmul_rn(wr, r[si]), __fmul_rn(wg, g[si])), __fmul_rn(wb, b[si]));
+    }
+}
+
 // dense transpose (rows x cols row-major -> col-major), used once per ctx for W
 static __global__ void k_transpose(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols)
 {
