@@ -212,9 +212,9 @@ Geo geo(int L, int P)
     return g;
 }
 
-struct Plan { int nsweep, nframe, gx_stats, gx_detect, nblk_base, nblk_extra, eblk_base, eblk_extra; };
+struct Plan { int nsweep, nframe, gx_stats, gx_detect, nblk_base, nblk_extra, eblk_base, eblk_extra, sblk_base, sblk_extra; };
 // Every launch is at most ONE wave of resident CTAs (persistent tile loops; a partial second wave would leave most SMs
-// idle for a whole tile loop): 2 per SM for the sweep and the detector, EMBED_CTAS_PER_SM for stats / apply.  The wave
+// idle for a whole tile loop): 2 per SM for the detector, SWEEP_CTAS_PER_SM / EMBED_CTAS_PER_SM for the sweep and stats / apply.  The wave
 // is split over the images of a batch as evenly as possible: image b gets base + (b < extra) CTAs, gridDim.x is the
 // larger of the two and the surplus CTAs exit at once.
 void split_wave(int cap, int batch, int ntiles, int* base, int* extra)
@@ -228,8 +228,10 @@ Plan plan(const wm_ctx* ctx, const Geo& g, int batch)
     Plan p;
     split_wave(2 * ctx->sms, batch, g.ntiles, &p.nblk_base, &p.nblk_extra);
     split_wave(EMBED_CTAS_PER_SM * ctx->sms, batch, g.ntiles, &p.eblk_base, &p.eblk_extra);
+    split_wave(SWEEP_CTAS_PER_SM * ctx->sms, batch, g.ntiles, &p.sblk_base, &p.sblk_extra);
     p.nframe = 0;  // the frame ring is shared by the sweep blocks
-    p.nsweep = p.gx_detect = p.nblk_base + (p.nblk_extra > 0 ? 1 : 0);
+    p.nsweep = p.sblk_base + (p.sblk_extra > 0 ? 1 : 0);
+    p.gx_detect = p.nblk_base + (p.nblk_extra > 0 ? 1 : 0);
     p.gx_stats = p.eblk_base + (p.eblk_extra > 0 ? 1 : 0);
     return p;
 }
@@ -337,7 +339,7 @@ int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int ba
     a.img = v.ptr; a.ld = v.ld; a.bstride = bstride;
     a.L = g.L; a.P = g.P; a.tiles_p = g.tiles_p; a.ntiles = g.ntiles;
     a.nsweep = pl.nsweep; a.nframe = pl.nframe;
-    a.nblk_base = pl.nblk_base; a.nblk_extra = pl.nblk_extra;
+    a.nblk_base = pl.sblk_base; a.nblk_extra = pl.sblk_extra;
     a.vec_ok = vec_ok(v.ptr, v.ld, bstride, 0, v.dtype);
     a.transposed = v.transposed;
     a.part = s.part;

@@ -55,13 +55,15 @@ constexpr int SZ_WT = TL * TP * 4;                   // W tile, no halo
 constexpr int U8_ROW = 160, U8_LEFT = 16, U8_OFF = U8_LEFT - HP;
 constexpr int U8_I34 = align128((TL + 2) * U8_ROW);
 constexpr int U8_I36 = align128((TL + 4) * U8_ROW);
-constexpr int SWEEP_NST = 3, SWEEP_NST_U8 = 4, EMBED_NST = 2, DETECT_NST = 2;
+constexpr int SWEEP_NST = 2, SWEEP_NST_U8 = 4, EMBED_NST = 2, DETECT_NST = 2;
+constexpr int SWEEP_CTAS_PER_SM = 3;  // the f64 lag accumulators live in smem so that three CTAs (24 warps) fit per SM
+constexpr int SWEEP_ACC = NLAG * NT * 8;  // [NLAG][NT] doubles
 constexpr int EMBED_CTAS_PER_SM = 3;  // stats / apply: 2 stages of 35 KB -> three CTAs (24 warps) per SM
 // dynamic shared memory per kernel: [NST stages][work tiles]; with f32 TMA the stage IS the work tile
 __host__ __device__ constexpr int sweep_stage(bool u8) { return u8 ? U8_I34 : SZ_I34; }
 __host__ __device__ constexpr int embed_stage(bool u8) { return (u8 ? U8_I34 : SZ_I34) + SZ_WT; }
 __host__ __device__ constexpr int detect_stage(bool u8) { return (u8 ? U8_I36 : SZ_I36) + SZ_I34; }  // Z (halo 2) + W (halo 1)
-constexpr int sweep_smem(bool tma, bool u8) { return tma ? (u8 ? SWEEP_NST_U8 * sweep_stage(true) + SZ_I34 : SWEEP_NST * sweep_stage(false)) : SZ_I34; }
+__host__ __device__ constexpr int sweep_smem(bool tma, bool u8) { return (tma ? (u8 ? SWEEP_NST_U8 * sweep_stage(true) + SZ_I34 : SWEEP_NST * sweep_stage(false)) : SZ_I34) + SWEEP_ACC; }
 constexpr int embed_smem(bool tma, bool u8) { return tma ? EMBED_NST * embed_stage(u8) + (u8 ? SZ_I34 : 0) : SZ_I34 + SZ_WT; }
 constexpr int detect_smem(bool tma, bool u8)  // + u tile
 {
@@ -777,7 +779,7 @@ __device__ __forceinline__ void sweep_tile_h2(const __half* __restrict__ tile, i
 }
 
 template <typename PixT, bool FP16, bool TMA>
-__global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtensorMap tmI, const SweepArgs a)
+__global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_constant__ CUtensorMap tmI, const SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * NFRM];
@@ -812,10 +814,16 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
                 for (int s = 0; s < NST - 1; s++)
                     if (sb + s * step < a.ntiles) { int ptl, ptp; it.peek(s, ptl, ptp); issue(ptl, ptp, s); }
         }
-        double dacc[NLAG];
+        // f64 accumulators of the 13 lags: one column per thread in smem ([v][thread], conflict-free), so they cost no
+        // registers; the f32 pair (e0, e1) is flushed into them every 8 tiles (64 px per accumulator: exact for integers)
+        double* const dsh = reinterpret_cast<double*>(dsm + sweep_smem(TMA, sizeof(PixT) == 1) - SWEEP_ACC) + threadIdx.x;
         float e0[NLAG], e1[NLAG];  // even / odd pixel accumulators
 #pragma unroll
-        for (int v = 0; v < NLAG; v++) { dacc[v] = 0.0; e0[v] = 0.0f; e1[v] = 0.0f; }
+        for (int v = 0; v < NLAG; v++) { dsh[v * NT] = 0.0; e0[v] = 0.0f; e1[v] = 0.0f; }
+        auto flush = [&]() {
+#pragma unroll
+            for (int v = 0; v < NLAG; v++) { dsh[v * NT] += (double)__fadd_rn(e0[v], e1[v]); e0[v] = 0.0f; e1[v] = 0.0f; }
+        };
         StagePos<NST> pos;
         int k = 0;
         if constexpr (U8T && FP16) {
@@ -852,10 +860,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
                 const bool full = l0 >= 1 && l0 + TL <= L - 1 && p0 >= 1 && p0 + TP <= P - 1;
                 if (full) sweep_tile_h2<true>(cur, l0, p0, L, P, e0, e1);
                 else sweep_tile_h2<false>(cur, l0, p0, L, P, e0, e1);
-                if ((k & 3) == 3) {
-#pragma unroll
-                    for (int v = 0; v < NLAG; v++) { dacc[v] += (double)__fadd_rn(e0[v], e1[v]); e0[v] = 0.0f; e1[v] = 0.0f; }
-                }
+                if ((k & 7) == 7) flush();
                 __syncthreads();  // nxt complete, cur free, the stage just converted may be refilled
                 if (has_next && tile_on_frame<TL + 2>(ntl * TL, ntp * TP - HP, L, P)) { fix_border<TL + 2>(nxt, ntl * TL, ntp * TP - HP, L, P); __syncthreads(); }
             }
@@ -889,15 +894,14 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const __grid_constant__ CUtenso
             const bool full = l0 >= 1 && l0 + TL <= L - 1 && p0 >= 1 && p0 + TP <= P - 1;
             if (full) sweep_tile<FP16, true>(tile, l0, p0, L, P, e0, e1);
             else sweep_tile<FP16, false>(tile, l0, p0, L, P, e0, e1);
-            if ((k & 3) == 3) {
-#pragma unroll
-                for (int v = 0; v < NLAG; v++) { dacc[v] += (double)__fadd_rn(e0[v], e1[v]); e0[v] = 0.0f; e1[v] = 0.0f; }
-            }
+            if ((k & 7) == 7) flush();
             if constexpr (TMA) __syncthreads();  // the stage just read may be refilled from the next iteration on
         }
         }
+        flush();
+        double dacc[NLAG];
 #pragma unroll
-        for (int v = 0; v < NLAG; v++) dacc[v] += (double)__fadd_rn(e0[v], e1[v]);
+        for (int v = 0; v < NLAG; v++) dacc[v] = dsh[v * NT];
         __syncthreads();
         block_sum<NLAG>(dacc, red);
         if (threadIdx.x < NLAG) part[(size_t)sb * NTOT + threadIdx.x] = red[threadIdx.x];
