@@ -665,3 +665,37 @@ def test_clones_on_threads(wmb, oracle):
     assert not errs, errs
     assert got == ref
     wm.close()
+
+
+@pytest.mark.parametrize("rows,cols", [(3, 3), (4, 5), (5, 7), (8, 300), (300, 8), (33, 129), (2, 64)])
+def test_tiny_and_degenerate_shapes(wmb, oracle, rows, cols):
+    """Far below the reference's 64-pixel minimum (main.cpp:161): the whole image is frame ring, tiles are mostly
+    overhang.  Everything must still equal the oracle (or be rejected: fewer than 3 lines cannot hold a 3x3 core)."""
+    W = util.normal_w(rows, cols)
+    if rows < 3 or cols < 3:
+        with pytest.raises(wmb.WatermarkError) as e:
+            wmb.Watermark(rows, cols, W, 3, 40.0)
+        assert e.value.code == -4
+        return
+    rng = np.random.default_rng(rows * 100 + cols)
+    img = rng.integers(0, 256, (rows, cols)).astype(np.float32)  # white noise: well conditioned even when tiny
+    wm = _mk(wmb, rows, cols, W)
+    for layout in LAYOUTS:
+        d = wmb.DeviceArray.from_numpy(wm, img, layout)
+        corr, st = wm.detectWatermark(d, wmb.ME)
+        Rx, rx = wm.debug(wmb.DBG_RX), wm.debug(wmb.DBG_RXVEC)
+        oRx, orx = oracle.rx(img, oracle.FAITHFUL)
+        assert np.array_equal(Rx, oRx) and np.array_equal(rx, orx)
+        od = oracle.detect(img, W, wmb.ME)
+        assert st == od["status"]
+        if st == 0:
+            assert abs(corr - od["corr"]) <= 1e-3 * max(abs(od["corr"]), 1e-2)
+        for mask in (wmb.ME, wmb.NVF):
+            out, a, st = wm.makeWatermark(d, d, mask)
+            o = oracle.embed(img, W, 40.0, mask)
+            assert st == o["status"]
+            if st == 0:
+                report("tiny %dx%d layout=%d mask=%d a rel=%.3g dpix=%.3g" % (rows, cols, layout, mask, abs(a - o["a"]) / o["a"], np.abs(out.numpy() - o["out"]).max()))
+                assert abs(a - o["a"]) / o["a"] <= 1e-3
+                assert np.abs(out.numpy() - o["out"]).max() <= 1e-4 * 255
+    wm.close()

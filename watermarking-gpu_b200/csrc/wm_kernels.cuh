@@ -182,29 +182,6 @@ __device__ __forceinline__ void load_tile(float* __restrict__ tile, const PixT* 
         *reinterpret_cast<float4*>(tile + r * SW + 4 * c) = v;
     }
 }
-// W tile without halo: TL x TP floats at (l0, p0); cells outside the image are never used
-__device__ __forceinline__ void load_w_tile(float* __restrict__ wt, const float* __restrict__ W, int L, int P, int l0,
-                                            int p0, bool vec_ok)
-{
-    constexpr int CH = TP / 4;
-    for (int idx = threadIdx.x; idx < TL * CH; idx += NT) {
-        const int r = idx / CH, c = idx - r * CH;
-        const int l = l0 + r, p = p0 + 4 * c;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (l < L && p < P) {
-            const float* wr = W + (long long)l * P + p;
-            if (vec_ok && p + 3 < P) v = __ldg(reinterpret_cast<const float4*>(wr));
-            else {
-                v.x = wr[0];
-                if (p + 1 < P) v.y = wr[1];
-                if (p + 2 < P) v.z = wr[2];
-                if (p + 3 < P) v.w = wr[3];
-            }
-        }
-        *reinterpret_cast<float4*>(wt + r * TP + 4 * c) = v;
-    }
-}
-
 // global loads pinned in program order (asm volatile): ptxas otherwise sinks read-only loads down to their first use,
 // i.e. past the barriers and the tile arithmetic they are meant to overlap with
 __device__ __forceinline__ float4 ld_pinned(const float4* p)
