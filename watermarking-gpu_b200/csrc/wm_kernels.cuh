@@ -19,12 +19,14 @@
 //   k_detect  detectWatermark after the sweep: e_z, u = mask.W, e_u and the three correlation sums
 //             (Watermark.cpp:221-231,248-249) in one pass
 //
-// Data movement.  Every kernel is persistent over 128 x 32 pixel tiles.  With TMA = true (f32 images whose base and
-// strides are 16-byte aligned) one elected thread streams the tiles (+ halo) and the matching W tiles into a ring
-// of shared-memory stages with cp.async.bulk.tensor (3-D tensor maps: pixel, line, image) signalled through
-// mbarriers, so the loads of tile i+2 are in flight while tile i is computed; out-of-image halo cells arrive
-// zero-filled and are overwritten with the replicated edge value (clamp-to-edge) by the few CTAs on the image
-// frame.  With TMA = false (u8 frames, odd strides) a cooperative clamped loader fills a single stage.
+// Data movement.  Every kernel is persistent over 128 x 32 pixel tiles.  With TMA = true (base and strides 16-byte
+// aligned) one elected thread streams the tiles (+ halo) and the matching W tiles into a ring of shared-memory stages
+// with cp.async.bulk.tensor (3-D tensor maps: pixel, line, image) signalled through mbarriers, so the loads of the
+// next tile(s) are in flight while a tile is computed; out-of-image halo cells arrive zero-filled and are overwritten
+// with the replicated edge value (clamp-to-edge) by the few CTAs on the image frame.  f32 tiles are used where they
+// land; u8 frames land as bytes (boxes that start 16-byte aligned in global memory) and are widened to f32 — or, for
+// the sweep, to fp16 — by a conversion pass.  With TMA = false (odd strides / sizes) a register-prefetched
+// cooperative clamped loader fills a single stage.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
