@@ -463,17 +463,16 @@ __device__ __forceinline__ float div_by(float a, float b, float rb /* = __frcp_r
     const float q = __fmul_rn(a, rb);
     return __fmaf_rn(__fmaf_rn(-q, b, a), rb, q);
 }
-// n/d for d in [0.9, 2^17], |n| <= d: the fast path of div.rn.f32 (reciprocal refined once, quotient refined twice)
-// without its range check and slow-path branch, which these operand ranges never take (checked on the host
-// against IEEE division over 1.5e9 operands of this range with the reciprocal seed perturbed by +-2 ulp).
+// var / (1 + var) of the NVF mask: rcp.approx, one Newton step on the reciprocal, one residual correction of the
+// quotient — no range check, no slow-path branch.  Equal to IEEE __fdiv_rn for EVERY float var in [-2^-6, 2^17) (the
+// naive variance of 0..255 pixels lies in about [-0.01, 16257]): checked exhaustively on a B200, 2.2e9 operands,
+// tools/microbench/div_check.cu (variant (1,1); with no Newton step exactly one operand differs).
 __device__ __forceinline__ float div_safe(float n, float d)
 {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
     y = __fmaf_rn(__fmaf_rn(-d, y, 1.0f), y, y);
-    y = __fmaf_rn(__fmaf_rn(-d, y, 1.0f), y, y);  // second refinement: exact even for a 2-ulp rcp.approx (host-verified)
-    float q = __fmul_rn(n, y);
-    q = __fmaf_rn(__fmaf_rn(-d, q, n), y, q);
+    const float q = __fmul_rn(n, y);
     return __fmaf_rn(__fmaf_rn(-d, q, n), y, q);
 }
 
