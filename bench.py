@@ -374,6 +374,13 @@ def main():
                "frames_per_step": n_e2e, "frames_in_flight": NS, "matches_resident_path": e2e_ok,
                "api": "wm_embed_batch / wm_detect_batch on wm_get_stream() slots; pinned host frames in, watermarked frames + scalars out"}
 
+    # multi-GPU: the only data that crosses ranks — per-frame scalars, gathered after the timed region
+    gathered = None
+    if dist is not None:
+        mine = torch.from_numpy(np.stack([a_host[1], c_host[1]])).to(dev)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        gathered = torch.stack(parts).cpu().numpy()  # [rank, (a, corr), frame]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -433,7 +440,10 @@ def main():
         "roofline": roof, "kernels": kern, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks,
         "results": {"a_nvf": float(a_host[0][0]), "a_me": float(a_host[1][0]), "corr_nvf": float(c_host[0][0]),
-                    "corr_me": float(c_host[1][0])},
+                    "corr_me": float(c_host[1][0]),
+                    "scalars_gathered": None if gathered is None else
+                    {"ranks": int(gathered.shape[0]), "frames_per_rank": int(gathered.shape[2]),
+                     "corr_me_mean": float(gathered[:, 1].mean()), "a_me_mean": float(gathered[:, 0].mean())}},
     }
     print(json.dumps(line))
     if dist is not None:
