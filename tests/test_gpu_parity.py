@@ -486,6 +486,57 @@ def test_tma_and_plain_paths_agree(wmb, oracle, rows, cols):
     wm.close()
 
 
+# ---------------------------------------------------------------------------------------------------
+# HMMA accumulation of the fp16-rounded products (WM_OPT_MMA_ACCUM) vs the FHADD chain
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,cols", [(64, 64), (67, 131), (200, 96), (512, 512), (1080, 1920), (2160, 3840)])
+def test_mma_and_fhadd_accumulation_agree(wmb, oracle, rows, cols):
+    """Integer-valued pixels: every rounded product and every partial sum is an integer below 2^24, so the tensor-pipe sums
+    must give the same bits as the scalar chain (and, at oracle-sized shapes, as the oracle).  Real-valued pixels: f32 partial
+    sums in a different association, Rx within 1e-6 and coefficients / results within north_star's tolerances."""
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    ii = util.natural_image(rows, cols, seed=11 + rows, integer=True)
+    for layout in LAYOUTS:
+        for dt in (np.uint8, np.float32):
+            got = {}
+            for mma in (1, 0):
+                wm.set_option(wmb.OPT_MMA_ACCUM, mma)
+                d = wmb.DeviceArray.from_numpy(wm, ii.astype(dt), layout)
+                corr, st = wm.detectWatermark(d, wmb.ME)
+                got[mma] = (wm.debug(wmb.DBG_RX), wm.debug(wmb.DBG_RXVEC), wm.debug(wmb.DBG_COEFFS), corr, st)
+            assert got[1][4] == 0 and got[0][4] == 0
+            assert np.array_equal(got[1][0], got[0][0]) and np.array_equal(got[1][1], got[0][1])
+            assert np.array_equal(got[1][2], got[0][2]) and got[1][3] == got[0][3]
+            if rows <= 512:
+                oRx, orx = oracle.rx(ii.astype(np.float32), oracle.FAITHFUL)
+                assert np.array_equal(got[1][0], oRx) and np.array_equal(got[1][1], orx)
+    img = util.natural_image(rows, cols, seed=5 + cols)
+    for layout in LAYOUTS:
+        got = {}
+        for mma in (1, 0):
+            wm.set_option(wmb.OPT_MMA_ACCUM, mma)
+            d = wmb.DeviceArray.from_numpy(wm, img, layout)
+            out, a, st = wm.makeWatermark(d, d, wmb.ME)
+            z = out.numpy()
+            corr, st2 = wm.detectWatermark(wmb.DeviceArray.from_numpy(wm, z, layout), wmb.ME)
+            got[mma] = (wm.debug(wmb.DBG_RX), wm.debug(wmb.DBG_COEFFS), a, z, corr)
+            assert st == 0 and st2 == 0
+        rR = util.rel(got[1][0], got[0][0])
+        rc = util.rel(got[1][1], got[0][1])
+        ra = abs(got[1][2] - got[0][2]) / abs(got[0][2])
+        rcorr = abs(got[1][4] - got[0][4]) / abs(got[0][4])
+        dpx = np.abs(got[1][3] - got[0][3]).max()
+        report("mma_vs_fhadd %dx%d layout=%d rel Rx=%.3g coef=%.3g a=%.3g corr=%.3g dpix=%.3g" % (rows, cols, layout, rR, rc, ra, rcorr, dpx))
+        assert rR <= 1e-6 and ra <= 1e-4 and rcorr <= 1e-4 and dpx <= 1e-4 * 255
+        if rows <= 512:
+            oRx, _ = oracle.rx(img, oracle.FAITHFUL)
+            r1, r0 = util.rel(got[1][0], oRx), util.rel(got[0][0], oRx)
+            report("mma_vs_fhadd %dx%d layout=%d Rx vs oracle: hmma %.3g fhadd %.3g" % (rows, cols, layout, r1, r0))
+            assert r1 <= 1e-6
+    wm.close()
+
+
 @pytest.mark.parametrize("rows,cols,ls", [(64, 64, 64), (96, 160, 192), (270, 480, 480), (130, 264, 272)])
 def test_u8_tma_and_plain_paths_agree(wmb, oracle, rows, cols, ls):
     """u8 frames resident on the device: TMA byte tiles + conversion pass vs the register-prefetched plain loader."""

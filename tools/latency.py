@@ -41,6 +41,17 @@ def main():
         print("%s: a=%.6f corr=%.6f" % (name, av, c))
     for k, v in res.items():
         print("%-12s %8.1f us/call  %8.1f FPS" % (k, v * 1e6, 1.0 / v))
+    # where the time goes: per-kernel device time (CUDA events; graphs are bypassed while timing is on)
+    wm.set_option(pkg.OPT_KERNEL_TIMING, 1)
+    wm.kernel_times(reset=True)
+    for _ in range(50):
+        for mask in (pkg.NVF, pkg.ME):
+            wm.makeWatermark(d, d, mask, out=out)
+            wm.detectWatermark(out, mask)
+    for name, (n, ms) in wm.kernel_times(reset=True).items():
+        if n:
+            print("   kernel %-13s %5d launches  avg %7.2f us" % (name, n, 1e3 * ms / n))
+    wm.set_option(pkg.OPT_KERNEL_TIMING, 0)
     tot = sum(res.values())
     print("all four ops: %.1f us -> %.1f frames/s (single image, synchronous calls, %dx%d)" % (tot * 1e6, 1.0 / tot, a.rows, a.cols))
 

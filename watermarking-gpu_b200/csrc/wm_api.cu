@@ -69,7 +69,7 @@ struct wm_ctx {
     float psnr = 0.f, strength = 0.f;
     std::shared_ptr<WShared> w;
     Slot slots[NSLOTS];
-    int opt_fp16 = 1, opt_timing = 0, opt_tma = 1, opt_serial = 0;
+    int opt_fp16 = 1, opt_timing = 0, opt_tma = 1, opt_serial = 0, opt_mma = 1;
     bool inject_coef = false;
     float injected[8];
     std::string err;
@@ -351,7 +351,7 @@ int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int ba
     if (tma) tma = make_tmap(&tmI, v.dtype, v.ptr, g.P, g.L, batch, v.ld, bstride, SW, TL + 2);
     {
         KTimer t(ctx, s, WM_K_SWEEP);
-        launch_sweep(v.dtype, ctx->opt_fp16 != 0, tma, dim3(pl.nsweep + pl.nframe, batch), s.stream, tmI, a);
+        launch_sweep(v.dtype, ctx->opt_fp16 ? (ctx->opt_mma ? 2 : 1) : 0, tma, dim3(pl.nsweep + pl.nframe, batch), s.stream, tmI, a);
     }
     CU(cudaGetLastError());
     return WM_OK;
@@ -692,7 +692,7 @@ int wm_clone(const wm_ctx* src, wm_ctx** out)
     ctx->rows = src->rows; ctx->cols = src->cols;
     ctx->p = src->p; ctx->psnr = src->psnr; ctx->strength = src->strength;
     ctx->w = src->w;
-    ctx->opt_fp16 = src->opt_fp16; ctx->opt_timing = src->opt_timing; ctx->opt_tma = src->opt_tma;
+    ctx->opt_fp16 = src->opt_fp16; ctx->opt_mma = src->opt_mma; ctx->opt_timing = src->opt_timing; ctx->opt_tma = src->opt_tma;
     const int rc = init_slots(ctx, nullptr);
     if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
     *out = ctx;
@@ -739,6 +739,7 @@ int wm_set_option(wm_ctx* ctx, int option, int value)
     case WM_OPT_USE_TMA: ctx->opt_tma = value != 0; return WM_OK;
     case WM_OPT_SERIAL_SLOTS: ctx->opt_serial = value != 0; return WM_OK;
     case WM_OPT_CUDA_GRAPHS: ctx->opt_graphs = value != 0; return WM_OK;
+    case WM_OPT_MMA_ACCUM: ctx->opt_mma = value != 0; return WM_OK;
     default: return fail(ctx, WM_ERR_ARG, "unknown option");
     }
 }
@@ -787,7 +788,7 @@ int wm_detect_batch(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stri
 int wm_embed(wm_ctx* ctx, const wm_image* in, const wm_image* base, wm_image* out, int mask, float* a_host)
 {
     if (!ctx) return WM_ERR_ARG;
-    const std::string key = "E" + std::to_string(mask) + image_key(in) + image_key(base) + image_key(out) + std::to_string(ctx->opt_fp16) +
+    const std::string key = "E" + std::to_string(mask) + image_key(in) + image_key(base) + image_key(out) + std::to_string(ctx->opt_fp16 + 2 * ctx->opt_mma) +
                             std::to_string(ctx->opt_tma);
     return run_sync(ctx, key, 1, a_host, [&]() { return do_embed(ctx, 0, in, base, out, 0, 0, 0, 1, mask); });
 }
@@ -795,7 +796,7 @@ int wm_embed(wm_ctx* ctx, const wm_image* in, const wm_image* base, wm_image* ou
 int wm_detect(wm_ctx* ctx, const wm_image* img, int mask, float* corr_host)
 {
     if (!ctx) return WM_ERR_ARG;
-    const std::string key = "D" + std::to_string(mask) + image_key(img) + std::to_string(ctx->opt_fp16) + std::to_string(ctx->opt_tma);
+    const std::string key = "D" + std::to_string(mask) + image_key(img) + std::to_string(ctx->opt_fp16 + 2 * ctx->opt_mma) + std::to_string(ctx->opt_tma);
     return run_sync(ctx, key, 2, corr_host, [&]() { return do_detect(ctx, 0, img, 0, 1, mask); });
 }
 

@@ -3,14 +3,23 @@
 
 namespace wm {
 
-void launch_sweep(int dtype, bool fp16, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const SweepArgs& a)
+template <typename PixT, bool TMA>
+static void launch_sweep_t(int acc, int smem, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const SweepArgs& a)
+{
+    if (acc == 2) WM_LAUNCH((k_sweep<PixT, 2, TMA>), smem, tmI, a);
+    else if (acc == 1) WM_LAUNCH((k_sweep<PixT, 1, TMA>), smem, tmI, a);
+    else WM_LAUNCH((k_sweep<PixT, 0, TMA>), smem, tmI, a);
+}
+
+// acc: 0 = f32 products, 1 = fp16-rounded products + FHADD accumulation, 2 = fp16-rounded products + HMMA accumulation
+void launch_sweep(int dtype, int acc, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const SweepArgs& a)
 {
     if (dtype == WM_F32) {
-        if (tma) { if (fp16) WM_LAUNCH((k_sweep<float, true, true>), sweep_smem(true, false), tmI, a); else WM_LAUNCH((k_sweep<float, false, true>), sweep_smem(true, false), tmI, a); }
-        else { if (fp16) WM_LAUNCH((k_sweep<float, true, false>), sweep_smem(false, false), tmI, a); else WM_LAUNCH((k_sweep<float, false, false>), sweep_smem(false, false), tmI, a); }
+        if (tma) launch_sweep_t<float, true>(acc, sweep_smem(true, false), grid, st, tmI, a);
+        else launch_sweep_t<float, false>(acc, sweep_smem(false, false), grid, st, tmI, a);
     } else {
-        if (tma) { if (fp16) WM_LAUNCH((k_sweep<uint8_t, true, true>), sweep_smem(true, true), tmI, a); else WM_LAUNCH((k_sweep<uint8_t, false, true>), sweep_smem(true, true), tmI, a); }
-        else { if (fp16) WM_LAUNCH((k_sweep<uint8_t, true, false>), sweep_smem(false, true), tmI, a); else WM_LAUNCH((k_sweep<uint8_t, false, false>), sweep_smem(false, true), tmI, a); }
+        if (tma) launch_sweep_t<uint8_t, true>(acc, sweep_smem(true, true), grid, st, tmI, a);
+        else launch_sweep_t<uint8_t, false>(acc, sweep_smem(false, true), grid, st, tmI, a);
     }
 }
 

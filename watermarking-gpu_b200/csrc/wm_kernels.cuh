@@ -447,6 +447,41 @@ __device__ __forceinline__ void acc2_f16(float& a0, float& a1, float x, float y)
 }
 __device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
 
+// Accumulating the rounded products on the tensor pipe (ACC mode 2).  One legacy HMMA (mma.sync m16n8k16, f16 x f16 + f32)
+// with a 0/1 selector matrix as B acts as FOUR independent per-lane mixed-precision adds, c[i] += lo(h_i) + hi(h_i):
+//   D[g][2t] = A[g][2t] + A[g][2t+1] (this lane's a0), D[g][2t+1] = this lane's a2, rows g+8 likewise (a1, a3),
+// i.e. B[k][n] = 1 iff k in {n, n+1} (n even) or k in {n+7, n+8} (n odd).  Products by 1.0 are exact and the f32 accumulation of
+// integer-valued terms below 2^24 is exact, so integer-valued pixels give the same bits as the FHADD chain; one HMMA replaces
+// eight FHADD issue slots and runs on a pipe the rest of the sweep leaves idle.
+struct MmaSel { unsigned b0, b1; };
+__device__ __forceinline__ MmaSel mma_selector()
+{
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    MmaSel s;
+    s.b0 = (!(g & 1) && 2 * t == g) ? 0x3C003C00u : 0u;      // (1.0h, 1.0h)
+    s.b1 = ((g & 1) && 2 * t == g - 1) ? 0x3C003C00u : 0u;
+    return s;
+}
+__device__ __forceinline__ void mma_acc4(float* c, unsigned h0, unsigned h1, unsigned h2, unsigned h3, const MmaSel& s)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(h0), "r"(h2), "r"(h1), "r"(h3), "r"(s.b0), "r"(s.b1));  // a0 -> c0, a2 -> c1, a1 -> c2, a3 -> c3
+}
+__device__ __forceinline__ unsigned pack_f16(float lo, float hi)
+{
+    unsigned h;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+    return h;
+}
+__device__ __forceinline__ unsigned mul_h2(unsigned x, unsigned y)
+{
+    unsigned h;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h) : "r"(x), "r"(y));
+    return h;
+}
+constexpr int NACC = 16;  // HMMA accumulators: c[v] = lag v (v < 12), c[12..15] = four partial sums of lag 12
+
 // ------------------------------------------------------------------------------------------------
 // exact divisions without the generic IEEE slow path (Markstein: q = RN(a*y), r = a - q*b exactly, RN(q + r*y)
 // is the correctly rounded a/b when y = RN(1/b)).  x/9: verified exhaustively against x/9.0f for every float
@@ -686,13 +721,57 @@ __device__ __forceinline__ void sweep_tile(const float* __restrict__ tile, int l
             const float x1 = (FULL || (vl && vp[jj + 1])) ? A[jj + 3] : 0.0f;
             // lag (0, d): A; lag (1, d): B; lag (2, d): C
 #define WM_LAG(v, R, off)                                                                                           \
-    if constexpr (FP16) acc2_f16(e0[v], e1[v], __fmul_rn(x0, R[jj + 2 + (off)]), __fmul_rn(x1, R[jj + 3 + (off)])); \
+    if constexpr (FP16 != 0) acc2_f16(e0[v], e1[v], __fmul_rn(x0, R[jj + 2 + (off)]), __fmul_rn(x1, R[jj + 3 + (off)])); \
     else { e0[v] = __fmaf_rn(x0, R[jj + 2 + (off)], e0[v]); e1[v] = __fmaf_rn(x1, R[jj + 3 + (off)], e1[v]); }
             WM_LAG(0, A, 0) WM_LAG(1, A, 1) WM_LAG(2, A, 2)
             WM_LAG(3, B, -2) WM_LAG(4, B, -1) WM_LAG(5, B, 0) WM_LAG(6, B, 1) WM_LAG(7, B, 2)
             WM_LAG(8, C, -2) WM_LAG(9, C, -1) WM_LAG(10, C, 0) WM_LAG(11, C, 1) WM_LAG(12, C, 2)
 #undef WM_LAG
         }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { A[i] = B[i]; B[i] = C[i]; }
+    }
+}
+
+// the same 13 lags with the rounded products summed by HMMA (see mma_acc4): per pixel pair 3 HMMAs take lags 0..11, the
+// four lag-12 pairs of two lines share a fourth
+template <bool FULL>
+__device__ __forceinline__ void sweep_tile_mma(const float* __restrict__ tile, int l0, int p0, int L, int P,
+                                               float (&c)[NACC], const MmaSel& sel)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float* base = tile + (4 * w) * SW + 4 * lane + 2;
+    const int pb = p0 + 4 * lane;
+    bool vp[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) vp[j] = FULL || ((pb + j >= 1) && (pb + j <= P - 2));
+    float A[8], B[8], C[8];
+    auto loadrow = [](float (&r)[8], const float* s) {
+        const float2 x = *reinterpret_cast<const float2*>(s);
+        const float4 y = *reinterpret_cast<const float4*>(s + 2);
+        const float2 z = *reinterpret_cast<const float2*>(s + 6);
+        r[0] = x.x; r[1] = x.y; r[2] = y.x; r[3] = y.y; r[4] = y.z; r[5] = y.w; r[6] = z.x; r[7] = z.y;
+    };
+    loadrow(A, base);
+    loadrow(B, base + SW);
+    unsigned q12[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        loadrow(C, base + (r + 2) * SW);
+        const int l = l0 + 4 * w + r;
+        const bool vl = FULL || ((l >= 1) && (l <= L - 2));
+#pragma unroll
+        for (int jj = 0; jj < 4; jj += 2) {
+            const float x0 = (FULL || (vl && vp[jj])) ? A[jj + 2] : 0.0f;
+            const float x1 = (FULL || (vl && vp[jj + 1])) ? A[jj + 3] : 0.0f;
+#define WM_PK(R, off) pack_f16(__fmul_rn(x0, R[jj + 2 + (off)]), __fmul_rn(x1, R[jj + 3 + (off)]))
+            mma_acc4(c + 0, WM_PK(A, 0), WM_PK(A, 1), WM_PK(A, 2), WM_PK(B, -2), sel);
+            mma_acc4(c + 4, WM_PK(B, -1), WM_PK(B, 0), WM_PK(B, 1), WM_PK(B, 2), sel);
+            mma_acc4(c + 8, WM_PK(C, -2), WM_PK(C, -1), WM_PK(C, 0), WM_PK(C, 1), sel);
+            q12[(r & 1) * 2 + (jj >> 1)] = WM_PK(C, 2);
+#undef WM_PK
+        }
+        if (r & 1) mma_acc4(c + 12, q12[0], q12[1], q12[2], q12[3], sel);
 #pragma unroll
         for (int i = 0; i < 8; i++) { A[i] = B[i]; B[i] = C[i]; }
     }
@@ -756,7 +835,57 @@ __device__ __forceinline__ void sweep_tile_h2(const __half* __restrict__ tile, i
     }
 }
 
-template <typename PixT, bool FP16, bool TMA>
+template <bool FULL>
+__device__ __forceinline__ void sweep_tile_h2_mma(const __half* __restrict__ tile, int l0, int p0, int L, int P,
+                                                  float (&c)[NACC], const MmaSel& sel)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const __half* base = tile + (4 * w) * SW + 4 * lane + 2;
+    const int pb = p0 + 4 * lane;
+    unsigned m01 = 0xffffffffu, m23 = 0xffffffffu;
+    if (!FULL) {
+        m01 = ((pb >= 1 && pb <= P - 2) ? 0x0000ffffu : 0u) | ((pb + 1 >= 1 && pb + 1 <= P - 2) ? 0xffff0000u : 0u);
+        m23 = ((pb + 2 >= 1 && pb + 2 <= P - 2) ? 0x0000ffffu : 0u) | ((pb + 3 >= 1 && pb + 3 <= P - 2) ? 0xffff0000u : 0u);
+    }
+    struct Row { unsigned h[4], s[3]; };
+    auto loadrow = [](Row& r, const __half* q) {
+        r.h[0] = *reinterpret_cast<const unsigned*>(q);
+        const uint2 mid = *reinterpret_cast<const uint2*>(q + 2);
+        r.h[1] = mid.x; r.h[2] = mid.y;
+        r.h[3] = *reinterpret_cast<const unsigned*>(q + 6);
+#pragma unroll
+        for (int i = 0; i < 3; i++) r.s[i] = __byte_perm(r.h[i], r.h[i + 1], 0x5432);
+    };
+    Row A, B, C;
+    loadrow(A, base);
+    loadrow(B, base + SW);
+    unsigned q12[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        loadrow(C, base + (r + 2) * SW);
+        unsigned x01 = A.h[1], x23 = A.h[2];
+        if (!FULL) {
+            const int l = l0 + 4 * w + r;
+            const bool vl = (l >= 1) && (l <= L - 2);
+            x01 = vl ? (x01 & m01) : 0u;
+            x23 = vl ? (x23 & m23) : 0u;
+        }
+        // pixel pair (0,1): partner pair of lag (dl, dp) is (dp, 1+dp); pair (2,3): (2+dp, 3+dp)
+        mma_acc4(c + 0, mul_h2(x01, A.h[1]), mul_h2(x01, A.s[1]), mul_h2(x01, A.h[2]), mul_h2(x01, B.h[0]), sel);
+        mma_acc4(c + 4, mul_h2(x01, B.s[0]), mul_h2(x01, B.h[1]), mul_h2(x01, B.s[1]), mul_h2(x01, B.h[2]), sel);
+        mma_acc4(c + 8, mul_h2(x01, C.h[0]), mul_h2(x01, C.s[0]), mul_h2(x01, C.h[1]), mul_h2(x01, C.s[1]), sel);
+        mma_acc4(c + 0, mul_h2(x23, A.h[2]), mul_h2(x23, A.s[2]), mul_h2(x23, A.h[3]), mul_h2(x23, B.h[1]), sel);
+        mma_acc4(c + 4, mul_h2(x23, B.s[1]), mul_h2(x23, B.h[2]), mul_h2(x23, B.s[2]), mul_h2(x23, B.h[3]), sel);
+        mma_acc4(c + 8, mul_h2(x23, C.h[1]), mul_h2(x23, C.s[1]), mul_h2(x23, C.h[2]), mul_h2(x23, C.s[2]), sel);
+        q12[(r & 1) * 2] = mul_h2(x01, C.h[2]);
+        q12[(r & 1) * 2 + 1] = mul_h2(x23, C.h[3]);
+        if (r & 1) mma_acc4(c + 12, q12[0], q12[1], q12[2], q12[3], sel);
+        A = B; B = C;
+    }
+}
+
+// FP16: 0 = f32 products (FFMA), 1 = products rounded to fp16, FHADD accumulation, 2 = rounded, HMMA accumulation
+template <typename PixT, int FP16, bool TMA>
 __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_constant__ CUtensorMap tmI, const SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char dsm[];
@@ -795,16 +924,27 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
         // f64 accumulators of the 13 lags: one column per thread in smem ([v][thread], conflict-free), so they cost no
         // registers; the f32 pair (e0, e1) is flushed into them every 8 tiles (64 px per accumulator: exact for integers)
         double* const dsh = reinterpret_cast<double*>(dsm + sweep_smem(TMA, sizeof(PixT) == 1) - SWEEP_ACC) + threadIdx.x;
-        float e0[NLAG], e1[NLAG];  // even / odd pixel accumulators
+        float e0[NLAG], e1[NLAG];  // even / odd pixel accumulators (FP16 modes 0, 1)
+        float cm[NACC];            // HMMA accumulators (mode 2): 128 products each between flushes (128 * 65504 < 2^24)
+        const MmaSel sel = mma_selector();
 #pragma unroll
         for (int v = 0; v < NLAG; v++) { dsh[v * NT] = 0.0; e0[v] = 0.0f; e1[v] = 0.0f; }
-        auto flush = [&]() {
 #pragma unroll
-            for (int v = 0; v < NLAG; v++) { dsh[v * NT] += (double)__fadd_rn(e0[v], e1[v]); e0[v] = 0.0f; e1[v] = 0.0f; }
+        for (int v = 0; v < NACC; v++) cm[v] = 0.0f;
+        auto flush = [&]() {
+            if constexpr (FP16 == 2) {
+#pragma unroll
+                for (int v = 0; v < NLAG - 1; v++) { dsh[v * NT] += (double)cm[v]; cm[v] = 0.0f; }
+                dsh[(NLAG - 1) * NT] += (double)__fadd_rn(__fadd_rn(cm[12], cm[13]), __fadd_rn(cm[14], cm[15]));
+                cm[12] = cm[13] = cm[14] = cm[15] = 0.0f;
+            } else {
+#pragma unroll
+                for (int v = 0; v < NLAG; v++) { dsh[v * NT] += (double)__fadd_rn(e0[v], e1[v]); e0[v] = 0.0f; e1[v] = 0.0f; }
+            }
         };
         StagePos<NST> pos;
         int k = 0;
-        if constexpr (U8T && FP16) {
+        if constexpr (U8T && FP16 != 0) {
             // u8 frames: fp16 work tiles + packed-half products.  Software pipeline with ONE barrier per tile: while tile k
             // is computed from work tile k&1, tile k+1 (already landed) is widened into the other work tile; the TMA
             // of tile k+NST-1 is issued at the top, so loads, conversion and arithmetic of three different tiles overlap.
@@ -836,8 +976,13 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
                     pos.next();
                 }
                 const bool full = l0 >= 1 && l0 + TL <= L - 1 && p0 >= 1 && p0 + TP <= P - 1;
-                if (full) sweep_tile_h2<true>(cur, l0, p0, L, P, e0, e1);
-                else sweep_tile_h2<false>(cur, l0, p0, L, P, e0, e1);
+                if constexpr (FP16 == 2) {
+                    if (full) sweep_tile_h2_mma<true>(cur, l0, p0, L, P, cm, sel);
+                    else sweep_tile_h2_mma<false>(cur, l0, p0, L, P, cm, sel);
+                } else {
+                    if (full) sweep_tile_h2<true>(cur, l0, p0, L, P, e0, e1);
+                    else sweep_tile_h2<false>(cur, l0, p0, L, P, e0, e1);
+                }
                 if ((k & 7) == 7) flush();
                 __syncthreads();  // nxt complete, cur free, the stage just converted may be refilled
                 if (has_next && tile_on_frame<TL + 2>(ntl * TL, ntp * TP - HP, L, P)) { fix_border<TL + 2>(nxt, ntl * TL, ntp * TP - HP, L, P); __syncthreads(); }
@@ -870,8 +1015,13 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
                 tile = work;
             }
             const bool full = l0 >= 1 && l0 + TL <= L - 1 && p0 >= 1 && p0 + TP <= P - 1;
-            if (full) sweep_tile<FP16, true>(tile, l0, p0, L, P, e0, e1);
-            else sweep_tile<FP16, false>(tile, l0, p0, L, P, e0, e1);
+            if constexpr (FP16 == 2) {
+                if (full) sweep_tile_mma<true>(tile, l0, p0, L, P, cm, sel);
+                else sweep_tile_mma<false>(tile, l0, p0, L, P, cm, sel);
+            } else {
+                if (full) sweep_tile<FP16 != 0, true>(tile, l0, p0, L, P, e0, e1);
+                else sweep_tile<FP16 != 0, false>(tile, l0, p0, L, P, e0, e1);
+            }
             if ((k & 7) == 7) flush();
             if constexpr (TMA) __syncthreads();  // the stage just read may be refilled from the next iteration on
         }
@@ -947,7 +1097,7 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
                         const int i = pi[q], j = pj[q];
                         const int li = i < 4 ? i : i + 1, lj = j == 8 ? 4 : (j < 4 ? j : j + 1);  // neighbour index -> window slot
                         float pr = __fmul_rn(win[px * 9 + li], win[px * 9 + lj]);
-                        if constexpr (FP16) pr = round_f16(pr);
+                        if constexpr (FP16 != 0) pr = round_f16(pr);
                         // rx[i], i <= 3 and every Rx pair: counted when p + o_i is not a core pixel; rx[i], i >= 4: when p is not
                         const bool use = (j == 8 && i >= 4) ? ((ncmask >> 4) & 1) : ((ncmask >> li) & 1);
                         if (lane + 32 * q < NFRM && use) { if (q == 0) f0 += (double)pr; else f1 += (double)pr; }
@@ -977,7 +1127,7 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
                 }
 #pragma unroll
                 for (int t = 0; t < NFRM; t += 2) {
-                    if constexpr (FP16) acc2_f16(tacc[t], tacc[t + 1], pr[t], pr[t + 1]);
+                    if constexpr (FP16 != 0) acc2_f16(tacc[t], tacc[t + 1], pr[t], pr[t + 1]);
                     else { tacc[t] = __fadd_rn(tacc[t], pr[t]); tacc[t + 1] = __fadd_rn(tacc[t + 1], pr[t + 1]); }
                 }
             }

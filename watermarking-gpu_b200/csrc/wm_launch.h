@@ -3,7 +3,7 @@
 #include "wm_kernels.cuh"
 
 namespace wm {
-void launch_sweep(int dtype, bool fp16, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const SweepArgs& a);
+void launch_sweep(int dtype, int acc, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const SweepArgs& a);
 void launch_stats(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a);
 void launch_apply(int in_dtype, int out_dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI,
                   const CUtensorMap& tmW, const EmbedArgs& a);
