@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--exact", action="store_true", help="f32 products in Rx/rx instead of the reference's fp16 rounding")
+    ap.add_argument("--frames", type=int, default=0, help="frames per step (0 = the workload's own count)")
+    ap.add_argument("--fhadd", action="store_true", help="sum the rounded Rx/rx products with the FHADD chain instead of HMMA (A/B)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per API call (0 = the whole batch in one call)")
     ap.add_argument("--slots", type=int, default=2, help="pipeline slots (streams) used round-robin when --chunk is set")
     args = ap.parse_args()
@@ -223,12 +225,16 @@ def main():
     C = pkg.C
 
     rows, cols, nfr, kind, dtype = WORKLOADS[wl]
+    if args.frames:
+        nfr = args.frames
     npx = rows * cols
     frames_np, W = make_inputs(rows, cols, nfr, dtype)
     stream = torch.cuda.Stream(device=dev)
     wm = pkg.Watermark(rows, cols, W, 3, 40.0, device=local_rank, stream=stream.cuda_stream)
     if args.exact:
         wm.set_option(pkg.OPT_FP16_PRODUCTS, 0)
+    if args.fhadd:
+        wm.set_option(pkg.OPT_MMA_ACCUM, 0)
     tdt = torch.uint8 if dtype == "u8" else torch.float32
     dt_code = pkg.U8 if dtype == "u8" else pkg.F32
     # image workloads: ArrayFire layout (column-major); video: row-major Y planes

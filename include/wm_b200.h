@@ -117,9 +117,11 @@ int wm_rgb2gray(wm_ctx *ctx, const wm_image *rgb, wm_image *gray, float wr, floa
  *   WM_DBG_RXVEC   8 doubles  rx                                                  Watermark.cpp:149
  *   WM_DBG_COEFFS  8 floats   prediction coefficients                             Watermark.cpp:203
  *   WM_DBG_SCALARS 8 doubles  {status, a, max|e|, sum (|mask|W)^2, dot, |ez|^2, |eu|^2, corr}
+ *   WM_DBG_PHASES  8 doubles  timeline of the last Rx sweep's last CTA, ns since that CTA started: [1] tiles done, [2] frame
+ *                             ring done, [3] elected last, [4] second-stage sums done, [5] 8x8 system solved (profiling aid)
  * wm_debug_set_coeffs injects coefficients: the next call skips the Rx sweep + solve (staged parity).
  * wm_debug_planes computes e_z (or NVF mask when what == WM_DBG_MASK_NVF) for an image into dst_dev. */
-enum { WM_DBG_RX = 0, WM_DBG_RXVEC = 1, WM_DBG_COEFFS = 2, WM_DBG_SCALARS = 3, WM_DBG_ERRSEQ = 4, WM_DBG_MASK_NVF = 5 };
+enum { WM_DBG_RX = 0, WM_DBG_RXVEC = 1, WM_DBG_COEFFS = 2, WM_DBG_SCALARS = 3, WM_DBG_ERRSEQ = 4, WM_DBG_MASK_NVF = 5, WM_DBG_PHASES = 6 };
 int wm_debug_get(wm_ctx *ctx, int what, void *dst_host);
 int wm_debug_set_coeffs(wm_ctx *ctx, const float *coeffs8_or_null);
 int wm_debug_plane(wm_ctx *ctx, const wm_image *img, int what, float *dst_dev /* same layout, dense */);

@@ -52,6 +52,14 @@ def main():
         if n:
             print("   kernel %-13s %5d launches  avg %7.2f us" % (name, n, 1e3 * ms / n))
     wm.set_option(pkg.OPT_KERNEL_TIMING, 0)
+    # timeline of the Rx sweep's critical path: the CTA that finishes last (second stage + solve), from %globaltimer
+    ph = []
+    for _ in range(20):
+        wm.detectWatermark(out, pkg.ME)
+        ph.append(wm.debug(pkg.DBG_PHASES))
+    import numpy as np
+    ph = np.median(np.array(ph), axis=0) / 1e3
+    print("   rx_sweep last CTA (us since its start): tiles %.1f | ring %.1f | elected %.1f | second-stage sums %.1f | solved %.1f" % tuple(ph[1:6]))
     tot = sum(res.values())
     print("all four ops: %.1f us -> %.1f frames/s (single image, synchronous calls, %dx%d)" % (tot * 1e6, 1.0 / tot, a.rows, a.cols))
 

@@ -22,7 +22,7 @@ COL_MAJOR, ROW_MAJOR = 0, 1
 F32, U8 = 0, 1
 OK, SINGULAR, ZERO_MASK = 0, 1, 2
 OPT_FP16_PRODUCTS, OPT_KERNEL_TIMING, OPT_USE_TMA, OPT_SERIAL_SLOTS, OPT_CUDA_GRAPHS, OPT_MMA_ACCUM = 1, 2, 3, 4, 5, 6
-DBG_RX, DBG_RXVEC, DBG_COEFFS, DBG_SCALARS, DBG_ERRSEQ, DBG_MASK_NVF = range(6)
+DBG_RX, DBG_RXVEC, DBG_COEFFS, DBG_SCALARS, DBG_ERRSEQ, DBG_MASK_NVF, DBG_PHASES = range(7)
 KERNEL_NAMES = ["rx_sweep", "me_stats", "nvf_stats", "embed_apply", "detect_apply"]
 VIDEO_EMBED, VIDEO_DETECT = 0, 1
 
@@ -350,7 +350,7 @@ class Watermark:
     # -- parity access ----------------------------------------------------------------------------
     def debug(self, what):
         shapes = {DBG_RX: (np.float64, 64), DBG_RXVEC: (np.float64, 8), DBG_COEFFS: (np.float32, 8),
-                  DBG_SCALARS: (np.float64, 8)}
+                  DBG_SCALARS: (np.float64, 8), DBG_PHASES: (np.float64, 8)}
         dt, n = shapes[what]
         out = np.zeros(n, dt)
         self._check(lib().wm_debug_get(self._h, what, out.ctypes.data))

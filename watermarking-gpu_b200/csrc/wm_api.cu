@@ -896,6 +896,11 @@ int wm_debug_get(wm_ctx* ctx, int what, void* dst)
         o[0] = h.status; o[1] = h.a; o[2] = h.emax; o[3] = d.sum2; o[4] = d.dot; o[5] = d.nz; o[6] = d.nu; o[7] = h.corr;
         return WM_OK;
     }
+    case WM_DBG_PHASES: {
+        double* o = (double*)dst;
+        for (int i = 0; i < 8; i++) o[i] = (i >= 1 && i <= 5) ? (double)(long long)(d.ts[i] - d.ts[0]) : 0.0;
+        return WM_OK;
+    }
     default: return fail(ctx, WM_ERR_ARG, "unknown debug item");
     }
 }

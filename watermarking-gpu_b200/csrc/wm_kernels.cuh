@@ -86,9 +86,16 @@ struct ScalDbg {
     double dot, nz, nu;
     double Rx[64];   // reference order, full symmetric
     double rx[8];
+    unsigned long long ts[8];  // k_sweep, last block of the image: %globaltimer (ns) at start / tiles done / ring done / elected / sums done / solved
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // CTAs working on image b of a batch: the launch's one wave of resident CTAs is split as evenly as possible, the first
 // `extra` images get one more (gridDim.x = base + (extra > 0); the surplus CTAs of the other images exit at once)
 __device__ __forceinline__ int blocks_of_image(int base, int extra, int b) { return base + (b < extra ? 1 : 0); }
@@ -415,20 +422,37 @@ __device__ __forceinline__ bool last_block(unsigned* counter, unsigned nblocks)
     return s_last != 0;
 }
 
-// fixed-order sum over blocks of column v of a [nblk][nv] f64 partial array, executed by one warp
-__device__ __forceinline__ double column_sum(const double* part, int nblk, int nv, int v)
+// Second stage, executed by the whole last block: column totals of a [nblk][NV] f64 partial array in a fixed order.
+// Thread t owns column t % NVP and row group t / NVP (G = NT / NVP groups, rows g, g + G, ...); a warp reads 32 consecutive
+// doubles of a row (coalesced) and every thread keeps 16 independent L2 loads in flight, so the whole array streams in a
+// few L2 round trips instead of one per row.  Columns >= MAXV0 are combined with max (non-negative values), the rest
+// with +.  out[v] (smem, NV entries) is valid for all threads after the call; scratch: NT doubles of smem.
+template <int NV, int NVP, int MAXV0>
+__device__ __forceinline__ void block_column_reduce(const double* __restrict__ part, int nblk, double* out, double* scratch)
 {
-    const int lane = threadIdx.x & 31;
-    double s = 0.0;
-    for (int b = lane; b < nblk; b += 32) s += __ldcg(part + (size_t)b * nv + v);
-    return warp_sum(s);
-}
-__device__ __forceinline__ float column_max(const double* part, int nblk, int nv, int v)
-{
-    const int lane = threadIdx.x & 31;
-    float s = 0.0f;
-    for (int b = lane; b < nblk; b += 32) s = fmaxf(s, (float)__ldcg(part + (size_t)b * nv + v));
-    return warp_max(s);
+    static_assert(NVP >= NV && (NVP & (NVP - 1)) == 0 && NVP <= NT, "NVP: power of two >= NV");
+    constexpr int G = NT / NVP, U = 16;
+    const int v = threadIdx.x & (NVP - 1), g = threadIdx.x / NVP;
+    double acc = 0.0;
+    if (v < NV) {
+        const double* col = part + v;
+        for (int b0 = g; b0 < nblk; b0 += G * U) {
+            double x[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) { const int b = b0 + u * G; x[u] = b < nblk ? __ldcg(col + (size_t)b * NV) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < U; u++) acc = v >= MAXV0 ? fmax(acc, x[u]) : acc + x[u];
+        }
+    }
+    scratch[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double t = scratch[threadIdx.x];
+#pragma unroll 4
+        for (int k = 1; k < G; k++) { const double y = scratch[k * NVP + threadIdx.x]; t = (int)threadIdx.x >= MAXV0 ? fmax(t, y) : t + y; }
+        out[threadIdx.x] = t;
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -899,6 +923,8 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nblk = blocks_of_image(a.nblk_base, a.nblk_extra, b);
     if ((int)blockIdx.x >= nblk) return;
+    unsigned long long ts0 = 0, ts1 = 0, ts2 = 0;
+    if (threadIdx.x == 0) ts0 = gtime();
 
     {
         const int sb = blockIdx.x, step = nblk;
@@ -1035,6 +1061,7 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
         if (threadIdx.x < NLAG) part[(size_t)sb * NTOT + threadIdx.x] = red[threadIdx.x];
         __syncthreads();
     }
+    if (threadIdx.x == 0) ts1 = gtime();
     {
         // ---- frame ring: pixels within 2 of the border, naive products guarded by "partner not in core" ----
         const int fb = blockIdx.x;
@@ -1063,7 +1090,7 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
         //       44 products in registers (32x fewer warp instructions per pixel), one block reduction at the end.
         float* win = reinterpret_cast<float*>(dsm);            // [NT][9]  (the tile stages are idle by now)
         unsigned* ncm = reinterpret_cast<unsigned*>(win + NT * 9);  // [NT]
-        const bool per_thread = count > (long long)nblk * 512;
+        const bool per_thread = count > (long long)nblk * 96;
         double f0 = 0.0, f1 = 0.0;
         float tacc[NFRM];
 #pragma unroll
@@ -1142,7 +1169,23 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
         }
         __syncthreads();
         if (per_thread) {
-            block_sum_f32<NFRM>(tacc, red);
+            // block reduction through smem (the tile stages and lag accumulators are idle by now): [NFRM][NT] floats, then
+            // four threads per partial sum 64 columns each in f64 (column index rotated by the thread id: conflict-free)
+            float* redf = reinterpret_cast<float*>(dsm);
+#pragma unroll
+            for (int v = 0; v < NFRM; v++) redf[v * NT + threadIdx.x] = tacc[v];
+            __syncthreads();
+            static_assert(NFRM * NT * 4 <= sweep_smem(false, false), "ring reduction buffer must fit the smallest sweep smem");
+            if (threadIdx.x < ((4 * NFRM + 31) & ~31)) {  // whole warps (shuffles below); the surplus lanes redo the last partial
+                const float* col = redf + min((int)threadIdx.x >> 2, NFRM - 1) * NT + (threadIdx.x & 3) * (NT / 4);
+                double sacc = 0.0;
+#pragma unroll 8
+                for (int k = 0; k < NT / 4; k++) sacc += (double)col[(k + threadIdx.x) & (NT / 4 - 1)];
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+                if ((threadIdx.x & 3) == 0 && threadIdx.x < 4 * NFRM) red[threadIdx.x >> 2] = sacc;
+            }
+            __syncthreads();
             if (threadIdx.x < NFRM) part[(size_t)fb * NTOT + NLAG + threadIdx.x] = ftot + red[threadIdx.x];
         } else {
             red[w * NFRM + lane] = f0;
@@ -1158,15 +1201,19 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
     }
 
     // ---- second stage + solve in the last block ----
+    if (threadIdx.x == 0) ts2 = gtime();
     if (!last_block(a.counter + b, nblk)) return;
+    unsigned long long ts3 = 0, ts4 = 0;
+    if (threadIdx.x == 0) ts3 = gtime();
     __shared__ double tot[NTOT];
     __shared__ double M[72];
-    for (int v = w; v < NTOT; v += NT / 32) {
-        const double s = column_sum(part, nblk, NTOT, v);
-        if (lane == 0) tot[v] = s;
-    }
-    __syncthreads();
+    block_column_reduce<NTOT, 64, NTOT>(part, nblk, tot, reinterpret_cast<double*>(dsm));
+    if (threadIdx.x == 0) ts4 = gtime();
     if (w == 0) solve_system(tot, a.scal + b, a.dbg + b, a.transposed, M);
+    if (threadIdx.x == 0) {
+        unsigned long long* ts = a.dbg[b].ts;
+        ts[0] = ts0; ts[1] = ts1; ts[2] = ts2; ts[3] = ts3; ts[4] = ts4; ts[5] = gtime(); ts[6] = 0; ts[7] = 0;
+    }
 }
 
 // ================================================================================================
@@ -1348,10 +1395,11 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
         }
     }
     if (!last_block(a.counter + b, nblk)) return;
+    __shared__ double tot2[2];
+    block_column_reduce<2, 2, 1>(a.part + (size_t)b * gridDim.x * 2, nblk, tot2, reinterpret_cast<double*>(dsm));
     if (w == 0) {
-        const double* part = a.part + (size_t)b * gridDim.x * 2;
-        const double S2 = column_sum(part, nblk, 2, 0);
-        const float mx = column_max(part, nblk, 2, 1);
+        const double S2 = tot2[0];
+        const float mx = (float)tot2[1];
         if (lane == 0) {
             double nrm = sqrt(S2);
             if (MASK == 0) nrm = nrm / (double)mx;
@@ -1682,11 +1730,7 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
     block_sum<3>(v3, red);
     if (threadIdx.x < 3) a.part[((size_t)b * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = red[threadIdx.x];
     if (!last_block(a.counter + b, step)) return;
-    if (w < 3) {
-        const double s = column_sum(a.part + (size_t)b * gridDim.x * 3, step, 3, w);
-        if (lane == 0) red[w] = s;
-    }
-    __syncthreads();
+    block_column_reduce<3, 4, 3>(a.part + (size_t)b * gridDim.x * 3, step, red, reinterpret_cast<double*>(dsm));
     if (threadIdx.x == 0) {
         a.dbg[b].dot = red[0]; a.dbg[b].nz = red[1]; a.dbg[b].nu = red[2];
         const float dotf = (float)red[0];
