@@ -26,7 +26,12 @@ def kname(full):
 
 
 def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .csv is the raw page already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv`): the captures
+    # themselves (40-50 MB each) do not fit gpurun's 64 MiB return channel together
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
 

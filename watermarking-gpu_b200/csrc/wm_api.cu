@@ -21,7 +21,7 @@ using namespace wm;
 
 namespace {
 
-constexpr int NSLOTS = 4;
+constexpr int NSLOTS = 8;
 thread_local std::string g_create_error;
 
 struct WShared {  // W is shared between clones, like the ref-counted af::array (Watermark.cpp:31)
@@ -989,8 +989,13 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
     // blockIdx.y); runs go round-robin over the slots so copies, kernels and the per-frame solves of different runs overlap
     const int64_t fbytes = H * Wd;
     int64_t B = v->frames_on_device ? std::max<int64_t>(1, std::min<int64_t>(32, (64LL << 20) / fbytes)) : 4;
-    for (int64_t g = 0, run = 0; g < ngated; g += B, run++) {
-        const int nb = (int)std::min<int64_t>(B, ngated - g);
+    // even runs (37 frames at 7 per run: 7,6,6,6,6,6 rather than 7,7,7,7,7,2)
+    const int64_t nruns = ngated > 0 ? (ngated + B - 1) / B : 0;
+    const int64_t run_base = nruns ? ngated / nruns : 0, run_extra = nruns ? ngated % nruns : 0;
+    B = run_base + (run_extra ? 1 : 0);
+    for (int64_t g = 0, run = 0, nbr = 0; run < nruns; g += nbr, run++) {
+        nbr = run_base + (run < run_extra ? 1 : 0);
+        const int nb = (int)nbr;
         const int si = ctx->opt_serial ? 0 : (int)(run % NSLOTS);
         Slot& s = ctx->slots[si];
         const int64_t i = i0 + g * K;

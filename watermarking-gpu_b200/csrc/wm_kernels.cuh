@@ -1090,17 +1090,26 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
         //       44 products in registers (32x fewer warp instructions per pixel), one block reduction at the end.
         float* win = reinterpret_cast<float*>(dsm);            // [NT][9]  (the tile stages are idle by now)
         unsigned* ncm = reinterpret_cast<unsigned*>(win + NT * 9);  // [NT]
-        const bool per_thread = count > (long long)nblk * 96;
+        // The ring is shared by the CTAs that walked one tile fewer than the others (when the tiles do not divide evenly and
+        // at least half of the CTAs are in that group), in equal contiguous slices — so a single image's critical path is
+        // max(2 tiles, 1 tile + ring slice), not 2 tiles + a 256-pixel chunk.
+        const int nlong = a.ntiles % nblk;  // CTAs 0 .. nlong-1 walked one more tile
+        const bool light_only = nlong != 0 && 2 * (nblk - nlong) >= nblk;
+        const int nring = light_only ? nblk - nlong : nblk;
+        const int rslot = light_only ? fb - nlong : fb;  // < 0: this CTA takes no ring pixels (its partials are zeros)
+        const long long per = (count + nring - 1) / nring;
+        const long long ring_lo = rslot < 0 ? count : min(count, per * rslot), ring_hi = rslot < 0 ? count : min(count, ring_lo + per);
+        const bool per_thread = per > 96;
         double f0 = 0.0, f1 = 0.0;
         float tacc[NFRM];
 #pragma unroll
         for (int v = 0; v < NFRM; v++) tacc[v] = 0.0f;
         int chunks = 0;
         double ftot = 0.0;  // mode (b): thread t < NFRM keeps the block total of partial t
-        for (long long c0 = (long long)fb * NT; c0 < count; c0 += (long long)nblk * NT) {
+        for (long long c0 = ring_lo; c0 < ring_hi; c0 += NT) {
             const long long idx = c0 + threadIdx.x;
             __syncthreads();
-            if (idx < count) {
+            if (idx < ring_hi) {
                 int l, p;
                 if (idx < n1) { l = (int)(idx / P); p = (int)(idx - (long long)l * P); }
                 else if (idx < n2) { const long long i2 = idx - n1; const int q = (int)(i2 / P); l = lbot + q; p = (int)(i2 - (long long)q * P); }
@@ -1115,7 +1124,7 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
                 ncm[threadIdx.x] = m;
             }
             __syncthreads();
-            const int nhere = (int)min((long long)NT, count - c0);
+            const int nhere = (int)min((long long)NT, ring_hi - c0);
             if (!per_thread) {
                 for (int px = w; px < nhere; px += NT / 32) {
                     const unsigned ncmask = ncm[px];
