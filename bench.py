@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--no-sync-proto", action="store_true", help="skip the single-image synchronous-call measurement (keeps ncu launch lists to the timed region)")
     ap.add_argument("--exact", action="store_true", help="f32 products in Rx/rx instead of the reference's fp16 rounding")
     ap.add_argument("--frames", type=int, default=0, help="frames per step (0 = the workload's own count)")
+    ap.add_argument("--no-tma", action="store_true", help="plain register-prefetched tile loaders instead of TMA (A/B)")
     ap.add_argument("--fhadd", action="store_true", help="sum the rounded Rx/rx products with the FHADD chain instead of HMMA (A/B)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per API call (0 = the whole batch in one call)")
     ap.add_argument("--slots", type=int, default=2, help="pipeline slots (streams) used round-robin when --chunk is set")
@@ -237,6 +238,8 @@ def main():
         wm.set_option(pkg.OPT_FP16_PRODUCTS, 0)
     if args.fhadd:
         wm.set_option(pkg.OPT_MMA_ACCUM, 0)
+    if args.no_tma:
+        wm.set_option(pkg.OPT_USE_TMA, 0)
     tdt = torch.uint8 if dtype == "u8" else torch.float32
     dt_code = pkg.U8 if dtype == "u8" else pkg.F32
     # image workloads: ArrayFire layout (column-major); video: row-major Y planes

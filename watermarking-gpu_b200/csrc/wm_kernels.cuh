@@ -287,37 +287,67 @@ struct WTilePrefetch {
     }
 };
 
-// u8 TMA stage (rows of U8_ROW bytes) -> f32 work tile (rows of SW floats)
+// u8 TMA stage (rows of U8_ROW bytes) -> f32 work tile (rows of SW floats).  Warp w takes rows w, w + 8, ...; lane l takes
+// the 4-pixel chunk l of the row (no index division, conflict-free LDS.32 / STS.128, every load issued before the first
+// conversion); the two chunks beyond 32 lanes (pixels 128..135) of all rows are one extra predicated step.
 template <int NROWS>
 __device__ __forceinline__ void convert_u8_tile(const unsigned char* __restrict__ src, float* __restrict__ dst)
 {
-    constexpr int CH = SW / 4;
-    for (int idx = threadIdx.x; idx < NROWS * CH; idx += NT) {
-        const int r = idx / CH, c = idx - r * CH;
-        const uchar4 u = *reinterpret_cast<const uchar4*>(src + r * U8_ROW + U8_OFF + 4 * c);
-        *reinterpret_cast<float4*>(dst + 4 * idx) = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
-    }
+    constexpr int NIT = (NROWS + NT / 32 - 1) / (NT / 32);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned char* s0 = src + w * U8_ROW + U8_OFF + 4 * lane;
+    float* d0 = dst + w * SW + 4 * lane;
+    unsigned u[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; i++)
+        if (w + i * (NT / 32) < NROWS) u[i] = *reinterpret_cast<const unsigned*>(s0 + i * (NT / 32) * U8_ROW);
+    const bool tail = threadIdx.x < 2 * NROWS;  // row t / 2, chunk 32 + t % 2
+    const int tr = threadIdx.x >> 1, tc = 32 + (threadIdx.x & 1);
+    unsigned ut = 0;
+    if (tail) ut = *reinterpret_cast<const unsigned*>(src + tr * U8_ROW + U8_OFF + 4 * tc);
+#pragma unroll
+    for (int i = 0; i < NIT; i++)
+        if (w + i * (NT / 32) < NROWS)
+            *reinterpret_cast<float4*>(d0 + i * (NT / 32) * SW) =
+                make_float4((float)(u[i] & 0xffu), (float)((u[i] >> 8) & 0xffu), (float)((u[i] >> 16) & 0xffu), (float)(u[i] >> 24));
+    if (tail)
+        *reinterpret_cast<float4*>(dst + tr * SW + 4 * tc) =
+            make_float4((float)(ut & 0xffu), (float)((ut >> 8) & 0xffu), (float)((ut >> 16) & 0xffu), (float)(ut >> 24));
 }
 
 // u8 TMA stage -> fp16 work tile (rows of SW halves).  Integers 0..255 are exact in fp16: byte b becomes the half with
 // bits 0x6400 | b (= 1024 + b, ulp 1 there), then 1024 is subtracted — two full-rate instructions per pixel pair.
+__device__ __forceinline__ uint2 u8x4_to_h4(unsigned u)
+{
+    const __half2 k1024 = __floats2half2_rn(1024.0f, 1024.0f);
+    unsigned lo = __byte_perm(u, 0x64646464u, 0x4140);  // (0x64, b1, 0x64, b0)
+    unsigned hi = __byte_perm(u, 0x64646464u, 0x4342);  // (0x64, b3, 0x64, b2)
+    const __half2 h0 = __hsub2(*reinterpret_cast<__half2*>(&lo), k1024);
+    const __half2 h1 = __hsub2(*reinterpret_cast<__half2*>(&hi), k1024);
+    uint2 o;
+    o.x = *reinterpret_cast<const unsigned*>(&h0);
+    o.y = *reinterpret_cast<const unsigned*>(&h1);
+    return o;
+}
 template <int NROWS>
 __device__ __forceinline__ void convert_u8_tile_h(const unsigned char* __restrict__ src, __half* __restrict__ dst)
 {
-    constexpr int CH = SW / 4;
-    const __half2 k1024 = __floats2half2_rn(1024.0f, 1024.0f);
-    for (int idx = threadIdx.x; idx < NROWS * CH; idx += NT) {
-        const int r = idx / CH, c = idx - r * CH;
-        const unsigned u = *reinterpret_cast<const unsigned*>(src + r * U8_ROW + U8_OFF + 4 * c);
-        unsigned lo = __byte_perm(u, 0x64646464u, 0x4140);  // (0x64, b1, 0x64, b0)
-        unsigned hi = __byte_perm(u, 0x64646464u, 0x4342);  // (0x64, b3, 0x64, b2)
-        const __half2 h0 = __hsub2(*reinterpret_cast<__half2*>(&lo), k1024);
-        const __half2 h1 = __hsub2(*reinterpret_cast<__half2*>(&hi), k1024);
-        uint2 o;
-        o.x = *reinterpret_cast<const unsigned*>(&h0);
-        o.y = *reinterpret_cast<const unsigned*>(&h1);
-        *reinterpret_cast<uint2*>(dst + 4 * idx) = o;
-    }
+    constexpr int NIT = (NROWS + NT / 32 - 1) / (NT / 32);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned char* s0 = src + w * U8_ROW + U8_OFF + 4 * lane;
+    __half* d0 = dst + w * SW + 4 * lane;
+    unsigned u[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; i++)
+        if (w + i * (NT / 32) < NROWS) u[i] = *reinterpret_cast<const unsigned*>(s0 + i * (NT / 32) * U8_ROW);
+    const bool tail = threadIdx.x < 2 * NROWS;
+    const int tr = threadIdx.x >> 1, tc = 32 + (threadIdx.x & 1);
+    unsigned ut = 0;
+    if (tail) ut = *reinterpret_cast<const unsigned*>(src + tr * U8_ROW + U8_OFF + 4 * tc);
+#pragma unroll
+    for (int i = 0; i < NIT; i++)
+        if (w + i * (NT / 32) < NROWS) *reinterpret_cast<uint2*>(d0 + i * (NT / 32) * SW) = u8x4_to_h4(u[i]);
+    if (tail) *reinterpret_cast<uint2*>(dst + tr * SW + 4 * tc) = u8x4_to_h4(ut);
 }
 
 // TMA tiles arrive zero-filled outside the image: overwrite those cells with the replicated edge value.
@@ -1654,7 +1684,7 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
     if (sc->status != 0) return;  // singular: corr = 0 was written by the sweep
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     const int L = a.L, P = a.P;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, step = blocks_of_image(a.nblk_base, a.nblk_extra, b);
+    const int step = blocks_of_image(a.nblk_base, a.nblk_extra, b);
     if ((int)blockIdx.x >= step) return;
     float c[8];
 #pragma unroll
