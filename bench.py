@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--workload", default="image1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the video4k record a default (image1080p) run appends")
     ap.add_argument("--no-sync-proto", action="store_true", help="skip the single-image synchronous-call measurement (keeps ncu launch lists to the timed region)")
     ap.add_argument("--exact", action="store_true", help="f32 products in Rx/rx instead of the reference's fp16 rounding")
     ap.add_argument("--frames", type=int, default=0, help="frames per step (0 = the workload's own count)")
@@ -224,12 +225,29 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    line = run_workload(args, wl, torch, dist, dev, rank, local_rank, world, args.frames)
+    # the other headline of BASELINE.json's metric (configs[2]: 4K u8 video, ME embed + detect per frame) rides along on a default
+    # run as a compact secondary record; `value`, `roofline`, `e2e` above stay those of the primary workload
+    if args.workload == "image1080p" and not args.no_secondary:
+        sec = run_workload(args, "video4k", torch, dist, dev, rank, local_rank, world, 0, secondary=True)
+        if line is not None and sec is not None:
+            line["secondary"] = {"video4k": {k: sec[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "config", "step_frac_of_peak", "e2e", "gpu_launches")}}
+            line["secondary"]["video4k"]["kernels"] = [{"kernel": k["kernel"], "avg_ms": k["avg_ms"], "achieved_gbs": k["achieved_gbs"]} for k in sec["kernels"]]
+    if line is not None:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, frames_override, secondary=False):
+    """One workload through warm-up, the timed region, e2e and (primary only) the CPU baseline; returns the JSON record on rank 0."""
     pkg = importlib.import_module("watermarking-gpu_b200")
     C = pkg.C
 
     rows, cols, nfr, kind, dtype = WORKLOADS[wl]
-    if args.frames:
-        nfr = args.frames
+    if frames_override:
+        nfr = frames_override
     npx = rows * cols
     frames_np, W = make_inputs(rows, cols, nfr, dtype)
     stream = torch.cuda.Stream(device=dev)
@@ -387,7 +405,7 @@ def main():
 
     # the reference's literal protocol for this config (main.cpp:167-223): ONE image, synchronous calls, mean over loops
     sync_proto = None
-    if kind == "image" and rank == 0 and not args.no_sync_proto:
+    if kind == "image" and rank == 0 and not args.no_sync_proto and not secondary:
         one_in = pkg.image_desc(d_in.data_ptr(), rows, cols, layout, dt_code)
         one_out = pkg.image_desc(d_out[0].data_ptr(), rows, cols, layout, dt_code)
         av, cv = C.c_float(0), C.c_float(0)
@@ -416,9 +434,7 @@ def main():
         dist.all_gather(parts, mine)
         gathered = torch.stack(parts).cpu().numpy()  # [rank, (a, corr), frame]
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
+        return None
 
     # ---- roofline of the dominant kernel (largest share of device time in the timed region) ----
     peak, peak_src = peaks()
@@ -451,7 +467,7 @@ def main():
     pairs = 2 if kind == "image" else 1
     step_bytes = PAIR_BYTES[dtype] * npx * nfr * pairs
     cb = None
-    if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only
+    if not args.no_cpu_baseline and world == 1 and not secondary:  # rank 0 at N = 1 only
         use_all_host_threads()
         from oracle import oracle
         v, n = cpu_baseline(oracle, frames_np, W, kind)
@@ -480,10 +496,7 @@ def main():
                     {"ranks": int(gathered.shape[0]), "frames_per_rank": int(gathered.shape[2]),
                      "corr_me_mean": float(gathered[:, 1].mean()), "a_me_mean": float(gathered[:, 0].mean())}},
     }
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
-    return 0
+    return line
 
 
 if __name__ == "__main__":

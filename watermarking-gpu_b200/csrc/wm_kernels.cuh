@@ -57,7 +57,11 @@ constexpr int SZ_WT = TL * TP * 4;                   // W tile, no halo
 constexpr int U8_ROW = 160, U8_LEFT = 16, U8_OFF = U8_LEFT - HP;
 constexpr int U8_I34 = align128((TL + 2) * U8_ROW);
 constexpr int U8_I36 = align128((TL + 4) * U8_ROW);
-constexpr int SWEEP_NST = 2, SWEEP_NST_U8 = 4, EMBED_NST = 2, DETECT_NST = 2;
+constexpr int SWEEP_NST = 2, SWEEP_NST_U8 = 4, EMBED_NST = 2, EMBED_NST_U8 = 3, DETECT_NST = 2;
+// geometry of a tile in shared memory, in elements: f32 (and fp16) work tiles are rows of SW cells; a u8 TMA stage is read where
+// it landed (rows of U8_ROW bytes, the tile's column 0 at byte U8_OFF) — stats / apply / detect widen the bytes in registers
+template <typename T> struct TileGeo { static constexpr int STRIDE = SW, OFF = 0; };
+template <> struct TileGeo<unsigned char> { static constexpr int STRIDE = U8_ROW, OFF = U8_OFF; };
 constexpr int SWEEP_CTAS_PER_SM = 3;  // the f64 lag accumulators live in smem so that three CTAs (24 warps) fit per SM
 constexpr int SWEEP_ACC = NLAG * NT * 8;  // [NLAG][NT] doubles
 constexpr int EMBED_CTAS_PER_SM = 3;  // stats / apply: 2 stages of 35 KB -> three CTAs (24 warps) per SM
@@ -66,10 +70,10 @@ __host__ __device__ constexpr int sweep_stage(bool u8) { return u8 ? U8_I34 : SZ
 __host__ __device__ constexpr int embed_stage(bool u8) { return (u8 ? U8_I34 : SZ_I34) + SZ_WT; }
 __host__ __device__ constexpr int detect_stage(bool u8) { return (u8 ? U8_I36 : SZ_I36) + SZ_I34; }  // Z (halo 2) + W (halo 1)
 __host__ __device__ constexpr int sweep_smem(bool tma, bool u8) { return (tma ? (u8 ? SWEEP_NST_U8 * sweep_stage(true) + SZ_I34 : SWEEP_NST * sweep_stage(false)) : SZ_I34) + SWEEP_ACC; }
-constexpr int embed_smem(bool tma, bool u8) { return tma ? EMBED_NST * embed_stage(u8) + (u8 ? SZ_I34 : 0) : SZ_I34 + SZ_WT; }
+constexpr int embed_smem(bool tma, bool u8) { return tma ? (u8 ? EMBED_NST_U8 : EMBED_NST) * embed_stage(u8) : SZ_I34 + SZ_WT; }
 constexpr int detect_smem(bool tma, bool u8)  // + u tile
 {
-    return (tma ? DETECT_NST * detect_stage(u8) + (u8 ? SZ_I36 : 0) : SZ_I36 + SZ_I34) + SZ_I34;
+    return (tma ? DETECT_NST * detect_stage(u8) : SZ_I36 + SZ_I34) + SZ_I34;
 }
 
 // per-image scalars living in device memory (one per batch entry), mirrored to pinned host memory
@@ -360,6 +364,8 @@ __device__ __forceinline__ bool tile_on_frame(int l_org, int p_org, int L, int P
 template <int NROWS, typename T>
 __device__ __forceinline__ void fix_border(T* tile, int l_org, int p_org, int L, int P)
 {
+    constexpr int ST = TileGeo<T>::STRIDE;
+    T* const t0 = tile + TileGeo<T>::OFF;  // column 0 of the tile
     // Only cells within 2 of the image are ever read by a valid pixel's window, so at most 2 lines above, 2 below,
     // 2 columns left and 2 right are patched; every source is an in-image cell of this tile.
     const int r_lo = max(0, -l_org), r_hi = min(NROWS, L - l_org);  // in-image rows [r_lo, r_hi)
@@ -369,14 +375,14 @@ __device__ __forceinline__ void fix_border(T* tile, int l_org, int p_org, int L,
         const int j = idx / SW, c = idx - j * SW;
         const int r = j < 2 ? r_lo - 1 - j : r_hi + (j - 2);
         if (r >= ra && r < rb && (r < r_lo || r >= r_hi))
-            tile[r * SW + c] = tile[clampi(r, r_lo, r_hi - 1) * SW + clampi(c, c_lo, c_hi - 1)];
+            t0[r * ST + c] = t0[clampi(r, r_lo, r_hi - 1) * ST + clampi(c, c_lo, c_hi - 1)];
     }
     if (c_lo > 0 || c_hi < SW) {
         for (int idx = threadIdx.x; idx < 4 * NROWS; idx += NT) {   // in-image rows, out-of-image columns (up to 4)
             const int r = idx >> 2, j = idx & 3;
             const int c = j < 2 ? c_lo - 1 - j : c_hi + (j - 2);
             if (r >= r_lo && r < r_hi && c >= 0 && c < SW && (c < c_lo || c >= c_hi))
-                tile[r * SW + c] = tile[r * SW + clampi(c, c_lo, c_hi - 1)];
+                t0[r * ST + c] = t0[r * ST + clampi(c, c_lo, c_hi - 1)];
         }
     }
 }
@@ -634,6 +640,21 @@ __device__ __forceinline__ void load_win6(float (&w)[6], const float* line, int 
         if (lane == 0) l = h; else r = h;
     }
     w[0] = l; w[1] = v.x; w[2] = v.y; w[3] = v.z; w[4] = v.w; w[5] = r;
+}
+
+// the same window from a u8 TMA stage line (`line` = row start; the tile's column sc sits at byte U8_OFF + sc, 4-byte aligned)
+__device__ __forceinline__ void load_win6(float (&w)[6], const unsigned char* line, int sc)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned u = *reinterpret_cast<const unsigned*>(line + U8_OFF + sc);
+    const float x0 = (float)(u & 0xffu), x1 = (float)((u >> 8) & 0xffu), x2 = (float)((u >> 16) & 0xffu), x3 = (float)(u >> 24);
+    float l = __shfl_up_sync(0xffffffffu, x3, 1);
+    float r = __shfl_down_sync(0xffffffffu, x0, 1);
+    if (lane == 0 || lane == 31) {
+        const float h = (float)line[U8_OFF + sc + (lane == 0 ? -1 : 4)];
+        if (lane == 0) l = h; else r = h;
+    }
+    w[0] = l; w[1] = x0; w[2] = x1; w[3] = x2; w[4] = x3; w[5] = r;
 }
 
 // ================================================================================================
@@ -1283,14 +1304,14 @@ template <typename PixT, bool TMA, typename Body>
 __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CUtensorMap* tmW, const EmbedArgs& a,
                                                 unsigned char* dsm, uint64_t* bars, Body body)
 {
-    constexpr int NST = TMA ? EMBED_NST : 1;
     constexpr bool U8T = TMA && sizeof(PixT) == 1;
+    constexpr int NST = TMA ? (U8T ? EMBED_NST_U8 : EMBED_NST) : 1;
     constexpr int STG = embed_stage(U8T), IPART = U8T ? U8_I34 : SZ_I34;
+    using TileT = typename std::conditional<U8T, unsigned char, float>::type;  // u8 TMA stages are read where they landed
     const int b = blockIdx.y, step = blocks_of_image(a.nblk_base, a.nblk_extra, b);
     if ((int)blockIdx.x >= step) return;  // surplus CTA of this image (block-uniform, before any barrier)
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     auto stage = [&](int s) { return dsm + (size_t)s * STG; };
-    float* const work = reinterpret_cast<float*>(dsm + (size_t)NST * STG);  // u8 TMA only
     auto issue = [&](int tl, int tp, int s) {  // thread 0 only
         mbar_expect_tx(&bars[s], (U8T ? (TL + 2) * U8_ROW : (TL + 2) * SW * 4) + SZ_WT);
         tma_load_3d(stage(s), tmI, tp * TP - (U8T ? U8_LEFT : HP), tl * TL - 1, b, &bars[s]);
@@ -1318,7 +1339,8 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
     }
     for (; it.t < a.ntiles; it.next()) {
         const int l0 = it.tl * TL, p0 = it.tp * TP;
-        float *tile, *wtile;
+        TileT* tile;
+        float* wtile;
         if constexpr (TMA) {
             if (threadIdx.x == 0 && it.t + (NST - 1) * step < a.ntiles) {
                 int ptl, ptp;
@@ -1328,13 +1350,12 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
             }
             mbar_wait(&bars[pos.s], pos.ph);
             wtile = reinterpret_cast<float*>(stage(pos.s) + IPART);
-            if constexpr (U8T) { tile = work; convert_u8_tile<TL + 2>(stage(pos.s), tile); __syncthreads(); }
-            else tile = reinterpret_cast<float*>(stage(pos.s));
+            tile = reinterpret_cast<TileT*>(stage(pos.s));
             pos.next();
             if (tile_on_frame<TL + 2>(l0 - 1, p0 - HP, a.L, a.P)) { fix_border<TL + 2>(tile, l0 - 1, p0 - HP, a.L, a.P); __syncthreads(); }
         } else {
-            tile = reinterpret_cast<float*>(dsm);
-            wtile = tile + SZ_I34 / 4;
+            tile = reinterpret_cast<TileT*>(dsm);
+            wtile = reinterpret_cast<float*>(dsm) + SZ_I34 / 4;
             __syncthreads();
             pre.commit(tile, img, a.ld, a.L, a.P);
             wpre.commit(wtile);
@@ -1352,18 +1373,19 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
 }
 
 // mask.W for one thread's 4 px x 4 lines: calls f(r, m[4], w[4], centre-line window) per line
-template <int MASK, bool TR, typename F>
-__device__ __forceinline__ void mask_lines(const float* __restrict__ tile, const float* __restrict__ wt, const float (&c)[8], F f)
+template <int MASK, bool TR, typename T, typename F>
+__device__ __forceinline__ void mask_lines(const T* __restrict__ tile, const float* __restrict__ wt, const float (&c)[8], F f)
 {
+    constexpr int ST = TileGeo<T>::STRIDE;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const float* tb = tile + (4 * w) * SW;  // smem line of image line l-1 for r = 0
+    const T* tb = tile + (4 * w) * ST;  // smem line of image line l-1 for r = 0
     const int scol = 4 * lane + HP;
     float r0[6], r1[6], r2[6];
     load_win6(r0, tb, scol);
-    load_win6(r1, tb + SW, scol);
+    load_win6(r1, tb + ST, scol);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        load_win6(r2, tb + (r + 2) * SW, scol);
+        load_win6(r2, tb + (r + 2) * ST, scol);
         const float4 wv = *reinterpret_cast<const float4*>(wt + (4 * w + r) * TP + 4 * lane);
         const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
         float m[4];
@@ -1388,7 +1410,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
 {
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * 2];
-    __shared__ __align__(8) uint64_t bars[EMBED_NST];
+    __shared__ __align__(8) uint64_t bars[EMBED_NST_U8];
     const int b = blockIdx.y;
     Scal* sc = a.scal + b;
     if (MASK == 0 && sc->status != 0) return;  // singular: a untouched, apply copies base through
@@ -1401,7 +1423,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
     float emax = 0.0f;
     const int nblk = blocks_of_image(a.nblk_base, a.nblk_extra, b);
     if ((int)blockIdx.x >= nblk) return;
-    embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&](const float* tile, const float* wt, int l0, int p0) {
+    embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&](const auto* tile, const float* wt, int l0, int p0) {
         const int pb = p0 + 4 * lane;
         float fs = 0.0f;
         auto run = [&](auto tag) {
@@ -1491,7 +1513,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
                                                  const EmbedArgs a)
 {
     extern __shared__ __align__(128) unsigned char dsm[];
-    __shared__ __align__(8) uint64_t bars[EMBED_NST];
+    __shared__ __align__(8) uint64_t bars[EMBED_NST_U8];
     const int b = blockIdx.y;
     const Scal* sc = a.scal + b;
     if ((int)blockIdx.x >= blocks_of_image(a.nblk_base, a.nblk_extra, b)) return;
@@ -1507,7 +1529,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
     const float rmx = MASK == 0 ? __frcp_rn(mx) : 0.0f;
     const bool out_vec = a.out_vec_ok != 0, base_vec = a.base_vec_ok != 0;
     const int channels = SB ? 1 : a.channels;
-    embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&](const float* tile, const float* wt, int l0, int p0) {
+    embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&](const auto* tile, const float* wt, int l0, int p0) {
         const int pb = p0 + 4 * lane;
         auto run = [&](auto tag) {
             constexpr bool FULL = decltype(tag)::value;
@@ -1571,24 +1593,25 @@ struct DetectArgs {
 };
 
 // one tile of the detector; FULL = the tile lies completely inside the image (its 1-pixel ring may not)
-template <int MASK, bool TR, bool FULL>
-__device__ __forceinline__ void detect_tile(const float* __restrict__ zt, const float* __restrict__ wt, float* __restrict__ ut,
+template <int MASK, bool TR, bool FULL, typename ZT>
+__device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const float* __restrict__ wt, float* __restrict__ ut,
                                             const float (&c)[8], const int (&ring_l)[2], const int (&ring_p)[2], int l0, int p0,
                                             int L, int P, float& fd, float& fz, float& fu)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int pb = p0 + 4 * lane;
     const int scol = 4 * lane + HP;
+    constexpr int ZS = TileGeo<ZT>::STRIDE, ZO = TileGeo<ZT>::OFF;
     float ez[4][4];
     // ---- phase 1a: my 4 x 4 pixels ----
     {
-        const float* zb = zt + (4 * w + 1) * SW;  // smem line of image line l-1 for r = 0
+        const ZT* zb = zt + (4 * w + 1) * ZS;  // smem line of image line l-1 for r = 0
         float r0[6], r1[6], r2[6];
         load_win6(r0, zb, scol);
-        load_win6(r1, zb + SW, scol);
+        load_win6(r1, zb + ZS, scol);
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            load_win6(r2, zb + (r + 2) * SW, scol);
+            load_win6(r2, zb + (r + 2) * ZS, scol);
             const float4 wv = *reinterpret_cast<const float4*>(wt + (4 * w + r + 1) * SW + scol);
             const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
             float uu[4];
@@ -1611,10 +1634,10 @@ __device__ __forceinline__ void detect_tile(const float* __restrict__ zt, const 
         const int rl = ring_l[q], rp = ring_p[q];
         const int l = l0 + rl, p = p0 + rp;
         if (rl <= TL && l >= 0 && l < L && p >= 0 && p < P) {
-            const float* zc = zt + (rl + 2) * SW + (rp + HP);
-            float q0[3] = {zc[-SW - 1], zc[-SW], zc[-SW + 1]};
-            float q1[3] = {zc[-1], zc[0], zc[1]};
-            float q2[3] = {zc[SW - 1], zc[SW], zc[SW + 1]};
+            const ZT* zc = zt + (rl + 2) * ZS + ZO + (rp + HP);
+            float q0[3] = {(float)zc[-ZS - 1], (float)zc[-ZS], (float)zc[-ZS + 1]};
+            float q1[3] = {(float)zc[-1], (float)zc[0], (float)zc[1]};
+            float q2[3] = {(float)zc[ZS - 1], (float)zc[ZS], (float)zc[ZS + 1]};
             float m;
             if constexpr (MASK == 0) m = fabsf(__fsub_rn(q1[1], predict<TR>(c, q0, q1, q2, 0)));
             else m = nvf_mask<TR>(q0, q1, q2, 0);
@@ -1677,8 +1700,8 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
     constexpr int NST = TMA ? DETECT_NST : 1;
     constexpr bool U8T = TMA && sizeof(PixT) == 1;
     constexpr int STG = TMA ? detect_stage(U8T) : SZ_I36 + SZ_I34, ZPART = U8T ? U8_I36 : SZ_I36;
-    float* const zwork = reinterpret_cast<float*>(dsm + (size_t)NST * STG);                        // u8 TMA only
-    float* const ut = reinterpret_cast<float*>(dsm + (size_t)NST * STG + (U8T ? SZ_I36 : 0));      // (TL+2) x SW, lines l0-1 .. l0+TL
+    using ZT = typename std::conditional<U8T, unsigned char, float>::type;  // u8 TMA stages are read where they landed
+    float* const ut = reinterpret_cast<float*>(dsm + (size_t)NST * STG);      // (TL+2) x SW, lines l0-1 .. l0+TL
     const int b = blockIdx.y;
     Scal* sc = a.scal + b;
     if (sc->status != 0) return;  // singular: corr = 0 was written by the sweep
@@ -1730,7 +1753,8 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
     }
     for (; it.t < a.ntiles; it.next()) {
         const int l0 = it.tl * TL, p0 = it.tp * TP;
-        float *zt, *wt;  // zt: (TL+4) x SW lines l0-2 ..; wt: (TL+2) x SW lines l0-1 ..
+        ZT* zt;     // (TL+4) lines from l0-2
+        float* wt;  // (TL+2) x SW lines l0-1 ..
         if constexpr (TMA) {
             if (threadIdx.x == 0 && it.t + (NST - 1) * step < a.ntiles) {
                 int ptl, ptp;
@@ -1740,13 +1764,12 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
             }
             mbar_wait(&bars[pos.s], pos.ph);
             wt = reinterpret_cast<float*>(stage(pos.s) + ZPART);
-            if constexpr (U8T) { zt = zwork; convert_u8_tile<TL + 4>(stage(pos.s), zt); __syncthreads(); }
-            else zt = reinterpret_cast<float*>(stage(pos.s));
+            zt = reinterpret_cast<ZT*>(stage(pos.s));
             pos.next();
             if (tile_on_frame<TL + 4>(l0 - 2, p0 - HP, L, P)) { fix_border<TL + 4>(zt, l0 - 2, p0 - HP, L, P); __syncthreads(); }
         } else {
-            zt = reinterpret_cast<float*>(dsm);
-            wt = zt + SZ_I36 / 4;
+            zt = reinterpret_cast<ZT*>(dsm);
+            wt = reinterpret_cast<float*>(dsm) + SZ_I36 / 4;
             __syncthreads();
             zpre.commit(zt, img, a.ld, L, P);
             wpre.commit(wt, a.W, P, L, P);
