@@ -751,3 +751,35 @@ def test_tiny_and_degenerate_shapes(wmb, oracle, rows, cols):
                 assert abs(a - o["a"]) / o["a"] <= 1e-3
                 assert np.abs(out.numpy() - o["out"]).max() <= 1e-4 * 255
     wm.close()
+
+
+def test_sample_app_cli(wmb, oracle, tmp_path):
+    """tools/sample_app.py: the reference's settings.ini-driven image flow (main.cpp:62-252) over the library — same keys,
+    same printed results; correlations and strengths must match the oracle's run of the same flow."""
+    import re
+    import subprocess
+    import sys
+    ini = tmp_path / "settings.ini"
+    ini.write_text("[paths]\nimage = %s\nwatermark = %s\n\n[options]\nsave_watermarked_files_to_disk = false\n"
+                   "execution_time_in_fps = true\n\n[parameters]\np = 3\npsnr = 40.0\n; comment\nloops_for_test = 2\n"
+                   % (util.PNG512_PATH, util.W512_PATH))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sample_app.py"), str(ini)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = r.stdout
+    assert "Each test will be executed 2 times" in out and "Calculation of NVF mask with 512 rows and 512 columns" in out
+    a = [float(x) for x in re.findall(r"Watermark strength \(parameter a\): ([0-9.eE+-]+)", out)]
+    c_nvf = float(re.search(r"Correlation \[NVF\]: ([0-9.eE+-]+)", out).group(1))
+    c_me = float(re.search(r"Correlation \[ME\]: ([0-9.eE+-]+)", out).group(1))
+    rgb = util.load_512_rgb()
+    W = util.load_w512()
+    og = oracle.rgb2gray(rgb)
+    for k, (mask, corr) in enumerate(((wmb.NVF, c_nvf), (wmb.ME, c_me))):
+        o = oracle.embed(og, W, 40.0, mask, base=rgb)
+        od = oracle.detect(oracle.rgb2gray(o["out"]), W, mask)
+        report("sample_app mask=%d a=%.6f/%.6f corr=%.6f/%.6f" % (mask, a[k], o["a"], corr, od["corr"]))
+        assert abs(a[k] - o["a"]) / o["a"] <= 1e-3 and abs(corr - od["corr"]) / abs(od["corr"]) <= 1e-3
+    # the reference's argument checks (main.cpp:89-97)
+    ini.write_text("[paths]\nimage = x.png\nwatermark = y\n[parameters]\np = 5\npsnr = 40\n")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sample_app.py"), str(ini)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "only p=3 is allowed" in r.stdout
