@@ -401,6 +401,8 @@ def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, frames_ove
         e2e = {"value": world * reps * n_e2e / e2e_s, "unit": "frames/s",
                "h2d_bytes_per_step": int(fb * n_e2e), "d2h_bytes_per_step": int(nout * fb * n_e2e + 2 * nout * 4 * n_e2e),
                "frames_per_step": n_e2e, "frames_in_flight": NS, "matches_resident_path": e2e_ok,
+               "h2d_gbs": world * reps * n_e2e / e2e_s * fb / 1e9, "d2h_gbs": world * reps * n_e2e / e2e_s * nout * fb / 1e9,
+               "pcie_note": "tools/pcie_bw.py on this pool's boxes: pinned copies reach 55 GB/s one way, 46 GB/s each way when both directions run",
                "api": "wm_embed_batch / wm_detect_batch on wm_get_stream() slots; pinned host frames in, watermarked frames + scalars out"}
 
     # the reference's literal protocol for this config (main.cpp:167-223): ONE image, synchronous calls, mean over loops

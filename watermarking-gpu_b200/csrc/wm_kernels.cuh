@@ -1595,7 +1595,7 @@ struct DetectArgs {
 // one tile of the detector; FULL = the tile lies completely inside the image (its 1-pixel ring may not)
 template <int MASK, bool TR, bool FULL, typename ZT>
 __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const float* __restrict__ wt, float* __restrict__ ut,
-                                            const float (&c)[8], const int (&ring_l)[2], const int (&ring_p)[2], int l0, int p0,
+                                            const float (&c)[8], int l0, int p0,
                                             int L, int P, float& fd, float& fz, float& fu)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1628,12 +1628,36 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const flo
             for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
         }
     }
-    // ---- phase 1b: the 1-pixel ring around the tile (in-image cells only) ----
+    // ---- phase 1b: the 1-pixel ring around the tile (in-image cells only).  The line above and the line below the tile are
+    // done by warps 0 and 1 with the vector code of phase 1a (one pass = 128 cells); the two columns, corners included, by
+    // threads 64 .. 131 with one cell each.  Cells past the image's last pixel hold junk that no valid pixel's window reads. ----
+    if (w < 2) {
+        const int rl = w == 0 ? -1 : TL;
+        const int l = l0 + rl;
+        if (l >= 0 && l < L) {  // warp-uniform
+            const ZT* zb = zt + (rl + 1) * ZS;
+            float r0[6], r1[6], r2[6];
+            load_win6(r0, zb, scol);
+            load_win6(r1, zb + ZS, scol);
+            load_win6(r2, zb + 2 * ZS, scol);
+            const float4 wv = *reinterpret_cast<const float4*>(wt + (rl + 1) * SW + scol);
+            const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+            float uu[4];
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int rl = ring_l[q], rp = ring_p[q];
+            for (int j = 0; j < 4; j++) {
+                float m;
+                if constexpr (MASK == 0) m = fabsf(__fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j)));
+                else m = nvf_mask<TR>(r0, r1, r2, j);
+                uu[j] = __fmul_rn(m, wq[j]);
+            }
+            *reinterpret_cast<float4*>(ut + (rl + 1) * SW + scol) = make_float4(uu[0], uu[1], uu[2], uu[3]);
+        }
+    } else if ((int)threadIdx.x < 64 + 2 * (TL + 2)) {
+        const int idx = threadIdx.x - 64;
+        const int rp = idx < TL + 2 ? -1 : TP;
+        const int rl = (idx < TL + 2 ? idx : idx - (TL + 2)) - 1;  // -1 .. TL
         const int l = l0 + rl, p = p0 + rp;
-        if (rl <= TL && l >= 0 && l < L && p >= 0 && p < P) {
+        if (l >= 0 && l < L && p >= 0 && p < P) {
             const ZT* zc = zt + (rl + 2) * ZS + ZO + (rp + HP);
             float q0[3] = {(float)zc[-ZS - 1], (float)zc[-ZS], (float)zc[-ZS + 1]};
             float q1[3] = {(float)zc[-1], (float)zc[0], (float)zc[1]};
@@ -1729,18 +1753,6 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
             for (int s = 0; s < NST - 1; s++)
                 if ((int)blockIdx.x + s * step < a.ntiles) { int ptl, ptp; it.peek(s, ptl, ptp); issue(ptl, ptp, s); }
     }
-    // my cells of the 1-pixel ring around a tile (relative to the tile origin), fixed for the whole kernel
-    int ring_l[2], ring_p[2];
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int idx = threadIdx.x + q * NT;
-        int rl = TL + 8, rp = 0;  // sentinel: no cell
-        if (idx < TP + 2) { rl = -1; rp = idx - 1; }
-        else if (idx < 2 * (TP + 2)) { rl = TL; rp = idx - (TP + 2) - 1; }
-        else if (idx < 2 * (TP + 2) + TL) { rl = idx - 2 * (TP + 2); rp = -1; }
-        else if (idx < 2 * (TP + 2) + 2 * TL) { rl = idx - 2 * (TP + 2) - TL; rp = TP; }
-        ring_l[q] = rl; ring_p[q] = rp;
-    }
     double ddot = 0.0, dnz = 0.0, dnu = 0.0;
     StagePos<NST> pos;
     TilePrefetch<PixT, TL + 4> zpre;
@@ -1782,8 +1794,8 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
             }
         }
         float fd = 0.0f, fz = 0.0f, fu = 0.0f;
-        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true>(zt, wt, ut, c, ring_l, ring_p, l0, p0, L, P, fd, fz, fu);
-        else detect_tile<MASK, TR, false>(zt, wt, ut, c, ring_l, ring_p, l0, p0, L, P, fd, fz, fu);
+        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu);
+        else detect_tile<MASK, TR, false>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu);
         ddot += (double)fd; dnz += (double)fz; dnu += (double)fu;
         if constexpr (TMA) __syncthreads();  // ut and the stage are rewritten from the next iteration on
     }
