@@ -469,17 +469,31 @@ def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, frames_ove
     pairs = 2 if kind == "image" else 1
     step_bytes = PAIR_BYTES[dtype] * npx * nfr * pairs
     cb = None
+    parity = None
     if not args.no_cpu_baseline and world == 1 and not secondary:  # rank 0 at N = 1 only
         use_all_host_threads()
         from oracle import oracle
         v, n = cpu_baseline(oracle, frames_np, W, kind)
+        # parity gate in the same job: frame 0 through the oracle against the scalars the timed region produced
+        if kind == "image":
+            chk = {}
+            for k2, mask in enumerate((oracle.NVF, oracle.ME)):
+                o = oracle.embed(frames_np[0], W, 40.0, mask)
+                od = oracle.detect(o["out"], W, mask)
+                chk["a_%s_rel" % ("nvf", "me")[k2]] = abs(float(a_host[k2][0]) - o["a"]) / abs(o["a"])
+                chk["corr_%s_rel" % ("nvf", "me")[k2]] = abs(float(c_host[k2][0]) - od["corr"]) / abs(od["corr"])
+        else:
+            st_, out_, a_ = oracle.embed_frame_u8(frames_np[0], W, 40.0, oracle.ME)
+            corr_ = oracle.detect_frame_u8(out_, W, oracle.ME)[1]
+            chk = {"a_me_rel": abs(float(a_host[1][0]) - a_) / abs(a_), "corr_me_rel": abs(float(c_host[1][0]) - corr_) / abs(corr_)}
+        parity = dict(chk, tolerance=1e-3, ok=bool(all(v_ <= 1e-3 for v_ in chk.values())), what="frame 0: GPU scalars of the timed region vs the CPU oracle")
         cb = {"value": v, "unit": "frames/s", "cores": oracle.num_threads(), "kind": "port",
               "sample": "%d frames of %s, same ops per frame, OpenMP oracle (restates Watermark.cpp; the reference's "
                         "ArrayFire/OpenCL stack cannot be built offline)" % (n, wl)}
     line = {
         "metric": "embed+detect FPS (NVF & PE masks)" if kind == "image" else "embed+detect FPS (PE mask, u8 video frames)",
         "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "wall_ms_per_step": (t1 - t0) * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if dtype == "f32" else "u8->f32", "data": "synthetic",
         "config": {"workload": wl, "rows": rows, "cols": cols, "frames_per_step": nfr, "p": 3, "psnr": 40.0,
                    "layout": "col-major (ArrayFire)" if layout == pkg.COL_MAJOR else "row-major Y plane",
@@ -490,7 +504,7 @@ def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, frames_ove
         "step_effective_gbs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
         "step_frac_of_peak": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
         "roofline": roof, "kernels": kern, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
-        "sync_single_image": sync_proto,
+        "sync_single_image": sync_proto, "parity": parity,
         "clocks": clocks,
         "results": {"a_nvf": float(a_host[0][0]), "a_me": float(a_host[1][0]), "corr_nvf": float(c_host[0][0]),
                     "corr_me": float(c_host[1][0]),
