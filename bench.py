@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--exact", action="store_true", help="f32 products in Rx/rx instead of the reference's fp16 rounding")
     ap.add_argument("--frames", type=int, default=0, help="frames per step (0 = the workload's own count)")
     ap.add_argument("--no-tma", action="store_true", help="plain register-prefetched tile loaders instead of TMA (A/B)")
+    ap.add_argument("--two-streams", action="store_true", help="A/B: NVF ops and ME ops of a step on two slots (kernel tails overlap)")
     ap.add_argument("--fhadd", action="store_true", help="sum the rounded Rx/rx products with the FHADD chain instead of HMMA (A/B)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per API call (0 = the whole batch in one call)")
     ap.add_argument("--slots", type=int, default=2, help="pipeline slots (streams) used round-robin when --chunk is set")
@@ -280,9 +281,10 @@ def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, frames_ove
             return
         if not args.chunk:
             for k, mask in enumerate((pkg.NVF, pkg.ME)):
-                wm.embed_batch(0, di, di, do[k], npx, npx, npx, nfr, mask, a_host[k], st_host)
-                wm.detect_batch(0, do[k], npx, nfr, mask, c_host[k], st_host)
-            wm.sync(0)
+                sl = k if args.two_streams else 0  # A/B: the NVF chain and the ME chain are independent
+                wm.embed_batch(sl, di, di, do[k], npx, npx, npx, nfr, mask, a_host[k], st_host)
+                wm.detect_batch(sl, do[k], npx, nfr, mask, c_host[k], st_host)
+            wm.sync(-1 if args.two_streams else 0)
             return
         # chunked: each call covers `chunk` frames so that one op's passes (sweep -> stats -> apply) find the frames
         # in L2; calls go round-robin over `slots` streams so launch gaps and per-image solves overlap
