@@ -24,9 +24,11 @@
 // with cp.async.bulk.tensor (3-D tensor maps: pixel, line, image) signalled through mbarriers, so the loads of the
 // next tile(s) are in flight while a tile is computed; out-of-image halo cells arrive zero-filled and are overwritten
 // with the replicated edge value (clamp-to-edge) by the few CTAs on the image frame.  f32 tiles are used where they
-// land; u8 frames land as bytes (boxes that start 16-byte aligned in global memory) and are widened to f32 — or, for
-// the sweep, to fp16 — by a conversion pass.  With TMA = false (odd strides / sizes) a register-prefetched
-// cooperative clamped loader fills a single stage.
+// land; u8 frames land as bytes (boxes that start 16-byte aligned in global memory): stats / apply / detect read the
+// byte stage directly and widen in registers (load_win6 on bytes), the sweep widens a tile once to fp16 so that its
+// products are packed-half multiplies.  With TMA = false (odd strides / sizes) a register-prefetched cooperative
+// clamped loader fills a single stage.  Every reduction ends in a last-block second stage run by the whole CTA
+// (block_column_reduce), so results are bit-reproducible for a given grid.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
