@@ -205,6 +205,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames per step (0 = the workload's own count)")
     ap.add_argument("--no-tma", action="store_true", help="plain register-prefetched tile loaders instead of TMA (A/B)")
     ap.add_argument("--two-streams", action="store_true", help="A/B: NVF ops and ME ops of a step on two slots (kernel tails overlap)")
+    ap.add_argument("--split-cost", type=int, default=None, help="WM_OPT_SPLIT_COST (A/B: -1 = never partition an unbalanced batch)")
     ap.add_argument("--fhadd", action="store_true", help="sum the rounded Rx/rx products with the FHADD chain instead of HMMA (A/B)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per API call (0 = the whole batch in one call)")
     ap.add_argument("--slots", type=int, default=2, help="pipeline slots (streams) used round-robin when --chunk is set")
@@ -259,6 +260,8 @@ def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, frames_ove
         wm.set_option(pkg.OPT_MMA_ACCUM, 0)
     if args.no_tma:
         wm.set_option(pkg.OPT_USE_TMA, 0)
+    if args.split_cost is not None:
+        wm.set_option(pkg.OPT_SPLIT_COST, args.split_cost)
     tdt = torch.uint8 if dtype == "u8" else torch.float32
     dt_code = pkg.U8 if dtype == "u8" else pkg.F32
     # image workloads: ArrayFire layout (column-major); video: row-major Y planes

@@ -64,6 +64,8 @@ enum {
     WM_OPT_USE_TMA = 3,       /* 1 (default): TMA tile loads when the shape allows; 0: always the plain loader */
     WM_OPT_SERIAL_SLOTS = 4,  /* 1: the video driver uses one slot (kernels do not overlap: per-kernel timing) */
     WM_OPT_CUDA_GRAPHS = 5,   /* 1 (default): wm_embed / wm_detect replay a captured CUDA graph when called again with the same arguments */
+    WM_OPT_SPLIT_COST = 7,    /* tile-times one more launch is assumed to cost (default 8: launch gap, pipeline ramp, second stage + solve tail) when a batch whose size does not divide
+                                 the resident CTA count is launched as better-balanced sub-batches; < 0: never split */
     WM_OPT_MMA_ACCUM = 6      /* 1 (default): the fp16-rounded Rx/rx products are summed on the tensor pipe (HMMA with a 0/1 selector
                                  matrix = four mixed-precision adds per lane); 0: FHADD chain.  Same bits for integer-valued pixels */
 };

@@ -783,3 +783,59 @@ def test_sample_app_cli(wmb, oracle, tmp_path):
     ini.write_text("[paths]\nimage = x.png\nwatermark = y\n[parameters]\np = 5\npsnr = 40\n")
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "sample_app.py"), str(ini)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "only p=3 is allowed" in r.stdout
+
+
+@pytest.mark.parametrize("B,rows,cols", [(64, 512, 512), (150, 256, 384), (500, 64, 64)])
+def test_unbalanced_batches_are_partitioned(wmb, oracle, B, rows, cols):
+    """A batch whose size does not divide the resident CTA count is launched as sub-batches (wm_api.cu: partition).  With the
+    split cost forced to 0 the partition is taken even for these small images; every image must come out as with a single
+    launch (same scalars to f32 rounding of a different f64 summation grouping, same pixels) and match the oracle."""
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    base_imgs = [util.natural_image(rows, cols, seed=900 + b) for b in range(8)]
+    imgs = np.stack([np.roll(base_imgs[b % 8], (b // 8, 2 * (b // 8)), (0, 1)) for b in range(B)])
+    if B > 70:
+        imgs[69] = 23.0  # singular system in the second sub-batch
+    L = wmb.lib()
+    din = L.wm_dev_alloc(wm._h, imgs.nbytes)
+    dout = L.wm_dev_alloc(wm._h, imgs.nbytes)
+    L.wm_dev_upload(wm._h, din, imgs.ctypes.data, imgs.nbytes)
+    npx = rows * cols
+    di = wmb.image_desc(din, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+    do = wmb.image_desc(dout, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+    res = {}
+    for cost in (-1, 0):
+        wm.set_option(wmb.OPT_SPLIT_COST, cost)
+        l0 = wm.launch_count
+        for mask in (wmb.ME, wmb.NVF):
+            a = np.full(B, np.nan, np.float32)
+            st = np.zeros(B, np.int32)
+            wm.embed_batch(0, di, di, do, npx, npx, npx, B, mask, a, st)
+            wm.sync(0)
+            outs = np.zeros_like(imgs)
+            L.wm_dev_download(wm._h, outs.ctypes.data, dout, outs.nbytes)
+            corr = np.zeros(B, np.float32)
+            st2 = np.zeros(B, np.int32)
+            wm.detect_batch(0, do, npx, B, mask, corr, st2)
+            wm.sync(0)
+            res[(cost, mask)] = (a, st.copy(), outs, corr, st2.copy())
+        res[(cost, "launches")] = wm.launch_count - l0
+    for mask in (wmb.ME, wmb.NVF):
+        a0, s0, o0, c0, t0 = res[(-1, mask)]
+        a1, s1, o1, c1, t1 = res[(0, mask)]
+        assert np.array_equal(s0, s1) and np.array_equal(t0, t1)
+        ok = s0 == 0
+        if B > 70 and mask == wmb.ME:
+            assert s0[69] != 0 and np.array_equal(o1[69], imgs[69])
+        ra = np.abs(a1[ok] - a0[ok]) / np.abs(a0[ok])
+        rc = np.abs(c1[ok] - c0[ok]) / np.abs(c0[ok])
+        report("partition B=%d %dx%d mask=%d max rel a=%.3g corr=%.3g dpix=%.3g" % (B, rows, cols, mask, ra.max(), rc.max(), np.abs(o1 - o0).max()))
+        assert ra.max() <= 1e-6 and rc.max() <= 1e-5 and np.abs(o1 - o0).max() <= 1e-4 * 255
+        for b in (0, B // 2, B - 1):
+            o = oracle.embed(imgs[b], W, 40.0, mask)
+            od = oracle.detect(o["out"], W, mask)
+            assert abs(a1[b] - o["a"]) / o["a"] <= 1e-3 and np.abs(o1[b] - o["out"]).max() <= 1e-4 * 255
+            assert abs(c1[b] - od["corr"]) / abs(od["corr"]) <= 1e-3
+    L.wm_dev_free(wm._h, din)
+    L.wm_dev_free(wm._h, dout)
+    wm.close()

@@ -21,7 +21,7 @@ ME, NVF = 0, 1                      # Watermark.hpp:10-14
 COL_MAJOR, ROW_MAJOR = 0, 1
 F32, U8 = 0, 1
 OK, SINGULAR, ZERO_MASK = 0, 1, 2
-OPT_FP16_PRODUCTS, OPT_KERNEL_TIMING, OPT_USE_TMA, OPT_SERIAL_SLOTS, OPT_CUDA_GRAPHS, OPT_MMA_ACCUM = 1, 2, 3, 4, 5, 6
+OPT_FP16_PRODUCTS, OPT_KERNEL_TIMING, OPT_USE_TMA, OPT_SERIAL_SLOTS, OPT_CUDA_GRAPHS, OPT_MMA_ACCUM, OPT_SPLIT_COST = 1, 2, 3, 4, 5, 6, 7
 DBG_RX, DBG_RXVEC, DBG_COEFFS, DBG_SCALARS, DBG_ERRSEQ, DBG_MASK_NVF, DBG_PHASES = range(7)
 KERNEL_NAMES = ["rx_sweep", "me_stats", "nvf_stats", "embed_apply", "detect_apply"]
 VIDEO_EMBED, VIDEO_DETECT = 0, 1

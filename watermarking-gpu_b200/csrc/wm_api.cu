@@ -70,6 +70,7 @@ struct wm_ctx {
     std::shared_ptr<WShared> w;
     Slot slots[NSLOTS];
     int opt_fp16 = 1, opt_timing = 0, opt_tma = 1, opt_serial = 0, opt_mma = 1;
+    int opt_split_cost = 8;  // tile-times one more launch is assumed to cost when a batch is partitioned (WM_OPT_SPLIT_COST)
     bool inject_coef = false;
     float injected[8];
     std::string err;
@@ -212,27 +213,75 @@ Geo geo(int L, int P)
     return g;
 }
 
-struct Plan { int nsweep, nframe, gx_stats, gx_detect, nblk_base, nblk_extra, eblk_base, eblk_extra, sblk_base, sblk_extra; };
-// Every launch is at most ONE wave of resident CTAs (persistent tile loops; a partial second wave would leave most SMs
-// idle for a whole tile loop): 2 per SM for the detector, SWEEP_CTAS_PER_SM / EMBED_CTAS_PER_SM for the sweep and stats / apply.  The wave
-// is split over the images of a batch as evenly as possible: image b gets base + (b < extra) CTAs, gridDim.x is the
-// larger of the two and the surplus CTAs exit at once.
+// One launch = at most ONE wave of resident CTAs (persistent tile loops; a partial second wave would leave most SMs idle for
+// a whole tile loop): 2 per SM for the detector, SWEEP_CTAS_PER_SM / EMBED_CTAS_PER_SM for the sweep and stats / apply.  The
+// wave is split over the images of the launch as evenly as possible: image b gets base + (b < extra) CTAs, gridDim.x is the
+// larger of the two and the surplus CTAs exit at once.  When that split is uneven (64 images on 444 CTAs: 60 get 7, 4 get 6
+// and set the pace), the batch is launched as sub-batches whose own splits are even enough to pay for the extra launch —
+// images are independent and every per-image buffer is indexed by the global image number (kernel argument b0).
+struct SubBatch { int b0, nb, base, extra; };
+struct Plan {
+    std::vector<SubBatch> sweep, embed, detect;
+    int nsweep, nframe, gx_stats, gx_detect;  // partial rows per image (strides) of the three families
+};
 void split_wave(int cap, int batch, int ntiles, int* base, int* extra)
 {
     *base = cap / batch; *extra = cap % batch;
     if (*base < 1) { *base = 1; *extra = 0; }
     if (*base >= ntiles) { *base = ntiles; *extra = 0; }
 }
+// duration of one wave of `cap` CTAs over m images, in tile-times of the slowest CTA
+int wave_cost(int cap, int m, int ntiles)
+{
+    if (m >= cap) return ((m + cap - 1) / cap) * ntiles;
+    const int base = cap / m;
+    return base >= ntiles ? 1 : (ntiles + base - 1) / base;
+}
+// a split must promise at least 8 % (the model ignores second-order effects; measured: a 4 % promise lost 10 %)
+static bool worth(long long split, long long single) { return split * 100 < single * 92; }
+// split_cost: what one more launch costs (launch gap + ramp / tail of one more wave), in tile-times
+std::vector<SubBatch> partition(int cap, int batch, int ntiles, int split_cost)
+{
+    std::vector<SubBatch> out;
+    int b0 = 0, rest = batch;
+    while (rest > 0) {
+        int take = rest;
+        if (rest > cap && rest % cap != 0) {
+            // more images than CTAs: whole waves of one CTA per image first, the remainder shares a wave of its own
+            const int full = (rest / cap) * cap;
+            if (worth(wave_cost(cap, full, ntiles) + split_cost + wave_cost(cap, rest - full, ntiles), wave_cost(cap, rest, ntiles))) take = full;
+        } else if (rest > 1 && rest < cap && cap % rest != 0) {
+            const int single = wave_cost(cap, rest, ntiles);
+            int best = single;
+            for (int na = 1; na < rest; na++) {
+                const int c = wave_cost(cap, na, ntiles) + split_cost + wave_cost(cap, rest - na, ntiles);
+                if (c < best && worth(c, single)) { best = c; take = na; }
+            }
+        }
+        SubBatch sb;
+        sb.b0 = b0; sb.nb = take;
+        split_wave(cap, take, ntiles, &sb.base, &sb.extra);
+        out.push_back(sb);
+        b0 += take; rest -= take;
+    }
+    return out;
+}
+int max_rows(const std::vector<SubBatch>& v)
+{
+    int m = 1;
+    for (const SubBatch& sb : v) m = std::max(m, sb.base + (sb.extra > 0 ? 1 : 0));
+    return m;
+}
 Plan plan(const wm_ctx* ctx, const Geo& g, int batch)
 {
     Plan p;
-    split_wave(2 * ctx->sms, batch, g.ntiles, &p.nblk_base, &p.nblk_extra);
-    split_wave(EMBED_CTAS_PER_SM * ctx->sms, batch, g.ntiles, &p.eblk_base, &p.eblk_extra);
-    split_wave(SWEEP_CTAS_PER_SM * ctx->sms, batch, g.ntiles, &p.sblk_base, &p.sblk_extra);
+    p.detect = partition(2 * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
+    p.embed = partition(EMBED_CTAS_PER_SM * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
+    p.sweep = partition(SWEEP_CTAS_PER_SM * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
     p.nframe = 0;  // the frame ring is shared by the sweep blocks
-    p.nsweep = p.sblk_base + (p.sblk_extra > 0 ? 1 : 0);
-    p.gx_detect = p.nblk_base + (p.nblk_extra > 0 ? 1 : 0);
-    p.gx_stats = p.eblk_base + (p.eblk_extra > 0 ? 1 : 0);
+    p.nsweep = max_rows(p.sweep);
+    p.gx_detect = max_rows(p.detect);
+    p.gx_stats = max_rows(p.embed);
     return p;
 }
 
@@ -339,7 +388,6 @@ int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int ba
     a.img = v.ptr; a.ld = v.ld; a.bstride = bstride;
     a.L = g.L; a.P = g.P; a.tiles_p = g.tiles_p; a.ntiles = g.ntiles;
     a.nsweep = pl.nsweep; a.nframe = pl.nframe;
-    a.nblk_base = pl.sblk_base; a.nblk_extra = pl.sblk_extra;
     a.vec_ok = vec_ok(v.ptr, v.ld, bstride, 0, v.dtype);
     a.transposed = v.transposed;
     a.part = s.part;
@@ -351,7 +399,10 @@ int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int ba
     if (tma) tma = make_tmap(&tmI, v.dtype, v.ptr, g.P, g.L, batch, v.ld, bstride, SW, TL + 2);
     {
         KTimer t(ctx, s, WM_K_SWEEP);
-        launch_sweep(v.dtype, ctx->opt_fp16 ? (ctx->opt_mma ? 2 : 1) : 0, tma, dim3(pl.nsweep + pl.nframe, batch), s.stream, tmI, a);
+        for (const SubBatch& sb : pl.sweep) {
+            a.b0 = sb.b0; a.nblk_base = sb.base; a.nblk_extra = sb.extra;
+            launch_sweep(v.dtype, ctx->opt_fp16 ? (ctx->opt_mma ? 2 : 1) : 0, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmI, a);
+        }
     }
     CU(cudaGetLastError());
     return WM_OK;
@@ -393,7 +444,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     ea.vec_ok = vec_ok(vi.ptr, vi.ld, in_stride, 0, vi.dtype);
     ea.w_vec_ok = (g.P % 4 == 0);
     ea.strength = ctx->strength;
-    ea.nblk_base = pl.eblk_base; ea.nblk_extra = pl.eblk_extra;
+    ea.pstride = pl.gx_stats;
     ea.part = s.part + stats_part_offset(pl, batch);
     ea.counter = s.counters + s.batch_cap;
     ea.scal = s.scal; ea.dbg = s.dbg;
@@ -411,12 +462,18 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
                    make_tmap(&tmW, WM_F32, W, g.P, g.L, 1, g.P, 0, TP, TL);
     {
         KTimer t(ctx, s, mask == WM_MASK_ME ? WM_K_ME_STATS : WM_K_NVF_STATS);
-        launch_stats(vi.dtype, mask, vi.transposed, tma, dim3(pl.gx_stats, batch), s.stream, tmI, tmW, ea);
+        for (const SubBatch& sb : pl.embed) {
+            ea.b0 = sb.b0; ea.nblk_base = sb.base; ea.nblk_extra = sb.extra;
+            launch_stats(vi.dtype, mask, vi.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmI, tmW, ea);
+        }
     }
     CU(cudaGetLastError());
     {
         KTimer t(ctx, s, WM_K_APPLY);
-        launch_apply(vi.dtype, vo.dtype, mask, vi.transposed, tma, dim3(pl.gx_stats, batch), s.stream, tmI, tmW, ea);
+        for (const SubBatch& sb : pl.embed) {
+            ea.b0 = sb.b0; ea.nblk_base = sb.base; ea.nblk_extra = sb.extra;
+            launch_apply(vi.dtype, vo.dtype, mask, vi.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmI, tmW, ea);
+        }
     }
     CU(cudaGetLastError());
     return push_result(ctx, s, 1, batch);
@@ -445,7 +502,7 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     da.L = g.L; da.P = g.P; da.tiles_p = g.tiles_p; da.ntiles = g.ntiles;
     da.vec_ok = vec_ok(v.ptr, v.ld, img_stride, 0, v.dtype);
     da.w_vec_ok = (g.P % 4 == 0);
-    da.nblk_base = pl.nblk_base; da.nblk_extra = pl.nblk_extra;
+    da.pstride = pl.gx_detect;
     da.part = s.part + stats_part_offset(pl, batch);
     da.counter = s.counters + 2 * s.batch_cap;
     da.scal = s.scal; da.dbg = s.dbg;
@@ -457,7 +514,10 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
                    make_tmap(&tmW, WM_F32, W, g.P, g.L, 1, g.P, 0, SW, TL + 2);
     {
         KTimer t(ctx, s, WM_K_DETECT);
-        launch_detect(v.dtype, mask, v.transposed, tma, dim3(pl.gx_detect, batch), s.stream, tmZ, tmW, da);
+        for (const SubBatch& sb : pl.detect) {
+            da.b0 = sb.b0; da.nblk_base = sb.base; da.nblk_extra = sb.extra;
+            launch_detect(v.dtype, mask, v.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmZ, tmW, da);
+        }
     }
     CU(cudaGetLastError());
     return push_result(ctx, s, 2, batch);
@@ -692,7 +752,7 @@ int wm_clone(const wm_ctx* src, wm_ctx** out)
     ctx->rows = src->rows; ctx->cols = src->cols;
     ctx->p = src->p; ctx->psnr = src->psnr; ctx->strength = src->strength;
     ctx->w = src->w;
-    ctx->opt_fp16 = src->opt_fp16; ctx->opt_mma = src->opt_mma; ctx->opt_timing = src->opt_timing; ctx->opt_tma = src->opt_tma;
+    ctx->opt_fp16 = src->opt_fp16; ctx->opt_mma = src->opt_mma; ctx->opt_split_cost = src->opt_split_cost; ctx->opt_timing = src->opt_timing; ctx->opt_tma = src->opt_tma;
     const int rc = init_slots(ctx, nullptr);
     if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
     *out = ctx;
@@ -740,6 +800,7 @@ int wm_set_option(wm_ctx* ctx, int option, int value)
     case WM_OPT_SERIAL_SLOTS: ctx->opt_serial = value != 0; return WM_OK;
     case WM_OPT_CUDA_GRAPHS: ctx->opt_graphs = value != 0; return WM_OK;
     case WM_OPT_MMA_ACCUM: ctx->opt_mma = value != 0; return WM_OK;
+    case WM_OPT_SPLIT_COST: ctx->opt_split_cost = value < 0 ? 1 << 28 : value; return WM_OK;
     default: return fail(ctx, WM_ERR_ARG, "unknown option");
     }
 }

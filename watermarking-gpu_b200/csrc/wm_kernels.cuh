@@ -673,7 +673,8 @@ struct SweepArgs {
     const void* img;
     long long ld, bstride;  // elements
     int L, P, tiles_p, ntiles;
-    int nsweep, nframe;  // nsweep = gridDim.x (partial stride); nframe unused (kept 0): the ring is shared by the sweep blocks
+    int nsweep, nframe;  // nsweep = partial rows per image (stride); nframe unused (kept 0): the ring is shared by the sweep blocks
+    int b0;              // first image of this launch (a batch may be launched as sub-batches, see wm_api.cu: partition)
     int nblk_base, nblk_extra;  // CTAs per image = nblk_base + (image < nblk_extra)
     int vec_ok, transposed;
     double* part;        // [batch][nsweep][NTOT]
@@ -969,12 +970,12 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
     __shared__ double red[8 * NFRM];
     __shared__ __align__(8) uint64_t bars[SWEEP_NST_U8];
     constexpr bool U8T = TMA && sizeof(PixT) == 1;
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + a.b0;
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     const int L = a.L, P = a.P;
     double* part = a.part + (size_t)b * (size_t)a.nsweep * NTOT;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int nblk = blocks_of_image(a.nblk_base, a.nblk_extra, b);
+    const int nblk = blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y);
     if ((int)blockIdx.x >= nblk) return;
     unsigned long long ts0 = 0, ts1 = 0, ts2 = 0;
     if (threadIdx.x == 0) ts0 = gtime();
@@ -1289,7 +1290,8 @@ struct EmbedArgs {
     int vec_ok, w_vec_ok;
     int nblk_base, nblk_extra;  // CTAs per image = nblk_base + (image < nblk_extra)
     float strength;
-    double* part;       // [batch][gridDim.x][2]       (stats)
+    int b0, pstride;    // first image of this launch; partial rows per image
+    double* part;       // [batch][pstride][2]         (stats)
     unsigned* counter;  // [batch]                     (stats)
     Scal* scal;
     ScalDbg* dbg;
@@ -1310,7 +1312,7 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
     constexpr int NST = TMA ? (U8T ? EMBED_NST_U8 : EMBED_NST) : 1;
     constexpr int STG = embed_stage(U8T), IPART = U8T ? U8_I34 : SZ_I34;
     using TileT = typename std::conditional<U8T, unsigned char, float>::type;  // u8 TMA stages are read where they landed
-    const int b = blockIdx.y, step = blocks_of_image(a.nblk_base, a.nblk_extra, b);
+    const int b = blockIdx.y + a.b0, step = blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y);
     if ((int)blockIdx.x >= step) return;  // surplus CTA of this image (block-uniform, before any barrier)
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     auto stage = [&](int s) { return dsm + (size_t)s * STG; };
@@ -1413,7 +1415,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * 2];
     __shared__ __align__(8) uint64_t bars[EMBED_NST_U8];
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + a.b0;
     Scal* sc = a.scal + b;
     if (MASK == 0 && sc->status != 0) return;  // singular: a untouched, apply copies base through
     const int L = a.L, P = a.P;
@@ -1423,7 +1425,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
     for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
     double dsum = 0.0;
     float emax = 0.0f;
-    const int nblk = blocks_of_image(a.nblk_base, a.nblk_extra, b);
+    const int nblk = blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y);
     if ((int)blockIdx.x >= nblk) return;
     embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&](const auto* tile, const float* wt, int l0, int p0) {
         const int pb = p0 + 4 * lane;
@@ -1453,13 +1455,13 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
         if (threadIdx.x == 0) {
             double ss = 0.0, mm = 0.0;
             for (int k = 0; k < NT / 32; k++) { ss += red[k * 2]; mm = fmax(mm, red[k * 2 + 1]); }
-            double* part = a.part + ((size_t)b * gridDim.x + blockIdx.x) * 2;
+            double* part = a.part + ((size_t)b * a.pstride + blockIdx.x) * 2;
             part[0] = ss; part[1] = mm;
         }
     }
     if (!last_block(a.counter + b, nblk)) return;
     __shared__ double tot2[2];
-    block_column_reduce<2, 2, 1>(a.part + (size_t)b * gridDim.x * 2, nblk, tot2, reinterpret_cast<double*>(dsm));
+    block_column_reduce<2, 2, 1>(a.part + (size_t)b * a.pstride * 2, nblk, tot2, reinterpret_cast<double*>(dsm));
     if (w == 0) {
         const double S2 = tot2[0];
         const float mx = (float)tot2[1];
@@ -1486,12 +1488,12 @@ template <> __device__ __forceinline__ uint8_t to_out<uint8_t>(float v) { return
 template <typename PixT, typename OutT>
 __device__ __forceinline__ void copy_base_through(const EmbedArgs& a)
 {
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + a.b0;
     const PixT* bas = reinterpret_cast<const PixT*>(a.base) + (long long)b * a.base_bstride;
     OutT* out = reinterpret_cast<OutT*>(a.out) + (long long)b * a.out_bstride;
     const long long n = (long long)a.L * a.P;
     for (int ch = 0; ch < a.channels; ch++)
-        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)blocks_of_image(a.nblk_base, a.nblk_extra, b) * NT) {
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y) * NT) {
             const int l = (int)(i / a.P), p = (int)(i - (long long)l * a.P);
             out[(long long)ch * a.out_pstride + (long long)l * a.out_ld + p] =
                 to_out<OutT>((float)bas[(long long)ch * a.base_pstride + (long long)l * a.base_ld + p]);
@@ -1516,9 +1518,9 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
 {
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ __align__(8) uint64_t bars[EMBED_NST_U8];
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + a.b0;
     const Scal* sc = a.scal + b;
-    if ((int)blockIdx.x >= blocks_of_image(a.nblk_base, a.nblk_extra, b)) return;
+    if ((int)blockIdx.x >= blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y)) return;
     if (sc->status != 0) { copy_base_through<PixT, OutT>(a); return; }
     const PixT* bas = reinterpret_cast<const PixT*>(a.base) + (long long)b * a.base_bstride;
     OutT* out = reinterpret_cast<OutT*>(a.out) + (long long)b * a.out_bstride;
@@ -1588,7 +1590,8 @@ struct DetectArgs {
     int L, P, tiles_p, ntiles;
     int vec_ok, w_vec_ok;
     int nblk_base, nblk_extra;  // CTAs per image = nblk_base + (image < nblk_extra)
-    double* part;       // [batch][gridDim.x][3]
+    int b0, pstride;    // first image of this launch; partial rows per image
+    double* part;       // [batch][pstride][3]
     unsigned* counter;
     Scal* scal;
     ScalDbg* dbg;
@@ -1728,12 +1731,12 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
     constexpr int STG = TMA ? detect_stage(U8T) : SZ_I36 + SZ_I34, ZPART = U8T ? U8_I36 : SZ_I36;
     using ZT = typename std::conditional<U8T, unsigned char, float>::type;  // u8 TMA stages are read where they landed
     float* const ut = reinterpret_cast<float*>(dsm + (size_t)NST * STG);      // (TL+2) x SW, lines l0-1 .. l0+TL
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + a.b0;
     Scal* sc = a.scal + b;
     if (sc->status != 0) return;  // singular: corr = 0 was written by the sweep
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     const int L = a.L, P = a.P;
-    const int step = blocks_of_image(a.nblk_base, a.nblk_extra, b);
+    const int step = blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y);
     if ((int)blockIdx.x >= step) return;
     float c[8];
 #pragma unroll
@@ -1804,9 +1807,9 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
     __syncthreads();
     const double v3[3] = {ddot, dnz, dnu};
     block_sum<3>(v3, red);
-    if (threadIdx.x < 3) a.part[((size_t)b * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = red[threadIdx.x];
+    if (threadIdx.x < 3) a.part[((size_t)b * a.pstride + blockIdx.x) * 3 + threadIdx.x] = red[threadIdx.x];
     if (!last_block(a.counter + b, step)) return;
-    block_column_reduce<3, 4, 3>(a.part + (size_t)b * gridDim.x * 3, step, red, reinterpret_cast<double*>(dsm));
+    block_column_reduce<3, 4, 3>(a.part + (size_t)b * a.pstride * 3, step, red, reinterpret_cast<double*>(dsm));
     if (threadIdx.x == 0) {
         a.dbg[b].dot = red[0]; a.dbg[b].nz = red[1]; a.dbg[b].nu = red[2];
         const float dotf = (float)red[0];
