@@ -147,6 +147,10 @@ def cpu_baseline(oracle, frames, W, kind, budget_s=12.0):
 def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (libgomp reads this at load)."""
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    try:  # undo bind_to_gpu_numa_node: the CPU arm uses every core of the box
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except OSError:
+        pass
 
 
 def run_reference(args, wl):
@@ -227,6 +231,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bind_to_gpu_numa_node(torch, local_rank)
     line = run_workload(args, wl, torch, dist, dev, rank, local_rank, world, args.frames)
     # the other headline of BASELINE.json's metric (configs[2]: 4K u8 video, ME embed + detect per frame) rides along on a default
     # run as a compact secondary record; `value`, `roofline`, `e2e` above stay those of the primary workload
@@ -240,6 +245,30 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+NUMA_NOTE = None
+
+
+def bind_to_gpu_numa_node(torch, index):
+    """Pin this rank's host threads to the CPUs next to its GPU BEFORE any pinned buffer is allocated (first touch puts the pages
+    on that NUMA node), so the e2e copies of several ranks do not all cross one socket's memory controllers / the inter-socket
+    link.  Best effort: NVML may be missing or the box may have one node."""
+    global NUMA_NOTE
+    if os.environ.get("WM_BENCH_NO_AFFINITY"):
+        NUMA_NOTE = "affinity off (WM_BENCH_NO_AFFINITY)"
+        return
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(index)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode() if bytes is str else bus)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        NUMA_NOTE = "host threads bound to the %d CPUs next to GPU %s (%d..%d)" % (len(cpus), bus, cpus[0], cpus[-1])
+    except Exception as e:  # noqa: BLE001
+        NUMA_NOTE = "no NUMA binding (%s)" % (str(e)[:80],)
 
 
 def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, frames_override, secondary=False):
@@ -407,7 +436,9 @@ def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, frames_ove
                "h2d_bytes_per_step": int(fb * n_e2e), "d2h_bytes_per_step": int(nout * fb * n_e2e + 2 * nout * 4 * n_e2e),
                "frames_per_step": n_e2e, "frames_in_flight": NS, "matches_resident_path": e2e_ok,
                "h2d_gbs": world * reps * n_e2e / e2e_s * fb / 1e9, "d2h_gbs": world * reps * n_e2e / e2e_s * nout * fb / 1e9,
-               "pcie_note": "tools/pcie_bw.py on this pool's boxes: pinned copies reach 55 GB/s one way, 46 GB/s each way when both directions run",
+               "host_affinity": NUMA_NOTE,
+               "pcie_note": "tools/pcie_bw.py on this pool's boxes (profiles/r1_pcie_bw.txt): one GPU copies 55 GB/s one way, 46 GB/s each way when both "
+                            "directions run; all 8 GPUs together only 118 GB/s D2H / 77 GB/s each way, which caps e2e at N = 8",
                "api": "wm_embed_batch / wm_detect_batch on wm_get_stream() slots; pinned host frames in, watermarked frames + scalars out"}
 
     # the reference's literal protocol for this config (main.cpp:167-223): ONE image, synchronous calls, mean over loops
