@@ -60,7 +60,23 @@ using namespace clc;
 
 // the kernel text, verbatim from the reference apart from the `(floatN)(` -> `make_floatN(` rewrite
 namespace k_nvf {
-#define p 3  // main.cpp:106 builds nvf with -Dp=3
+#define p 3  // main.cpp:106 builds nvf with -Dp=<settings.ini p>; main.cpp:89 only lets 3 through
+#include "nvf.cl.inc"
+#undef p
+}
+// the other window sizes the class accepts (Watermark.cpp:24): the same kernel text with -Dp=5 / 7 / 9
+namespace k_nvf5 {
+#define p 5
+#include "nvf.cl.inc"
+#undef p
+}
+namespace k_nvf7 {
+#define p 7
+#include "nvf.cl.inc"
+#undef p
+}
+namespace k_nvf9 {
+#define p 9
 #include "nvf.cl.inc"
 #undef p
 }
@@ -84,6 +100,20 @@ void ref_nvf(const float* img, int rows, int cols, float* out)
     std::vector<float> local(19 * 19);  // Watermark.cpp:100: (16 + p)^2 floats
     run_ndrange(align_up(rows, 16), align_up(cols, 16), 16, 16,
                 [&]() { k_nvf::nvf(&im, out, reinterpret_cast<float(*)[18]>(local.data())); });
+}
+
+int ref_nvf_p(const float* img, int rows, int cols, int pw, float* out)
+{
+    const image2d im{img, rows, cols};
+    std::vector<float> local((16 + pw) * (16 + pw));  // Watermark.cpp:100
+    const size_t gr = align_up(rows, 16), gc = align_up(cols, 16);
+    switch (pw) {
+    case 3: run_ndrange(gr, gc, 16, 16, [&]() { k_nvf::nvf(&im, out, reinterpret_cast<float(*)[18]>(local.data())); }); return 0;
+    case 5: run_ndrange(gr, gc, 16, 16, [&]() { k_nvf5::nvf(&im, out, reinterpret_cast<float(*)[20]>(local.data())); }); return 0;
+    case 7: run_ndrange(gr, gc, 16, 16, [&]() { k_nvf7::nvf(&im, out, reinterpret_cast<float(*)[22]>(local.data())); }); return 0;
+    case 9: run_ndrange(gr, gc, 16, 16, [&]() { k_nvf9::nvf(&im, out, reinterpret_cast<float(*)[24]>(local.data())); }); return 0;
+    default: return -1;
+    }
 }
 
 void ref_scaled_neighbors(const float* img, int rows, int cols, const float* coeffs, float* out)

@@ -21,12 +21,12 @@ ME, NVF = 0, 1
 
 class Opts(C.Structure):
     _fields_ = [("fp16_products", C.c_int), ("sum_f32", C.c_int), ("solve_f32", C.c_int),
-                ("contract", C.c_int)]
+                ("contract", C.c_int), ("p", C.c_int)]
 
 
-def opts(fp16_products=1, sum_f32=0, solve_f32=0, contract=1):
-    """Canonical (default) = reference-faithful fp16 products, f64 sums/solve, fused mul-add."""
-    return Opts(fp16_products, sum_f32, solve_f32, contract)
+def opts(fp16_products=1, sum_f32=0, solve_f32=0, contract=1, p=3):
+    """Canonical (default) = reference-faithful fp16 products, f64 sums/solve, fused mul-add, 3x3 NVF window."""
+    return Opts(fp16_products, sum_f32, solve_f32, contract, p)
 
 
 FAITHFUL = opts()

@@ -28,6 +28,7 @@ def lib(fma=False):
         L = C.CDLL(path)
         fp = C.POINTER(C.c_float)
         L.ref_nvf.argtypes = [fp, C.c_int, C.c_int, fp]
+        L.ref_nvf_p.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp]
         L.ref_scaled_neighbors.argtypes = [fp, C.c_int, C.c_int, fp, fp]
         L.ref_me.argtypes = [fp, C.c_int, C.c_int, fp, fp]
         _libs[key] = L
@@ -42,11 +43,15 @@ def _p(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
-def nvf(img, fma=False):
+def nvf(img, fma=False, p=3):
+    """the reference's nvf kernel compiled with -Dp=<p> (kernels/nvf.hpp:14-17; p in 3, 5, 7, 9)"""
     rows, cols = img.shape
     buf = _colmajor(img)
     out = np.zeros_like(buf)
-    lib(fma).ref_nvf(_p(buf), rows, cols, _p(out))
+    if p == 3:
+        lib(fma).ref_nvf(_p(buf), rows, cols, _p(out))
+    elif lib(fma).ref_nvf_p(_p(buf), rows, cols, p, _p(out)) != 0:
+        raise ValueError("p must be 3, 5, 7 or 9")
     return np.ascontiguousarray(out.T)
 
 

@@ -32,6 +32,8 @@
  *   solve_f32     : 0 = f64 LU (canonical), 1 = f32 LU, both partial pivoting
  *   contract      : 1 = a*b+c fused where -cl-mad-enable permits (canonical,
  *                       NVIDIA OpenCL behaviour), 0 = separately rounded
+ *   p             : NVF window size (3 unless stated; the ME parts are p = 3 only,
+ *                   as in the reference)
  */
 #include <math.h>
 #include <stdint.h>
@@ -47,6 +49,7 @@ typedef struct {
     int sum_f32;
     int solve_f32;
     int contract;
+    int p;              /* NVF window size 3, 5, 7 or 9 (Watermark.cpp:24, kernels/nvf.hpp:14-17); 0 = 3 */
 } wmo_opts;
 
 enum { WMO_ME = 0, WMO_NVF = 1 }; /* Watermark.hpp:10-14 */
@@ -95,22 +98,24 @@ static double reduce_f32_array(const float *v, size_t n, int sum_f32)
     return s;
 }
 
-/* kernels/nvf.hpp:37-50 — NVF mask over the replicated 3x3 window */
+/* kernels/nvf.hpp:14-50 — NVF mask over the replicated p x p window (the kernel is compiled with -Dp, main.cpp:106) */
 void wmo_nvf(const float *img, int rows, int cols, float *mask, const wmo_opts *o)
 {
     const int contract = o->contract;
+    const int pw = o->p ? o->p : 3, pad = pw / 2;
+    const float psq = (float)(pw * pw); /* kernels/nvf.hpp:15,47: int pSquared, sum / pSquared */
 #pragma omp parallel for schedule(static)
     for (int r = 0; r < rows; r++) {
         for (int c = 0; c < cols; c++) {
             float sum = 0.0f, sumSq = 0.0f;
-            for (int i = -1; i <= 1; i++)
-                for (int j = -1; j <= 1; j++) {
+            for (int i = -pad; i <= pad; i++)
+                for (int j = -pad; j <= pad; j++) {
                     float v = px(img, rows, cols, r + i, c + j);
                     sum += v;
                     sumSq = contract ? fmaf(v, v, sumSq) : sumSq + v * v;
                 }
-            float mean = sum / 9.0f;
-            float q = sumSq / 9.0f;
+            float mean = sum / psq;
+            float q = sumSq / psq;
             float var = contract ? fmaf(-mean, mean, q) : q - mean * mean;
             mask[(size_t)r * cols + c] = var / (1.0f + var);
         }

@@ -27,6 +27,15 @@ def test_nvf_kernel(oracle, ref, rows, cols):
     assert np.abs(oracle.nvf(img, oracle.opts(contract=1)) - ref.nvf(img, fma=True)).max() <= 1e-2
 
 
+@pytest.mark.parametrize("p", [5, 7, 9])
+@pytest.mark.parametrize("rows,cols", [(64, 64), (67, 131), (130, 70)])
+def test_nvf_kernel_larger_windows(oracle, ref, rows, cols, p):
+    """The class accepts p in {3, 5, 7, 9} (Watermark.cpp:24); the nvf kernel is generic in p (kernels/nvf.hpp:14-17)."""
+    img = util.natural_image(rows, cols, seed=10 + p)
+    assert np.array_equal(oracle.nvf(img, oracle.opts(contract=0, p=p)), ref.nvf(img, fma=False, p=p))
+    assert np.abs(oracle.nvf(img, oracle.opts(contract=1, p=p)) - ref.nvf(img, fma=True, p=p)).max() <= 2e-2
+
+
 @pytest.mark.parametrize("rows,cols", SHAPES)
 def test_scaled_neighbors_kernel(oracle, ref, rows, cols):
     img = util.natural_image(rows, cols, seed=2) if rows != 512 else util.load_512_gray(oracle)
