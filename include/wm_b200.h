@@ -70,7 +70,9 @@ enum {
                                  matrix = four mixed-precision adds per lane); 0: FHADD chain.  Same bits for integer-valued pixels */
 };
 
-/* ---- lifetime: Watermark ctor / copy-ctor / reinitialize / dtor (Watermark.cpp:21-85) ---- */
+/* ---- lifetime: Watermark ctor / copy-ctor / reinitialize / dtor (Watermark.cpp:21-85) ----
+ * p: 3, 5, 7 or 9 like the reference's constructor (anything else: WM_ERR_BAD_P, "Wrong p parameter: <p>!").  p is the NVF
+ * window (kernels/nvf.hpp:14-17); the prediction-error mask and the detector are 3 x 3 for every p, as in the reference. */
 int wm_create(wm_ctx **out, int64_t rows, int64_t cols, const float *w_host_rowmajor, int p, float psnr,
               int device, void *cuda_stream /* cudaStream_t or NULL = own stream */);
 int wm_create_from_file(wm_ctx **out, int64_t rows, int64_t cols, const char *w_path, int p, float psnr,

@@ -839,3 +839,61 @@ def test_unbalanced_batches_are_partitioned(wmb, oracle, B, rows, cols):
     L.wm_dev_free(wm._h, din)
     L.wm_dev_free(wm._h, dout)
     wm.close()
+
+
+@pytest.mark.parametrize("p", [5, 7, 9])
+@pytest.mark.parametrize("rows,cols", [(64, 64), (67, 131), (270, 480)])
+def test_nvf_larger_windows(wmb, oracle, rows, cols, p):
+    """p in {5, 7, 9} (Watermark.cpp:24; kernels/nvf.hpp is generic in p): the NVF mask uses the p x p window, the
+    prediction-error parts stay 3 x 3 as in the reference.  Mask planes bit-identical to the oracle (itself pinned against
+    the reference's kernel text compiled with -Dp), embed / detect within north_star's tolerances, ME results untouched."""
+    img = util.natural_image(rows, cols, seed=40 + p)
+    W = util.normal_w(rows, cols)
+    o = oracle.opts(p=p)
+    wm = wmb.Watermark(rows, cols, W, p, 40.0)
+    wm3 = _mk(wmb, rows, cols, W)
+    onv = oracle.nvf(img, o)
+    for layout in LAYOUTS:
+        d = wmb.DeviceArray.from_numpy(wm, img, layout)
+        nv = wm.debug_plane(d, wmb.DBG_MASK_NVF)
+        report("nvf_p%d %dx%d layout=%d plane exact=%s rel=%.3g" % (p, rows, cols, layout, np.array_equal(nv, onv), util.rel(nv, onv)))
+        assert np.array_equal(nv, onv)
+        out, a, st = wm.makeWatermark(d, d, wmb.NVF)
+        oe = oracle.embed(img, W, 40.0, wmb.NVF, o=o)
+        got = out.numpy()
+        assert st == 0 and abs(a - oe["a"]) / oe["a"] <= 1e-3 and np.abs(got - oe["out"]).max() <= 1e-4 * 255
+        corr, st2 = wm.detectWatermark(wmb.DeviceArray.from_numpy(wm, got, layout), wmb.NVF)
+        od = oracle.detect(got, W, wmb.NVF, o=o)
+        report("nvf_p%d %dx%d layout=%d a=%.6f/%.6f corr=%.6f/%.6f" % (p, rows, cols, layout, a, oe["a"], corr, od["corr"]))
+        assert st2 == 0 and abs(corr - od["corr"]) / abs(od["corr"]) <= 1e-3
+        # the ME mask does not depend on p
+        out_me, a_me, _ = wm.makeWatermark(d, d, wmb.ME)
+        d3 = wmb.DeviceArray.from_numpy(wm3, img, layout)
+        out3, a3, _ = wm3.makeWatermark(d3, d3, wmb.ME)
+        assert a_me == a3 and np.array_equal(out_me.numpy(), out3.numpy())
+    # u8 frames and a small batch through the same path
+    y = util.natural_image(rows, cols, seed=50 + p, integer=True)
+    dy = wmb.DeviceArray.from_numpy(wm, y, wmb.ROW_MAJOR)
+    nvy = wm.debug_plane(dy, wmb.DBG_MASK_NVF)
+    assert np.array_equal(nvy, oracle.nvf(y.astype(np.float32), o))
+    B = 5
+    imgs = np.stack([util.natural_image(rows, cols, seed=60 + b) for b in range(B)])
+    L = wmb.lib()
+    din = L.wm_dev_alloc(wm._h, imgs.nbytes)
+    dout = L.wm_dev_alloc(wm._h, imgs.nbytes)
+    L.wm_dev_upload(wm._h, din, imgs.ctypes.data, imgs.nbytes)
+    di = wmb.image_desc(din, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+    do = wmb.image_desc(dout, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+    ab = np.zeros(B, np.float32)
+    cb = np.zeros(B, np.float32)
+    wm.embed_batch(0, di, di, do, rows * cols, rows * cols, rows * cols, B, wmb.NVF, ab)
+    wm.detect_batch(0, do, rows * cols, B, wmb.NVF, cb)
+    wm.sync(0)
+    for b in (0, B - 1):
+        oe = oracle.embed(imgs[b], W, 40.0, wmb.NVF, o=o)
+        od = oracle.detect(oe["out"], W, wmb.NVF, o=o)
+        assert abs(ab[b] - oe["a"]) / oe["a"] <= 1e-3 and abs(cb[b] - od["corr"]) / abs(od["corr"]) <= 1e-3
+    L.wm_dev_free(wm._h, din)
+    L.wm_dev_free(wm._h, dout)
+    wm.close()
+    wm3.close()

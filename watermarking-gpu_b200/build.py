@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwm_b200.so")
-SOURCES = [os.path.join(CSRC, f) for f in ("wm_api.cu", "wm_k_sweep.cu", "wm_k_stats.cu", "wm_k_apply.cu", "wm_k_detect.cu")]
+SOURCES = [os.path.join(CSRC, f) for f in ("wm_api.cu", "wm_k_sweep.cu", "wm_k_stats.cu", "wm_k_apply.cu", "wm_k_detect.cu", "wm_k_nvfp.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, "wm_kernels.cuh"), os.path.join(CSRC, "wm_launch.h"), os.path.join(ROOT, "include", "wm_b200.h")]
 OBJDIR = os.path.join(HERE, "build")
 

@@ -57,6 +57,7 @@ struct Slot {
     void* stage_in = nullptr; size_t stage_in_cap = 0;
     void* stage_base = nullptr; size_t stage_base_cap = 0;
     void* stage_out = nullptr; size_t stage_out_cap = 0;
+    void* maskp = nullptr; size_t maskp_cap = 0;  // NVF mask planes of a batch when p > 3 (k_nvfp)
     std::vector<TimedLaunch> timed;
 };
 
@@ -408,6 +409,32 @@ int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int ba
     return WM_OK;
 }
 
+// NVF mask with a p x p window, p > 3 (Watermark.cpp:96-114 with -Dp=5/7/9): one dense L x P plane per image of the batch
+int enqueue_nvf_planes(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int batch, const Geo& g, float* dst = nullptr)
+{
+    const size_t plane = (size_t)g.L * g.P;
+    if (!dst) {
+        const size_t need = plane * batch * sizeof(float);
+        if (need > s.maskp_cap) {
+            if (!s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+            CU(cudaStreamSynchronize(s.stream));
+            clear_graphs(ctx);
+            int rc;
+            if ((rc = ensure_stage(ctx, &s.maskp, &s.maskp_cap, need))) return rc;
+        }
+        dst = (float*)s.maskp;
+    }
+    NvfpArgs a;
+    a.img = v.ptr; a.ld = v.ld; a.bstride = bstride;
+    a.L = g.L; a.P = g.P; a.tiles_p = g.tiles_p; a.ntiles = g.ntiles;
+    a.vec_ok = vec_ok(v.ptr, v.ld, bstride, 0, v.dtype);
+    a.dst = dst; a.dst_bstride = (long long)plane;
+    const int gx = std::max(1, std::min(g.ntiles, (4 * ctx->sms + batch - 1) / batch));
+    launch_nvfp(v.dtype, ctx->p, v.transposed, dim3(gx, batch), s.stream, a);
+    CU(cudaGetLastError());
+    return WM_OK;
+}
+
 size_t stats_part_offset(const Plan& pl, int batch) { return (size_t)batch * (size_t)pl.nsweep * NTOT; }
 
 int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm_image* out, int64_t in_stride,
@@ -445,6 +472,9 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     ea.w_vec_ok = (g.P % 4 == 0);
     ea.strength = ctx->strength;
     ea.pstride = pl.gx_stats;
+    const bool planes = mask == WM_MASK_NVF && ctx->p != 3;  // larger NVF windows: the mask comes from k_nvfp's planes
+    const int kmask = planes ? 2 : mask;
+    ea.maskp = nullptr; ea.mask_bstride = (long long)g.L * g.P;
     ea.part = s.part + stats_part_offset(pl, batch);
     ea.counter = s.counters + s.batch_cap;
     ea.scal = s.scal; ea.dbg = s.dbg;
@@ -462,9 +492,13 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
                    make_tmap(&tmW, WM_F32, W, g.P, g.L, 1, g.P, 0, TP, TL);
     {
         KTimer t(ctx, s, mask == WM_MASK_ME ? WM_K_ME_STATS : WM_K_NVF_STATS);
+        if (planes) {
+            if ((rc = enqueue_nvf_planes(ctx, s, vi, in_stride, batch, g))) return rc;
+            ea.maskp = (const float*)s.maskp;
+        }
         for (const SubBatch& sb : pl.embed) {
             ea.b0 = sb.b0; ea.nblk_base = sb.base; ea.nblk_extra = sb.extra;
-            launch_stats(vi.dtype, mask, vi.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmI, tmW, ea);
+            launch_stats(vi.dtype, kmask, vi.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmI, tmW, ea);
         }
     }
     CU(cudaGetLastError());
@@ -472,7 +506,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
         KTimer t(ctx, s, WM_K_APPLY);
         for (const SubBatch& sb : pl.embed) {
             ea.b0 = sb.b0; ea.nblk_base = sb.base; ea.nblk_extra = sb.extra;
-            launch_apply(vi.dtype, vo.dtype, mask, vi.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmI, tmW, ea);
+            launch_apply(vi.dtype, vo.dtype, kmask, vi.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmI, tmW, ea);
         }
     }
     CU(cudaGetLastError());
@@ -503,6 +537,8 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     da.vec_ok = vec_ok(v.ptr, v.ld, img_stride, 0, v.dtype);
     da.w_vec_ok = (g.P % 4 == 0);
     da.pstride = pl.gx_detect;
+    const bool planes = mask == WM_MASK_NVF && ctx->p != 3;
+    da.maskp = nullptr; da.mask_bstride = (long long)g.L * g.P;
     da.part = s.part + stats_part_offset(pl, batch);
     da.counter = s.counters + 2 * s.batch_cap;
     da.scal = s.scal; da.dbg = s.dbg;
@@ -514,9 +550,13 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
                    make_tmap(&tmW, WM_F32, W, g.P, g.L, 1, g.P, 0, SW, TL + 2);
     {
         KTimer t(ctx, s, WM_K_DETECT);
+        if (planes) {
+            if ((rc = enqueue_nvf_planes(ctx, s, v, img_stride, batch, g))) return rc;
+            da.maskp = (const float*)s.maskp;
+        }
         for (const SubBatch& sb : pl.detect) {
             da.b0 = sb.b0; da.nblk_base = sb.base; da.nblk_extra = sb.extra;
-            launch_detect(v.dtype, mask, v.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmZ, tmW, da);
+            launch_detect(v.dtype, planes ? 2 : mask, v.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmZ, tmW, da);
         }
     }
     CU(cudaGetLastError());
@@ -602,6 +642,7 @@ void free_slot(Slot& s)
     if (s.stage_in) cudaFree(s.stage_in);
     if (s.stage_base) cudaFree(s.stage_base);
     if (s.stage_out) cudaFree(s.stage_out);
+    if (s.maskp) cudaFree(s.maskp);
     for (auto& t : s.timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
@@ -614,7 +655,6 @@ int create_common(wm_ctx** out, int64_t rows, int64_t cols, int p, float psnr, i
     *out = nullptr;
     // Watermark.cpp:24-25
     if (p != 3 && p != 5 && p != 7 && p != 9) return fail(nullptr, WM_ERR_BAD_P, "Wrong p parameter: " + std::to_string(p) + "!");
-    if (p != 3) return fail(nullptr, WM_ERR_BAD_P, "p = " + std::to_string(p) + ": only p = 3 is implemented (main.cpp:89 enforces 3)");
     if (!(psnr > 0.0f)) return fail(nullptr, WM_ERR_ARG, "psnr must be > 0 (main.cpp:96)");
     if (rows < 3 || cols < 3 || rows > (1 << 30) / 4 || cols > (1 << 30) / 4) return fail(nullptr, WM_ERR_DIMS, "unsupported image dims");
     int ndev = 0;
@@ -989,6 +1029,12 @@ int wm_debug_plane(wm_ctx* ctx, const wm_image* img, int what, float* dst_dev)
     if ((rc = ensure_slot(ctx, s, 1, std::max(pl.gx_stats, pl.gx_detect), pl.nsweep, pl.nframe))) return rc;
     if (what == WM_DBG_ERRSEQ) {
         if ((rc = enqueue_sweep(ctx, s, v, 0, 1, g, pl))) return rc;
+    }
+    if (what == WM_DBG_MASK_NVF && ctx->p != 3) {  // the p x p window goes through k_nvfp, straight into the caller's plane
+        if ((rc = enqueue_nvf_planes(ctx, s, v, 0, 1, g, dst_dev))) return rc;
+        ctx->launches++;
+        CU(cudaStreamSynchronize(s.stream));
+        return WM_OK;
     }
     PlaneArgs pa;
     pa.img = v.ptr; pa.ld = v.ld;

@@ -6,7 +6,8 @@ namespace wm {
 template <typename PixT, typename OutT, bool TMA, bool SB>
 void launch_apply_s(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const EmbedArgs& a)
 {
-    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 0, true, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 0, false, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
+    if (mask == 2) { WM_LAUNCH((k_apply<PixT, OutT, 2, false, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }  // NVF plane (p > 3)
+    else if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 0, true, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 0, false, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
     else { if (tr) WM_LAUNCH((k_apply<PixT, OutT, 1, true, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); else WM_LAUNCH((k_apply<PixT, OutT, 1, false, TMA, SB>), embed_smem(TMA, sizeof(PixT) == 1), tmI, tmW, a); }
 }
 template <typename PixT, typename OutT, bool TMA>

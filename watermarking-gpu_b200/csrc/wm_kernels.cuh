@@ -1291,6 +1291,8 @@ struct EmbedArgs {
     int nblk_base, nblk_extra;  // CTAs per image = nblk_base + (image < nblk_extra)
     float strength;
     int b0, pstride;    // first image of this launch; partial rows per image
+    const float* maskp; // MASK == 2: precomputed NVF mask planes (p > 3), dense L x P per image
+    long long mask_bstride;
     double* part;       // [batch][pstride][2]         (stats)
     unsigned* counter;  // [batch]                     (stats)
     Scal* scal;
@@ -1377,8 +1379,23 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
 }
 
 // mask.W for one thread's 4 px x 4 lines: calls f(r, m[4], w[4], centre-line window) per line
+// where a thread finds its 4 x 4 cells of a precomputed mask plane (MASK == 2): pointer to (its first line, its first pixel),
+// the plane's row stride and how many lines / pixels from there are inside the image
+struct MaskSrc { const float* p; int stride, nl, np; };
+__device__ __forceinline__ void mask_from_plane(float (&m)[4], const MaskSrc& ms, int r)
+{
+    const float* row = ms.p + (long long)r * ms.stride;
+    if (r < ms.nl && ms.np >= 4 && (ms.stride & 3) == 0) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row));
+        m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) m[j] = (r < ms.nl && j < ms.np) ? __ldg(row + j) : 0.0f;
+    }
+}
 template <int MASK, bool TR, typename T, typename F>
-__device__ __forceinline__ void mask_lines(const T* __restrict__ tile, const float* __restrict__ wt, const float (&c)[8], F f)
+__device__ __forceinline__ void mask_lines(const T* __restrict__ tile, const float* __restrict__ wt, const float (&c)[8], F f,
+                                           const MaskSrc ms = MaskSrc{nullptr, 0, 0, 0})
 {
     constexpr int ST = TileGeo<T>::STRIDE;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1393,10 +1410,13 @@ __device__ __forceinline__ void mask_lines(const T* __restrict__ tile, const flo
         const float4 wv = *reinterpret_cast<const float4*>(wt + (4 * w + r) * TP + 4 * lane);
         const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
         float m[4];
+        if constexpr (MASK == 2) mask_from_plane(m, ms, r);
+        else {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if constexpr (MASK == 0) m[j] = fabsf(__fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j)));
-            else m[j] = nvf_mask<TR>(r0, r1, r2, j);
+            for (int j = 0; j < 4; j++) {
+                if constexpr (MASK == 0) m[j] = fabsf(__fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j)));
+                else m[j] = nvf_mask<TR>(r0, r1, r2, j);
+            }
         }
         f(r, m, wq, r1);
 #pragma unroll
@@ -1442,7 +1462,8 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
                     const float u = __fmul_rn(mj, wq[j]);
                     fs = __fmaf_rn(u, u, fs);
                 }
-            });
+            }, MASK == 2 ? MaskSrc{a.maskp + (long long)b * a.mask_bstride + (long long)(l0 + 4 * w) * P + pb, P, L - (l0 + 4 * w), P - pb}
+                         : MaskSrc{nullptr, 0, 0, 0});
         };
         if (l0 + TL <= L && p0 + TP <= P) run(BoolTag<true>{}); else run(BoolTag<false>{});
         dsum += (double)fs;
@@ -1569,7 +1590,8 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
                     OutT* orow = out + (long long)ch * a.out_pstride + (long long)l * a.out_ld + pb;
                     store4<OutT>(orow, ov, out_vec && (FULL || nvalid >= 4), nvalid);
                 }
-            });
+            }, MASK == 2 ? MaskSrc{a.maskp + (long long)b * a.mask_bstride + (long long)(l0 + 4 * w) * P + pb, P, L - (l0 + 4 * w), P - pb}
+                         : MaskSrc{nullptr, 0, 0, 0});
         };
         if (l0 + TL <= L && p0 + TP <= P) run(BoolTag<true>{}); else run(BoolTag<false>{});
     });
@@ -1591,6 +1613,8 @@ struct DetectArgs {
     int vec_ok, w_vec_ok;
     int nblk_base, nblk_extra;  // CTAs per image = nblk_base + (image < nblk_extra)
     int b0, pstride;    // first image of this launch; partial rows per image
+    const float* maskp; // MASK == 2: precomputed NVF mask planes (p > 3), dense L x P per image
+    long long mask_bstride;
     double* part;       // [batch][pstride][3]
     unsigned* counter;
     Scal* scal;
@@ -1601,8 +1625,10 @@ struct DetectArgs {
 template <int MASK, bool TR, bool FULL, typename ZT>
 __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const float* __restrict__ wt, float* __restrict__ ut,
                                             const float (&c)[8], int l0, int p0,
-                                            int L, int P, float& fd, float& fz, float& fu)
+                                            int L, int P, float& fd, float& fz, float& fu, const float* __restrict__ mplane = nullptr)
 {
+    // MASK == 2: the NVF mask (p > 3) was computed into a dense L x P plane beforehand
+    auto plane_at = [&](int l, int p) { return (l < L && p < P) ? __ldg(mplane + (long long)l * P + p) : 0.0f; };
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int pb = p0 + 4 * lane;
     const int scol = 4 * lane + HP;
@@ -1625,7 +1651,9 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const flo
                 const float e = __fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j));
                 ez[r][j] = e;
                 float m;
-                if constexpr (MASK == 0) m = fabsf(e); else m = nvf_mask<TR>(r0, r1, r2, j);
+                if constexpr (MASK == 0) m = fabsf(e);
+                else if constexpr (MASK == 1) m = nvf_mask<TR>(r0, r1, r2, j);
+                else m = plane_at(l0 + 4 * w + r, pb + j);
                 uu[j] = __fmul_rn(m, wq[j]);
             }
             *reinterpret_cast<float4*>(ut + (4 * w + r + 1) * SW + scol) = make_float4(uu[0], uu[1], uu[2], uu[3]);
@@ -1652,7 +1680,8 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const flo
             for (int j = 0; j < 4; j++) {
                 float m;
                 if constexpr (MASK == 0) m = fabsf(__fsub_rn(r1[j + 1], predict<TR>(c, r0, r1, r2, j)));
-                else m = nvf_mask<TR>(r0, r1, r2, j);
+                else if constexpr (MASK == 1) m = nvf_mask<TR>(r0, r1, r2, j);
+                else m = plane_at(l, pb + j);
                 uu[j] = __fmul_rn(m, wq[j]);
             }
             *reinterpret_cast<float4*>(ut + (rl + 1) * SW + scol) = make_float4(uu[0], uu[1], uu[2], uu[3]);
@@ -1669,7 +1698,8 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const flo
             float q2[3] = {(float)zc[ZS - 1], (float)zc[ZS], (float)zc[ZS + 1]};
             float m;
             if constexpr (MASK == 0) m = fabsf(__fsub_rn(q1[1], predict<TR>(c, q0, q1, q2, 0)));
-            else m = nvf_mask<TR>(q0, q1, q2, 0);
+            else if constexpr (MASK == 1) m = nvf_mask<TR>(q0, q1, q2, 0);
+            else m = plane_at(l, p);
             ut[(rl + 1) * SW + (rp + HP)] = __fmul_rn(m, wt[(rl + 1) * SW + (rp + HP)]);
         }
     }
@@ -1799,8 +1829,8 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
             }
         }
         float fd = 0.0f, fz = 0.0f, fu = 0.0f;
-        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu);
-        else detect_tile<MASK, TR, false>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu);
+        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr);
+        else detect_tile<MASK, TR, false>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr);
         ddot += (double)fd; dnz += (double)fz; dnu += (double)fu;
         if constexpr (TMA) __syncthreads();  // ut and the stage are rewritten from the next iteration on
     }
@@ -1863,6 +1893,62 @@ __global__ void __launch_bounds__(NT, 3) k_plane(const PlaneArgs a)
             }
 #pragma unroll
             for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
+        }
+    }
+}
+
+// ================================================================================================
+// NVF mask for the larger windows the class accepts (p = 5, 7, 9: Watermark.cpp:24, kernels/nvf.hpp:14-50), written
+// to a dense L x P plane per image that k_stats / k_apply / k_detect then read (MASK == 2).  The reference's only caller
+// refuses p != 3 (main.cpp:89), so this path is kept simple rather than fused: sum / sumSq over the p x p window in the
+// reference's order (rows outer, columns inner), mean = sum / p^2, var = sumSq / p^2 - mean^2, mask = var / (1 + var).
+// ================================================================================================
+struct NvfpArgs {
+    const void* img;
+    long long ld, bstride;
+    int L, P, tiles_p, ntiles, vec_ok;
+    float* dst;  // [batch][L x P]
+    long long dst_bstride;
+};
+template <typename PixT, int PW, bool TR>
+__global__ void __launch_bounds__(NT) k_nvfp(const NvfpArgs a)
+{
+    constexpr int PAD = PW / 2;
+    static_assert(PAD <= HP, "column halo kept in smem must cover the window");
+    __shared__ __align__(16) float tile[(TL + 2 * PAD) * SW];
+    const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)blockIdx.y * a.bstride;
+    float* dst = a.dst + (long long)blockIdx.y * a.dst_bstride;
+    const int L = a.L, P = a.P;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float psq = (float)(PW * PW);
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        const int tl = t / a.tiles_p, tp = t - tl * a.tiles_p;
+        const int l0 = tl * TL, p0 = tp * TP;
+        __syncthreads();
+        load_tile<PixT, TL + 2 * PAD>(tile, img, a.ld, L, P, l0 - PAD, p0 - HP, a.vec_ok != 0);
+        __syncthreads();
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) {
+            const int l = l0 + 4 * w + r;
+#pragma unroll 1
+            for (int j = 0; j < 4; j++) {
+                const int p = p0 + 4 * lane + j;
+                if (l >= L || p >= P) continue;
+                const float* ctr = tile + (4 * w + r + PAD) * SW + (4 * lane + j + HP);
+                float s = 0.0f, q = 0.0f;
+                bool first = true;
+#pragma unroll
+                for (int i = -PAD; i <= PAD; i++)      // reference: row offset (outer)
+#pragma unroll
+                    for (int k = -PAD; k <= PAD; k++) {  // reference: column offset (inner)
+                        const float v = TR ? ctr[k * SW + i] : ctr[i * SW + k];  // col-major images: lines are columns
+                        if (first) { s = v; q = __fmul_rn(v, v); first = false; }
+                        else { s = __fadd_rn(s, v); q = __fmaf_rn(v, v, q); }
+                    }
+                const float mean = __fdiv_rn(s, psq);
+                const float var = __fmaf_rn(-mean, mean, __fdiv_rn(q, psq));
+                dst[(long long)l * P + p] = div_safe(var, __fadd_rn(1.0f, var));
+            }
         }
     }
 }
