@@ -897,3 +897,24 @@ def test_nvf_larger_windows(wmb, oracle, rows, cols, p):
     L.wm_dev_free(wm._h, dout)
     wm.close()
     wm3.close()
+
+
+@pytest.mark.parametrize("rows,cols", [(3, 3), (4, 5), (8, 300), (33, 129)])
+def test_nvf_larger_windows_tiny_and_strided(wmb, oracle, rows, cols):
+    """p = 9 on images smaller than the window (every read clamps) and on a strided buffer."""
+    p = 9
+    img = util.natural_image(rows, cols, seed=70 + rows)
+    W = util.normal_w(rows, cols)
+    o = oracle.opts(p=p)
+    wm = wmb.Watermark(rows, cols, W, p, 40.0)
+    onv = oracle.nvf(img, o)
+    for layout in LAYOUTS:
+        for ld in (0, (cols if layout == wmb.ROW_MAJOR else rows) + 5):
+            d = wmb.DeviceArray.from_numpy(wm, img, layout, ld=ld)
+            assert np.array_equal(wm.debug_plane(d, wmb.DBG_MASK_NVF), onv)
+            out, a, st = wm.makeWatermark(d, d, wmb.NVF)
+            oe = oracle.embed(img, W, 40.0, wmb.NVF, o=o)
+            if oe["status"] == 0 and np.isfinite(oe["a"]):
+                assert st == 0 and abs(a - oe["a"]) / abs(oe["a"]) <= 1e-3
+                assert np.abs(out.numpy() - oe["out"]).max() <= 1e-4 * 255
+    wm.close()
