@@ -24,6 +24,13 @@ __global__ void __launch_bounds__(256) k(float* out, float seed)
             if (OP == 4 && (i & 1) == 0) { unsigned h; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(a[i]), "f"(a[i + 1])); b[i] = __uint_as_float(h); }  // F2FP
             if (OP == 5) a[i] = __fadd_rn(a[i], b[i]);                                               // FADD
             if (OP == 6 && i < UNROLL / 2) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(ua[i]) : "l"(sc));      // FADD2
+            if (OP == 7 && i < UNROLL / 2) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(ua[i]) : "l"(sc));      // FMUL2
+            if (OP == 8) { unsigned x = __float_as_uint(a[i]); asm volatile("cvt.rn.f32.u8 %0, %1;" : "=f"(a[i]) : "r"(x & 0xffu)); }              // I2F.U8 (+LOP)
+            if (OP == 9) { unsigned x = __float_as_uint(a[i]); x = __byte_perm(x, 0x4b000000u, 0x7440); a[i] = __fadd_rn(__uint_as_float(x), -8388608.0f); }  // PRMT + FADD: byte -> float
+            if (OP == 10) { unsigned x = __float_as_uint(a[i]); asm volatile("mul.rn.f16x2 %0, %0, %1;" : "+r"(x) : "r"(0x00010001u)); a[i] = __uint_as_float(x); }  // HMUL2, subnormal operand
+            if (OP == 11) { unsigned x = __float_as_uint(a[i]); asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(x) : "r"(hh), "r"(0x80008000u)); a[i] = __uint_as_float(x); }  // HFMA2
+            if (OP == 12) { unsigned x = __float_as_uint(a[i]); if (i & 1) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(x) : "r"(hh), "r"(0x80008000u)); else asm volatile("mul.rn.f16x2 %0, %0, %1;" : "+r"(x) : "r"(hh)); a[i] = __uint_as_float(x); }  // HMUL2 / HFMA2 alternating
+            if (OP == 13) { unsigned x = __float_as_uint(a[i]); x = __byte_perm(x, __float_as_uint(b[i]), 0x5432); a[i] = __uint_as_float(x); }  // PRMT
         }
     }
     float s = 0;
@@ -63,5 +70,12 @@ int main()
     run<2>("FHADD", UNROLL, d, p.multiProcessorCount, clk);
     run<3>("HMUL2", UNROLL, d, p.multiProcessorCount, clk);
     run<4>("F2FP", UNROLL / 2, d, p.multiProcessorCount, clk);
+    run<7>("FMUL2", UNROLL / 2, d, p.multiProcessorCount, clk);
+    run<8>("I2F.U8", UNROLL, d, p.multiProcessorCount, clk);
+    run<9>("PRMT+FADD", UNROLL, d, p.multiProcessorCount, clk);
+    run<10>("HMUL2sub", UNROLL, d, p.multiProcessorCount, clk);
+    run<11>("HFMA2", UNROLL, d, p.multiProcessorCount, clk);
+    run<12>("HMUL2/HFMA2", UNROLL, d, p.multiProcessorCount, clk);
+    run<13>("PRMT", UNROLL, d, p.multiProcessorCount, clk);
     return 0;
 }

@@ -102,6 +102,24 @@ __device__ __forceinline__ unsigned long long gtime()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// u8 -> f32 without I2F: cvt.rn.f32.u8 (SASS I2F.U8) issues at 0.5 warp-instructions per clock per SM on sm_100a (8 clocks of
+// the conversion pipe per warp, tools/microbench/pipes.cu), which made the conversion of the u8 kernels' windows as expensive
+// as their arithmetic.  Instead: byte b -> the half with bits 0x6400 | b (= 1024 + b, exact), one PRMT per PAIR of pixels,
+// then a mixed-precision add of -1024 (FHADD, full rate on the FMA pipe) widens and removes the bias in one exact step.
+__device__ __forceinline__ void u8x4_to_f32(unsigned u, float& x0, float& x1, float& x2, float& x3)
+{
+    const unsigned lo = __byte_perm(u, 0x64646464u, 0x4140);  // (0x64, b1, 0x64, b0)
+    const unsigned hi = __byte_perm(u, 0x64646464u, 0x4342);  // (0x64, b3, 0x64, b2)
+    asm("{\n\t.reg .b16 a, b, c, d;\n\t"
+        "mov.b32 {a, b}, %4;\n\tmov.b32 {c, d}, %5;\n\t"
+        "add.rn.f32.f16 %0, a, %6;\n\tadd.rn.f32.f16 %1, b, %6;\n\t"
+        "add.rn.f32.f16 %2, c, %6;\n\tadd.rn.f32.f16 %3, d, %6;\n\t}"
+        : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(lo), "r"(hi), "f"(-1024.0f));
+}
+// single pixel: 2^23 + b as an f32 bit pattern, minus 2^23 (LOP3 + FADD)
+__device__ __forceinline__ float px_f32(unsigned char b) { return __fadd_rn(__uint_as_float(0x4b000000u | (unsigned)b), -8388608.0f); }
+__device__ __forceinline__ float px_f32(float v) { return v; }
+
 // CTAs working on image b of a batch: the launch's one wave of resident CTAs is split as evenly as possible, the first
 // `extra` images get one more (gridDim.x = base + (extra > 0); the surplus CTAs of the other images exit at once)
 __device__ __forceinline__ int blocks_of_image(int base, int extra, int b) { return base + (b < extra ? 1 : 0); }
@@ -185,8 +203,7 @@ __device__ __forceinline__ void load_tile(float* __restrict__ tile, const PixT* 
             if constexpr (sizeof(PixT) == 4) {
                 v = __ldg(reinterpret_cast<const float4*>(row + p));
             } else {
-                const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(row + p));
-                v = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+                u8x4_to_f32(__ldg(reinterpret_cast<const unsigned*>(row + p)), v.x, v.y, v.z, v.w);
             }
         } else {
             v.x = (float)row[clampi(p, 0, P - 1)];
@@ -247,7 +264,7 @@ struct TilePrefetch {
                 float4 f;
                 if ((ok >> k) & 1) {
                     if constexpr (sizeof(PixT) == 4) f = *reinterpret_cast<const float4*>(&v[k]);
-                    else f = make_float4((float)v[k].x, (float)v[k].y, (float)v[k].z, (float)v[k].w);
+                    else u8x4_to_f32(*reinterpret_cast<const unsigned*>(&v[k]), f.x, f.y, f.z, f.w);
                 } else {
                     const int r = idx / CH, c = idx - r * CH;
                     const PixT* row = img + (long long)clampi(l_org + r, 0, L - 1) * ld;
@@ -314,11 +331,9 @@ __device__ __forceinline__ void convert_u8_tile(const unsigned char* __restrict_
 #pragma unroll
     for (int i = 0; i < NIT; i++)
         if (w + i * (NT / 32) < NROWS)
-            *reinterpret_cast<float4*>(d0 + i * (NT / 32) * SW) =
-                make_float4((float)(u[i] & 0xffu), (float)((u[i] >> 8) & 0xffu), (float)((u[i] >> 16) & 0xffu), (float)(u[i] >> 24));
+        { float4 f; u8x4_to_f32(u[i], f.x, f.y, f.z, f.w); *reinterpret_cast<float4*>(d0 + i * (NT / 32) * SW) = f; }
     if (tail)
-        *reinterpret_cast<float4*>(dst + tr * SW + 4 * tc) =
-            make_float4((float)(ut & 0xffu), (float)((ut >> 8) & 0xffu), (float)((ut >> 16) & 0xffu), (float)(ut >> 24));
+    { float4 f; u8x4_to_f32(ut, f.x, f.y, f.z, f.w); *reinterpret_cast<float4*>(dst + tr * SW + 4 * tc) = f; }
 }
 
 // u8 TMA stage -> fp16 work tile (rows of SW halves).  Integers 0..255 are exact in fp16: byte b becomes the half with
@@ -649,11 +664,12 @@ __device__ __forceinline__ void load_win6(float (&w)[6], const unsigned char* li
 {
     const int lane = threadIdx.x & 31;
     const unsigned u = *reinterpret_cast<const unsigned*>(line + U8_OFF + sc);
-    const float x0 = (float)(u & 0xffu), x1 = (float)((u >> 8) & 0xffu), x2 = (float)((u >> 16) & 0xffu), x3 = (float)(u >> 24);
+    float x0, x1, x2, x3;
+    u8x4_to_f32(u, x0, x1, x2, x3);
     float l = __shfl_up_sync(0xffffffffu, x3, 1);
     float r = __shfl_down_sync(0xffffffffu, x0, 1);
     if (lane == 0 || lane == 31) {
-        const float h = (float)line[U8_OFF + sc + (lane == 0 ? -1 : 4)];
+        const float h = px_f32(line[U8_OFF + sc + (lane == 0 ? -1 : 4)]);
         if (lane == 0) l = h; else r = h;
     }
     w[0] = l; w[1] = x0; w[2] = x1; w[3] = x2; w[4] = x3; w[5] = r;
@@ -1173,7 +1189,7 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
                 for (int k = 0; k < 9; k++) {  // raster order, k = 4 is the centre
                     const int ll = l + k / 3 - 1, pp = p + k % 3 - 1;
                     if (!(ll >= 1 && ll <= L - 2 && pp >= 1 && pp <= P - 2)) m |= 1u << k;
-                    win[threadIdx.x * 9 + k] = (float)img[(long long)clampi(ll, 0, L - 1) * a.ld + clampi(pp, 0, P - 1)];
+                    win[threadIdx.x * 9 + k] = px_f32(img[(long long)clampi(ll, 0, L - 1) * a.ld + clampi(pp, 0, P - 1)]);
                 }
                 ncm[threadIdx.x] = m;
             }
@@ -1576,8 +1592,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
                                 const float4 v = __ldg(reinterpret_cast<const float4*>(br));
                                 bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
                             } else {
-                                const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(br));
-                                bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+                                u8x4_to_f32(__ldg(reinterpret_cast<const unsigned*>(br)), bv[0], bv[1], bv[2], bv[3]);
                             }
                         } else {
 #pragma unroll
@@ -1693,9 +1708,9 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const flo
         const int l = l0 + rl, p = p0 + rp;
         if (l >= 0 && l < L && p >= 0 && p < P) {
             const ZT* zc = zt + (rl + 2) * ZS + ZO + (rp + HP);
-            float q0[3] = {(float)zc[-ZS - 1], (float)zc[-ZS], (float)zc[-ZS + 1]};
-            float q1[3] = {(float)zc[-1], (float)zc[0], (float)zc[1]};
-            float q2[3] = {(float)zc[ZS - 1], (float)zc[ZS], (float)zc[ZS + 1]};
+            float q0[3] = {px_f32(zc[-ZS - 1]), px_f32(zc[-ZS]), px_f32(zc[-ZS + 1])};
+            float q1[3] = {px_f32(zc[-1]), px_f32(zc[0]), px_f32(zc[1])};
+            float q2[3] = {px_f32(zc[ZS - 1]), px_f32(zc[ZS]), px_f32(zc[ZS + 1])};
             float m;
             if constexpr (MASK == 0) m = fabsf(__fsub_rn(q1[1], predict<TR>(c, q0, q1, q2, 0)));
             else if constexpr (MASK == 1) m = nvf_mask<TR>(q0, q1, q2, 0);
