@@ -66,8 +66,12 @@ enum {
     WM_OPT_CUDA_GRAPHS = 5,   /* 1 (default): wm_embed / wm_detect replay a captured CUDA graph when called again with the same arguments */
     WM_OPT_SPLIT_COST = 7,    /* tile-times one more launch is assumed to cost (default 8: launch gap, pipeline ramp, second stage + solve tail) when a batch whose size does not divide
                                  the resident CTA count is launched as better-balanced sub-batches; < 0: never split */
-    WM_OPT_MMA_ACCUM = 6      /* 1 (default): the fp16-rounded Rx/rx products are summed on the tensor pipe (HMMA with a 0/1 selector
+    WM_OPT_MMA_ACCUM = 6,     /* 1 (default): the fp16-rounded Rx/rx products are summed on the tensor pipe (HMMA with a 0/1 selector
                                  matrix = four mixed-precision adds per lane); 0: FHADD chain.  Same bits for integer-valued pixels */
+    WM_OPT_HOST_RUN_FRAMES = 9, /* frames per run (one batched launch sequence + its copies) of wm_process_frames when frames are in HOST memory; default 4 */
+    WM_OPT_F32_SOLVE = 8      /* 0 (default): the 8x8 system is summed and solved in f64 (pivot cut 1e-12 max|Rx|); 1: Rx / rx are rounded to f32
+                                 and solved by an f32 LU (pivot cut 1e-6 max|Rx|) like af::solve on the reference's f32 arrays
+                                 (Watermark.cpp:203) — the mode to use when pinning against a real ArrayFire run */
 };
 
 /* ---- lifetime: Watermark ctor / copy-ctor / reinitialize / dtor (Watermark.cpp:21-85) ----
@@ -112,6 +116,15 @@ int wm_embed_host(wm_ctx *ctx, const wm_image *in_gray_host, const wm_image *bas
                   int mask_type, float *a_host);
 int wm_detect_host(wm_ctx *ctx, const wm_image *img_host, int mask_type, float *corr_host);
 
+/* Pipelined host-buffer form: `batch` host images (element strides as in the device batch API, 0 = dense) are staged with 2-D copies on the
+ * slot's stream, processed as one batched launch sequence and copied back; the call returns at once, results (and the output images) are
+ * valid after wm_sync(ctx, slot).  Strided host views are honoured: only the images' own pixels are read or written. */
+int wm_embed_host_batch(wm_ctx *ctx, int slot, const wm_image *in_gray_host, const wm_image *base_host, wm_image *out_host,
+                        int64_t in_stride, int64_t base_stride, int64_t out_stride, int batch, int mask_type,
+                        float *a_host, int *status_host);
+int wm_detect_host_batch(wm_ctx *ctx, int slot, const wm_image *img_host, int64_t img_stride, int batch, int mask_type,
+                         float *corr_host, int *status_host);
+
 /* ---- af::rgb2gray(rgb, wr, wg, wb) of the reference's image flow (main.cpp:142-154,196-197): planar f32 RGB -> gray ---- */
 int wm_rgb2gray(wm_ctx *ctx, const wm_image *rgb, wm_image *gray, float wr, float wg, float wb);
 
@@ -131,8 +144,9 @@ int wm_debug_set_coeffs(wm_ctx *ctx, const float *coeffs8_or_null);
 int wm_debug_plane(wm_ctx *ctx, const wm_image *img, int what, float *dst_dev /* same layout, dense */);
 
 /* per-kernel device time (ms) accumulated since the last reset, when WM_OPT_KERNEL_TIMING is on.
- * names: 0 rx_sweep(+solve) 1 me_stats 2 nvf_stats 3 embed_apply 4 detect_apply.  Returns count of launches. */
-enum { WM_K_SWEEP = 0, WM_K_ME_STATS = 1, WM_K_NVF_STATS = 2, WM_K_APPLY = 3, WM_K_DETECT = 4, WM_K_COUNT = 5 };
+ * names: 0 rx_sweep(+solve) 1 me_stats 2 nvf_stats 3 me_apply 4 me_detect 5 nvf_apply 6 nvf_detect.  Returns the number of timed brackets
+ * (one per op call: all sub-batch launches of that kernel family). */
+enum { WM_K_SWEEP = 0, WM_K_ME_STATS = 1, WM_K_NVF_STATS = 2, WM_K_APPLY = 3, WM_K_DETECT = 4, WM_K_APPLY_NVF = 5, WM_K_DETECT_NVF = 6, WM_K_COUNT = 7 };
 int64_t wm_get_kernel_times(wm_ctx *ctx, int kernel, double *total_ms, int reset);
 int64_t wm_launch_count(const wm_ctx *ctx); /* kernels launched by this ctx since creation */
 
@@ -148,14 +162,25 @@ typedef struct wm_video_ctx {
     int32_t frames_on_device; /* 1: `frames`/`out` are device pointers; 0: host (pinned recommended) */
     int32_t reserved;
 } wm_video_ctx;
-enum { WM_VIDEO_EMBED = 0, WM_VIDEO_DETECT = 1 };
+enum { WM_VIDEO_EMBED = 0, WM_VIDEO_DETECT = 1, WM_VIDEO_EMBED_VERIFY = 2 };
 /* Processes frames [first_index, first_index + n_frames) of a stream: frame i is gated by
  * (i % watermark_interval == 0) exactly as main.cpp:346,395 (global index, so shards agree).
  * EMBED: out receives every frame's Y plane (contiguous height x width; gated-off frames are copied
- * through), scalars[i] = a.  DETECT: scalars[i] = correlation (NaN for gated-off frames).  out may be NULL
- * for DETECT.  Returns the number of frames processed or a negative error. */
+ * through), scalars[i] = a (NaN for gated-off and for unsolvable frames).  DETECT: scalars[i] = correlation (NaN for gated-off frames).  out may be NULL
+ * for DETECT.
+ * EMBED_VERIFY: EMBED, then DETECT on each frame just written while it is still on the device (no second upload): scalars_host has
+ * 2 * n_frames entries, [i] = a, [n_frames + i] = correlation.  Returns the number of frames processed or a negative error. */
 int64_t wm_process_frames(const wm_video_ctx *v, int mode, const uint8_t *frames, uint8_t *out,
                           int64_t first_index, int64_t n_frames, float *scalars_host);
+
+/* Multi-GPU form (the gate of main.cpp:346,395 is on the GLOBAL frame index): the range [first_index, first_index + n_frames)
+ * is cut into `ngpus` contiguous chunks by wm_shard_frames; chunk g is processed by v[g] (a wm_video_ctx whose watermark lives on the device
+ * that should do the work; several contexts may share a device) on its own host thread.  chunk_frames[g] / chunk_out[g] point at the FIRST frame
+ * of chunk g (host or device memory according to v[g]->frames_on_device), so device-resident chunks need no common address space.
+ * scalars_host[i] belongs to global frame first_index + i.  No collective: only these scalars leave a GPU.  Returns frames processed. */
+void wm_shard_frames(int64_t n_frames, int rank, int world, int64_t *first, int64_t *count);
+int64_t wm_process_frames_multi(const wm_video_ctx *const *v, int ngpus, int mode, const uint8_t *const *chunk_frames,
+                                uint8_t *const *chunk_out, int64_t first_index, int64_t n_frames, float *scalars_host);
 
 /* ---- small device-memory helpers for FFI hosts without a CUDA binding (tests, ctypes) ---- */
 void *wm_dev_alloc(wm_ctx *ctx, int64_t bytes);

@@ -1,0 +1,354 @@
+"""GPU tests added in round 2: strided host views, the pipelined host batch API, batch-stride conventions, the multi-GPU video driver
+(contexts on one device stand in for several GPUs), embed + verify mode, the f32 solve option and the spread between the oracle's
+precision modes (the reference sums and solves in f32: Watermark.cpp:148-149,203)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import util
+from test_gpu_parity import _mk, report
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-buffer API on strided views: only the images' own pixels may be read or written
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", [0, 1])
+def test_host_api_strided_views_keep_padding(wmb, oracle, layout):
+    rows, cols, pad = 72, 100, 12
+    img = util.natural_image(rows, cols, seed=41)
+    rgb = np.stack([np.clip(img + d, 0, 255) for d in (-7.0, 0.0, 9.0)]).astype(np.float32)
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    L_, P_ = (cols, rows) if layout == wmb.COL_MAJOR else (rows, cols)
+    ld = P_ + pad
+    SENT = np.float32(-12345.0)
+
+    def to_mem(planes):  # (ch, rows, cols) -> strided memory (ch, L + 2 lines of plane padding, ld)
+        ch = planes.shape[0]
+        buf = np.full((ch, L_ + 2, ld), SENT, np.float32)
+        for c in range(ch):
+            buf[c, :L_, :P_] = planes[c].T if layout == wmb.COL_MAJOR else planes[c]
+        return buf
+
+    def from_mem(buf):
+        v = buf[:, :L_, :P_]
+        return np.stack([p.T if layout == wmb.COL_MAJOR else p for p in v])
+
+    gin = to_mem(img[None])
+    base = to_mem(rgb)
+    out = np.full_like(base, SENT)
+    ps = (L_ + 2) * ld
+    di = wmb.image_desc(gin.ctypes.data, rows, cols, layout, wmb.F32, ld=ld, channels=1, plane_stride=ps)
+    db = wmb.image_desc(base.ctypes.data, rows, cols, layout, wmb.F32, ld=ld, channels=3, plane_stride=ps)
+    do = wmb.image_desc(out.ctypes.data, rows, cols, layout, wmb.F32, ld=ld, channels=3, plane_stride=ps)
+    a = C.c_float(0)
+    for mask in (wmb.ME, wmb.NVF):
+        out[:] = SENT
+        rc = wmb.lib().wm_embed_host(wm._h, C.byref(di), C.byref(db), C.byref(do), mask, C.byref(a))
+        assert rc == 0
+        o = oracle.embed(img, W, 40.0, mask, base=rgb)
+        got = from_mem(out)
+        assert abs(a.value - o["a"]) / o["a"] <= 1e-3
+        assert np.abs(got - o["out"]).max() <= 1e-4 * 255
+        # every byte outside the three planes' pixels is untouched
+        chk = out.copy()
+        chk[:, :L_, :P_] = SENT
+        assert np.all(chk == SENT), "row / plane padding of the output view was overwritten"
+        # detection from a strided one-channel host view of the first plane
+        dz = wmb.image_desc(out.ctypes.data, rows, cols, layout, wmb.F32, ld=ld, channels=1, plane_stride=ps)
+        corr = C.c_float(0)
+        assert wmb.lib().wm_detect_host(wm._h, C.byref(dz), mask, C.byref(corr)) == 0
+        od = oracle.detect(o["out"][0], W, mask)
+        assert abs(corr.value - od["corr"]) / abs(od["corr"]) <= 1e-3
+    assert np.all(gin[:, L_:, :] == SENT) and np.all(gin[:, :, P_:] == SENT)
+    wm.close()
+
+
+def test_host_batch_api_pipelined(wmb, oracle):
+    rows, cols, B = 96, 128, 6
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    imgs = np.stack([util.natural_image(rows, cols, seed=500 + b) for b in range(B)])
+    outs = np.zeros_like(imgs)
+    a = np.zeros(B, np.float32)
+    corr = np.zeros(B, np.float32)
+    st = np.zeros(B, np.int32)
+    npx = rows * cols
+    # two calls of 3 frames on two slots, then detection of the watermarked HOST frames on the same slots (stream order makes the
+    # D2H copy of `outs` finish before the H2D copy that re-reads it)
+    for k, sl in ((0, 1), (1, 2)):
+        o = 3 * k
+        hin = wmb.image_desc(imgs[o].ctypes.data, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+        hout = wmb.image_desc(outs[o].ctypes.data, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+        wm.embed_host_batch(sl, hin, hin, hout, npx, npx, npx, 3, wmb.ME, a[o:o + 3], st[o:o + 3])
+        wm.detect_host_batch(sl, hout, npx, 3, wmb.ME, corr[o:o + 3])
+    wm.sync(-1)
+    for b in range(B):
+        o = oracle.embed(imgs[b], W, 40.0, wmb.ME)
+        od = oracle.detect(o["out"], W, wmb.ME)
+        assert st[b] == 0
+        assert abs(a[b] - o["a"]) / o["a"] <= 1e-3
+        assert np.abs(outs[b] - o["out"]).max() <= 1e-4 * 255
+        assert abs(corr[b] - od["corr"]) / abs(od["corr"]) <= 1e-3
+    wm.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# batch strides: 0 = dense; overlapping images and out-over-in are rejected
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tma", [1, 0])
+def test_batch_stride_zero_is_dense_and_overlaps_are_rejected(wmb, oracle, tma):
+    rows, cols, B = 64, 128, 4
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    wm.set_option(wmb.OPT_USE_TMA, tma)
+    imgs = np.stack([util.natural_image(rows, cols, seed=600 + b) for b in range(B)])
+    L = wmb.lib()
+    din = L.wm_dev_alloc(wm._h, imgs.nbytes)
+    dout = L.wm_dev_alloc(wm._h, imgs.nbytes)
+    L.wm_dev_upload(wm._h, din, imgs.ctypes.data, imgs.nbytes)
+    di = wmb.image_desc(din, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+    do = wmb.image_desc(dout, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+    npx = rows * cols
+    res = {}
+    for stride in (npx, 0):
+        a = np.zeros(B, np.float32)
+        wm.embed_batch(0, di, di, do, stride, stride, stride, B, wmb.ME, a)
+        wm.sync(0)
+        o = np.zeros_like(imgs)
+        L.wm_dev_download(wm._h, o.ctypes.data, dout, o.nbytes)
+        c = np.zeros(B, np.float32)
+        wm.detect_batch(0, do, stride, B, wmb.ME, c)
+        wm.sync(0)
+        res[stride] = (a, o, c)
+    assert np.array_equal(res[0][0], res[npx][0]) and np.array_equal(res[0][1], res[npx][1]) and np.array_equal(res[0][2], res[npx][2])
+    assert len(set(res[0][0].tolist())) == B  # four different images gave four different strengths
+    a = np.zeros(B, np.float32)
+    with pytest.raises(wmb.WatermarkError) as e:   # images of the batch would overlap
+        wm.embed_batch(0, di, di, do, npx // 2, npx // 2, npx, B, wmb.ME, a)
+    assert e.value.code == -5
+    with pytest.raises(wmb.WatermarkError):        # out inside the input range
+        do2 = wmb.image_desc(din + 4 * npx, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+        wm.embed_batch(0, di, di, do2, npx, npx, npx, 2, wmb.ME, a)
+    with pytest.raises(wmb.WatermarkError):
+        wm.detect_batch(0, di, 16, B, wmb.ME, a)
+    L.wm_dev_free(wm._h, din)
+    L.wm_dev_free(wm._h, dout)
+    wm.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-GPU video driver: contiguous chunks of the global index, one host thread per context
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("on_device", [False, True])
+@pytest.mark.parametrize("ngpus,interval", [(2, 1), (3, 2), (4, 3)])
+def test_process_frames_multi_equals_single(wmb, oracle, ngpus, interval, on_device):
+    rows, cols, ls, n, first = 96, 160, 176, 11, 5
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    clones = [wm.clone() for _ in range(ngpus)]  # one context per "device" (all on device 0 here: the chunking and threading are the same)
+    frames = np.zeros((n, rows, ls), np.uint8)
+    for i in range(n):
+        frames[i, :, :cols] = util.natural_image(rows, cols, seed=700 + i, integer=True)
+    L = wmb.lib()
+    fbytes, obytes = rows * ls, rows * cols
+    if on_device:
+        dfr = L.wm_dev_alloc(wm._h, frames.nbytes)
+        dout = L.wm_dev_alloc(wm._h, n * obytes)
+        dout2 = L.wm_dev_alloc(wm._h, n * obytes)
+        L.wm_dev_upload(wm._h, dfr, frames.ctypes.data, frames.nbytes)
+        src, dst, dst2 = dfr, dout, dout2
+    else:
+        out_h, out_h2 = np.zeros((n, rows, cols), np.uint8), np.zeros((n, rows, cols), np.uint8)
+        src, dst, dst2 = frames.ctypes.data, out_h.ctypes.data, out_h2.ctypes.data
+
+    def download(ptr, host):
+        if on_device:
+            o = np.zeros((n, rows, cols), np.uint8)
+            L.wm_dev_download(wm._h, o.ctypes.data, ptr, o.nbytes)
+            return o
+        return host.copy()
+
+    one = wmb.VideoProcessingContext(wm, rows, cols, interval, linesize=ls, frames_on_device=on_device)
+    a1 = np.zeros(n, np.float32)
+    wmb.process_frames(one, wmb.VIDEO_EMBED, src, dst, first, n, a1)
+    ref_out = download(dst, None if on_device else out_h)
+    ctxs = [wmb.VideoProcessingContext(c, rows, cols, interval, linesize=ls, frames_on_device=on_device) for c in clones]
+    firsts = [wmb.shard_frames(n, g, ngpus)[0] for g in range(ngpus)]
+    a2 = np.full(n, 7.0, np.float32)
+    got = wmb.process_frames_multi(ctxs, wmb.VIDEO_EMBED, [src + f * fbytes for f in firsts], [dst2 + f * obytes for f in firsts], first, n, a2)
+    assert got == n
+    out2 = download(dst2, None if on_device else out_h2)
+    assert np.array_equal(ref_out, out2)
+    assert np.array_equal(a1, a2, equal_nan=True)
+    gated = (first + np.arange(n)) % interval == 0
+    assert np.all(np.isnan(a2[~gated])) and not np.any(np.isnan(a2[gated]))
+    # detection over the chunks, same comparison
+    one_d = wmb.VideoProcessingContext(wm, rows, cols, interval, linesize=cols, frames_on_device=on_device)
+    c1, c2 = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    wmb.process_frames(one_d, wmb.VIDEO_DETECT, dst, None, first, n, c1)
+    ctxs_d = [wmb.VideoProcessingContext(c, rows, cols, interval, linesize=cols, frames_on_device=on_device) for c in clones]
+    wmb.process_frames_multi(ctxs_d, wmb.VIDEO_DETECT, [dst2 + f * obytes for f in firsts], None, first, n, c2)
+    assert np.array_equal(c1, c2, equal_nan=True)
+    i = int(np.flatnonzero(gated)[-1])
+    st, oo, oa = oracle.embed_frame_u8(frames[i], W, 40.0, oracle.ME, width=cols)
+    assert abs(a2[i] - oa) / oa <= 1e-3 and np.abs(out2[i].astype(int) - oo.astype(int)).max() <= 1
+    if on_device:
+        for p in (dfr, dout, dout2):
+            L.wm_dev_free(wm._h, p)
+    for c in clones:
+        c.close()
+    wm.close()
+
+
+def test_shard_frames_matches_python_split(wmb):
+    for n in (1, 7, 64, 513, 1036):
+        for world in (1, 2, 3, 4, 8):
+            nxt = 0
+            for r in range(world):
+                first, cnt = wmb.shard_frames(n, r, world)
+                base, rem = divmod(n, world)
+                assert first == r * base + min(r, rem) and cnt == base + (1 if r < rem else 0)
+                assert first == nxt
+                nxt += cnt
+            assert nxt == n
+
+
+@pytest.mark.parametrize("on_device", [False, True])
+def test_video_embed_verify_mode(wmb, oracle, on_device):
+    """EMBED_VERIFY = EMBED followed by DETECT on the written frames, without a second upload."""
+    rows, cols, ls, n, interval, first = 120, 200, 224, 9, 2, 3
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    frames = np.zeros((n, rows, ls), np.uint8)
+    for i in range(n):
+        frames[i, :, :cols] = util.natural_image(rows, cols, seed=800 + i, integer=True)
+    frames[4, :, :cols] = 93  # global index 7: gated off (interval 2)
+    frames[5, :, :cols] = 93  # global index 8: gated on, constant -> unsolvable: a stays NaN, frame copied through
+    L = wmb.lib()
+    out_a, out_b = np.zeros((n, rows, cols), np.uint8), np.zeros((n, rows, cols), np.uint8)
+    if on_device:
+        dfr = L.wm_dev_alloc(wm._h, frames.nbytes)
+        da, db = L.wm_dev_alloc(wm._h, out_a.nbytes), L.wm_dev_alloc(wm._h, out_b.nbytes)
+        L.wm_dev_upload(wm._h, dfr, frames.ctypes.data, frames.nbytes)
+        src, pa, pb = dfr, da, db
+    else:
+        src, pa, pb = frames.ctypes.data, out_a.ctypes.data, out_b.ctypes.data
+    ctx = wmb.VideoProcessingContext(wm, rows, cols, interval, linesize=ls, frames_on_device=on_device)
+    ctx_d = wmb.VideoProcessingContext(wm, rows, cols, interval, linesize=cols, frames_on_device=on_device)
+    a1, c1 = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    wmb.process_frames(ctx, wmb.VIDEO_EMBED, src, pa, first, n, a1)
+    wmb.process_frames(ctx_d, wmb.VIDEO_DETECT, pa, None, first, n, c1)
+    both = np.zeros(2 * n, np.float32)
+    wmb.process_frames(ctx, wmb.VIDEO_EMBED_VERIFY, src, pb, first, n, both)
+    if on_device:
+        L.wm_dev_download(wm._h, out_a.ctypes.data, da, out_a.nbytes)
+        L.wm_dev_download(wm._h, out_b.ctypes.data, db, out_b.nbytes)
+    assert np.array_equal(out_a, out_b)
+    assert np.array_equal(a1, both[:n], equal_nan=True) and np.array_equal(c1, both[n:], equal_nan=True)
+    assert np.isnan(a1[5]) and np.array_equal(out_a[5], frames[5, :, :cols]) and c1[5] == 0.0   # unsolvable frame (Watermark.cpp:164-165,246-247)
+    assert np.isnan(a1[4]) and np.isnan(c1[4])                                                    # gated off
+    assert not np.isnan(a1[1]) and not np.isnan(c1[1])
+    if on_device:
+        for p in (dfr, da, db):
+            L.wm_dev_free(wm._h, p)
+    wm.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# precision modes: the reference reduces and solves in f32 (ArrayFire); ours in f64.  Measure and bound the spread.
+# ---------------------------------------------------------------------------------------------------
+def test_f32_solve_option_matches_f32_lu(wmb, oracle):
+    img = util.load_512_gray(oracle)
+    W = util.load_w512()
+    wm = _mk(wmb, 512, 512, W)
+    d = wmb.DeviceArray.from_numpy(wm, img, wmb.COL_MAJOR)
+    wm.detectWatermark(d, wmb.ME)
+    c64 = wm.debug(wmb.DBG_COEFFS).copy()
+    Rx, rx = wm.debug(wmb.DBG_RX), wm.debug(wmb.DBG_RXVEC)
+    wm.set_option(wmb.OPT_F32_SOLVE, 1)
+    wm.detectWatermark(d, wmb.ME)
+    c32 = wm.debug(wmb.DBG_COEFFS).copy()
+    st, o32 = oracle.solve8(Rx, rx, f32=True)
+    st, o64 = oracle.solve8(Rx, rx, f32=False)
+    report("f32-solve option: |c32 - oracle f32 LU| = %.3g, |c32 - c64| = %.3g (rel to max|c|)" % (
+        util.rel(c32, o32), util.rel(c32, c64)))
+    assert np.array_equal(c64, o64.astype(np.float32))
+    assert util.rel(c32, o32) <= 2e-6          # same algorithm in f32; the host LU may contract mul-sub into fma
+    assert 0 < util.rel(c32, c64) <= 5e-3      # the f32 LU of this cond ~1e4 system moves the coefficients visibly
+    wm.close()
+
+
+@pytest.mark.parametrize("name", ["512", "1080p"])
+def test_gpu_lies_inside_the_spread_of_the_precision_modes(wmb, oracle, name):
+    """run the oracle as the reference would (f32 sums + f32 LU, STRICT_F32), canonically (f64) and without the fp16
+    rounding (EXACT); print how far those differ from each other and how far the GPU is from the canonical mode.  The GPU must be
+    much closer to the canonical mode than the modes are to each other — i.e. it sits inside the reference's own noise."""
+    if name == "512":
+        img, W = util.load_512_gray(oracle), util.load_w512()
+    else:
+        img, W = util.natural_image(1080, 1920, seed=5), util.normal_w(1080, 1920, seed=28390211)
+    rows, cols = img.shape
+    wm = _mk(wmb, rows, cols, W)
+    d = wmb.DeviceArray.from_numpy(wm, img, wmb.COL_MAJOR)
+    for mask in (wmb.ME, wmb.NVF):
+        out, a, st = wm.makeWatermark(d, d, mask)
+        coef = wm.debug(wmb.DBG_COEFFS).copy()
+        got = out.numpy()
+        corr, st2 = wm.detectWatermark(out, mask)
+        modes = {"canonical": oracle.FAITHFUL, "strict_f32": oracle.STRICT_F32, "exact": oracle.EXACT}
+        ref = {}
+        for k, o in modes.items():
+            e = oracle.embed(img, W, 40.0, mask, o=o)
+            dd = oracle.detect(e["out"], W, mask, o=o)
+            ref[k] = dict(a=e["a"], corr=dd["corr"], out=e["out"], coef=e["coef"], mask=e["mask"])
+        can = ref["canonical"]
+        gpu_dev = dict(a=abs(a - can["a"]) / abs(can["a"]), corr=abs(corr - can["corr"]) / abs(can["corr"]),
+                       out=float(np.abs(got - can["out"]).max()) / 255.0,
+                       coef=util.rel(coef, can["coef"]) if mask == wmb.ME else 0.0)
+        for k in ("strict_f32", "exact"):
+            r = ref[k]
+            spread = dict(a=abs(r["a"] - can["a"]) / abs(can["a"]), corr=abs(r["corr"] - can["corr"]) / abs(can["corr"]),
+                          out=float(np.abs(r["out"] - can["out"]).max()) / 255.0,
+                          coef=util.rel(r["coef"], can["coef"]) if mask == wmb.ME else 0.0, mask=util.rel(r["mask"], can["mask"]))
+            report("spread %s mask=%d %-10s vs canonical: a %.3g corr %.3g pixels/255 %.3g coef %.3g mask %.3g | GPU vs canonical: a %.3g corr %.3g pixels/255 %.3g coef %.3g" % (
+                name, mask, k, spread["a"], spread["corr"], spread["out"], spread["coef"], spread["mask"],
+                gpu_dev["a"], gpu_dev["corr"], gpu_dev["out"], gpu_dev["coef"]))
+            for q in ("a", "corr", "out", "coef"):
+                assert gpu_dev[q] <= max(spread[q], 2e-6), (q, gpu_dev[q], spread[q])
+        assert gpu_dev["a"] <= 1e-3 and gpu_dev["corr"] <= 1e-3 and gpu_dev["out"] <= 1e-4
+    wm.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the detector's three sums one by one, and NVF detection where every pixel touches the nested clamp
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("rows,cols", [(3, 3), (4, 5), (5, 7), (8, 300), (300, 8), (33, 129), (64, 64), (130, 260)])
+def test_detector_sums_individually(wmb, oracle, rows, cols, layout):
+    img = util.natural_image(rows, cols, seed=900 + rows + cols)
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    d = wmb.DeviceArray.from_numpy(wm, img, layout)
+    for mask in (wmb.ME, wmb.NVF):
+        od = oracle.detect(img, W, mask)
+        if od["status"] != 0:
+            continue
+        wm.debug_set_coeffs(od["coef"])  # same coefficients on both sides: the sums are compared, not the solve
+        corr, st = wm.detectWatermark(d, mask)
+        s = wm.debug(wmb.DBG_SCALARS)
+        ez, eu, u = od["ez"].astype(np.float64), od["eu"].astype(np.float64), od["u"].astype(np.float64)
+        # the kernel drops the 1 / max|e| scale of the ME mask (it cancels in the correlation): rescale its sums to compare
+        k = float(np.abs(od["ez"]).max()) if mask == wmb.ME else 1.0
+        want = dict(dot=float((eu * ez).sum()), nz=float((ez * ez).sum()), nu=float((eu * eu).sum()))
+        got = dict(dot=s[4] / k, nz=s[5], nu=s[6] / (k * k))
+        for q in want:
+            rel = abs(got[q] - want[q]) / max(abs(want[q]), 1e-30)
+            report("detect sums %dx%d layout=%d mask=%d %s rel=%.3g" % (rows, cols, layout, mask, q, rel))
+            assert rel <= 2e-5, (q, got[q], want[q])
+        assert abs(corr - od["corr"]) / max(abs(od["corr"]), 1e-30) <= 1e-4
+        wm.debug_set_coeffs(None)
+    wm.close()

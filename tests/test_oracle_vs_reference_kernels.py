@@ -2,6 +2,8 @@
 (oracle/clshim -> oracle/_ref/libref_kernels_*.so, built from /root/reference/Watermark_GPU/kernels/*.hpp).
 The reference ships no golden vectors, so this is the pin for the three OpenCL kernels; the
 ArrayFire calls between them stay a restatement of documented semantics."""
+import os
+
 import numpy as np
 import pytest
 
@@ -14,7 +16,11 @@ SHAPES = [(64, 64), (48, 80), (67, 131), (130, 70), (512, 512)]
 def ref():
     from oracle import ref_kernels
     if not ref_kernels.available():
-        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+        # the only external pin of the three kernels must not disappear silently: oracle/_ref is built by `make -C oracle` where
+        # /root/reference exists and travels (prebuilt) to boxes without it
+        if os.environ.get("WM_ALLOW_MISSING_REF") == "1":
+            pytest.skip("oracle/_ref not built and WM_ALLOW_MISSING_REF=1")
+        pytest.fail("oracle/_ref is missing: run `make -C oracle` where /root/reference is present (or set WM_ALLOW_MISSING_REF=1 to skip the pin)")
     return ref_kernels
 
 

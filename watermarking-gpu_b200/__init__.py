@@ -22,15 +22,17 @@ COL_MAJOR, ROW_MAJOR = 0, 1
 F32, U8 = 0, 1
 OK, SINGULAR, ZERO_MASK = 0, 1, 2
 OPT_FP16_PRODUCTS, OPT_KERNEL_TIMING, OPT_USE_TMA, OPT_SERIAL_SLOTS, OPT_CUDA_GRAPHS, OPT_MMA_ACCUM, OPT_SPLIT_COST = 1, 2, 3, 4, 5, 6, 7
+OPT_F32_SOLVE, OPT_HOST_RUN_FRAMES = 8, 9
 DBG_RX, DBG_RXVEC, DBG_COEFFS, DBG_SCALARS, DBG_ERRSEQ, DBG_MASK_NVF, DBG_PHASES = range(7)
-KERNEL_NAMES = ["rx_sweep", "me_stats", "nvf_stats", "embed_apply", "detect_apply"]
-VIDEO_EMBED, VIDEO_DETECT = 0, 1
+KERNEL_NAMES = ["rx_sweep", "me_stats", "nvf_stats", "me_apply", "me_detect", "nvf_apply", "nvf_detect"]
+VIDEO_EMBED, VIDEO_DETECT, VIDEO_EMBED_VERIFY = 0, 1, 2
 
 # every symbol include/wm_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "wm_create", "wm_create_from_file", "wm_clone", "wm_reinitialize", "wm_reinitialize_from_file", "wm_destroy",
     "wm_set_option", "wm_last_error", "wm_strength_factor", "wm_embed", "wm_detect", "wm_num_slots", "wm_get_stream",
-    "wm_embed_batch", "wm_detect_batch", "wm_sync", "wm_embed_host", "wm_detect_host", "wm_rgb2gray", "wm_debug_get",
+    "wm_embed_batch", "wm_detect_batch", "wm_sync", "wm_embed_host", "wm_detect_host", "wm_embed_host_batch",
+    "wm_detect_host_batch", "wm_shard_frames", "wm_process_frames_multi", "wm_rgb2gray", "wm_debug_get",
     "wm_debug_set_coeffs", "wm_debug_plane", "wm_get_kernel_times", "wm_launch_count", "wm_process_frames",
     "wm_dev_alloc", "wm_dev_free", "wm_dev_upload", "wm_dev_download", "wm_host_alloc_pinned",
     "wm_host_free_pinned", "wm_device_count", "wm_version",
@@ -98,6 +100,12 @@ def lib():
     L.wm_sync.argtypes = [vp, i32]
     L.wm_embed_host.argtypes = [vp, imp, imp, imp, i32, fp]
     L.wm_detect_host.argtypes = [vp, imp, i32, fp]
+    L.wm_embed_host_batch.argtypes = [vp, i32, imp, imp, imp, i64, i64, i64, i32, i32, fp, ip]
+    L.wm_detect_host_batch.argtypes = [vp, i32, imp, i64, i32, i32, fp, ip]
+    L.wm_shard_frames.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.wm_shard_frames.restype = None
+    L.wm_process_frames_multi.argtypes = [C.POINTER(C.POINTER(wm_video_ctx)), i32, i32, C.POINTER(vp), C.POINTER(vp), i64, i64, fp]
+    L.wm_process_frames_multi.restype = i64
     L.wm_rgb2gray.argtypes = [vp, imp, imp, C.c_float, C.c_float, C.c_float]
     L.wm_debug_get.argtypes = [vp, i32, vp]
     L.wm_debug_set_coeffs.argtypes = [vp, fp]
@@ -321,6 +329,20 @@ class Watermark:
         rc = self._check(lib().wm_detect_host(self._h, C.byref(d), mask_type, C.byref(corr)))
         return corr.value, rc
 
+    def embed_host_batch(self, slot, in_desc, base_desc, out_desc, in_stride, base_stride, out_stride, batch, mask_type,
+                         a_out, status_out=None):
+        """Pipelined host-buffer form (descs over HOST pointers); results and output images are valid after sync(slot)."""
+        self._check(lib().wm_embed_host_batch(
+            self._h, slot, C.byref(in_desc), C.byref(base_desc), C.byref(out_desc), in_stride, base_stride, out_stride,
+            batch, mask_type, a_out.ctypes.data_as(C.POINTER(C.c_float)),
+            status_out.ctypes.data_as(C.POINTER(C.c_int)) if status_out is not None else None))
+
+    def detect_host_batch(self, slot, img_desc, img_stride, batch, mask_type, corr_out, status_out=None):
+        self._check(lib().wm_detect_host_batch(
+            self._h, slot, C.byref(img_desc), img_stride, batch, mask_type,
+            corr_out.ctypes.data_as(C.POINTER(C.c_float)),
+            status_out.ctypes.data_as(C.POINTER(C.c_int)) if status_out is not None else None))
+
     # -- batched / pipelined ----------------------------------------------------------------------
     def embed_batch(self, slot, in_desc, base_desc, out_desc, in_stride, base_stride, out_stride, batch, mask_type,
                     a_out, status_out=None):
@@ -406,7 +428,23 @@ def process_frames(ctx, mode, frames_ptr, out_ptr, first_index, n_frames, scalar
 
 
 def shard_frames(n_frames, rank, world):
-    """Contiguous chunk of the global frame index owned by `rank`: [first, first+count)."""
-    base, rem = divmod(n_frames, world)
-    first = rank * base + min(rank, rem)
-    return first, base + (1 if rank < rem else 0)
+    """Contiguous chunk of the global frame index owned by `rank`: [first, first+count) — the library's own
+    split (wm_shard_frames), so that every host language cuts the index range the same way."""
+    first, count = C.c_int64(0), C.c_int64(0)
+    lib().wm_shard_frames(n_frames, rank, world, C.byref(first), C.byref(count))
+    return int(first.value), int(count.value)
+
+
+def process_frames_multi(ctxs, mode, chunk_frames, chunk_out, first_index, n_frames, scalars):
+    """wm_process_frames_multi: ctxs[g] (VideoProcessingContext, one per device / host thread) handles the g-th contiguous chunk of
+    [first_index, first_index + n_frames); chunk_frames[g] / chunk_out[g] are raw pointers to the first frame of chunk g."""
+    n = len(ctxs)
+    arr = (C.POINTER(wm_video_ctx) * n)(*[C.pointer(c._c) for c in ctxs])
+    fr = (C.c_void_p * n)(*[C.c_void_p(p) for p in chunk_frames])
+    ou = (C.c_void_p * n)(*[C.c_void_p(p) for p in chunk_out]) if chunk_out is not None else None
+    r = lib().wm_process_frames_multi(arr, n, mode, fr, ou, first_index, n_frames,
+                                      scalars.ctypes.data_as(C.POINTER(C.c_float)) if scalars is not None else None)
+    if r < 0:
+        msgs = [lib().wm_last_error(c.watermarkObj._h).decode() for c in ctxs]
+        raise WatermarkError(int(r), "; ".join(m for m in msgs if m))
+    return int(r)

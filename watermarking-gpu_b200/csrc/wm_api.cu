@@ -13,6 +13,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace wm;
@@ -70,7 +71,8 @@ struct wm_ctx {
     float psnr = 0.f, strength = 0.f;
     std::shared_ptr<WShared> w;
     Slot slots[NSLOTS];
-    int opt_fp16 = 1, opt_timing = 0, opt_tma = 1, opt_serial = 0, opt_mma = 1;
+    int opt_fp16 = 1, opt_timing = 0, opt_tma = 1, opt_serial = 0, opt_mma = 1, opt_f32_solve = 0;
+    int opt_host_run = 4;    // frames per run of the video driver's host-frame path (WM_OPT_HOST_RUN_FRAMES)
     int opt_split_cost = 8;  // tile-times one more launch is assumed to cost when a batch is partitioned (WM_OPT_SPLIT_COST)
     bool inject_coef = false;
     float injected[8];
@@ -132,6 +134,26 @@ bool vec_ok(const void* p, long long ld, long long bstride, long long pstride, i
     return ((uintptr_t)p % al == 0) && (ld % 4 == 0) && (bstride % 4 == 0) && (pstride % 4 == 0);
 }
 
+
+// batch stride conventions (include/wm_b200.h): 0 means dense (plane_stride * channels, i.e. L * ld * channels for dense planes); a stride
+// smaller than one image would make the images of a batch overlap.  Resolved once, so the tensor maps, the plain loaders and the
+// apply kernel's base / out addressing all see the same number.
+int resolve_stride(wm_ctx* ctx, const View& v, int batch, int64_t* stride, const char* what)
+{
+    const long long one = v.pstride * (v.channels - 1) + (long long)v.L * v.ld;  // elements spanned by one image
+    if (*stride == 0) *stride = v.pstride * v.channels;
+    if (batch > 1 && *stride < one) return fail(ctx, WM_ERR_ARG, std::string(what) + " batch stride smaller than one image");
+    return WM_OK;
+}
+// [first, last) bytes touched by a batch
+void byte_range(const View& v, int64_t stride, int batch, uintptr_t* lo, uintptr_t* hi)
+{
+    const long long es = v.dtype == WM_F32 ? 4 : 1;
+    const long long last = (long long)(batch - 1) * stride + v.pstride * (v.channels - 1) + (long long)(v.L - 1) * v.ld + v.P;
+    *lo = (uintptr_t)v.ptr;
+    *hi = (uintptr_t)v.ptr + (uintptr_t)(last * es);
+}
+
 int finish_slot(wm_ctx* ctx, Slot& s);
 void clear_graphs(wm_ctx* ctx)
 {
@@ -159,7 +181,7 @@ int ensure_slot(wm_ctx* ctx, Slot& s, int batch, int gx_max, int nsweep, int nfr
         CU(cudaMemsetAsync(s.scal, 0, sizeof(Scal) * batch, s.stream));
         CU(cudaMalloc(&s.dbg, sizeof(ScalDbg) * batch));
         CU(cudaMemsetAsync(s.dbg, 0, sizeof(ScalDbg) * batch, s.stream));
-        s.host_cap = (size_t)std::max(batch * 4, 64);
+        s.host_cap = (size_t)std::max(batch * 16, 256);  // 16 ops of this batch size may be queued before a delivery is forced
         s.host_used = 0;
         CU(cudaMallocHost(&s.scal_host, sizeof(Scal) * s.host_cap));
         s.batch_cap = batch;
@@ -391,6 +413,7 @@ int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int ba
     a.nsweep = pl.nsweep; a.nframe = pl.nframe;
     a.vec_ok = vec_ok(v.ptr, v.ld, bstride, 0, v.dtype);
     a.transposed = v.transposed;
+    a.solve_f32 = ctx->opt_f32_solve;
     a.part = s.part;
     a.counter = s.counters;
     a.scal = s.scal; a.dbg = s.dbg;
@@ -452,7 +475,15 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     if (vb.transposed != vi.transposed || vo.transposed != vi.transposed) return fail(ctx, WM_ERR_ARG, "in/base/out layouts differ");
     if (vb.dtype != vi.dtype) return fail(ctx, WM_ERR_ARG, "base dtype must equal input dtype");
     if (vo.channels != vb.channels) return fail(ctx, WM_ERR_ARG, "out channels != base channels");
-    if (vo.ptr == vi.ptr) return fail(ctx, WM_ERR_ARG, "out must not alias the gray input (neighbour reads race with stores)");
+    if ((rc = resolve_stride(ctx, vi, batch, &in_stride, "in"))) return rc;
+    if ((rc = resolve_stride(ctx, vb, batch, &base_stride, "base"))) return rc;
+    if ((rc = resolve_stride(ctx, vo, batch, &out_stride, "out"))) return rc;
+    {
+        uintptr_t ilo, ihi, olo, ohi;
+        byte_range(vi, in_stride, batch, &ilo, &ihi);
+        byte_range(vo, out_stride, batch, &olo, &ohi);
+        if (olo < ihi && ilo < ohi) return fail(ctx, WM_ERR_ARG, "out must not overlap the gray input (neighbour reads race with stores)");
+    }
     CU(cudaSetDevice(ctx->device));
     Slot& s = ctx->slots[slot];
     const Geo g = geo(vi.L, vi.P);
@@ -503,7 +534,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     }
     CU(cudaGetLastError());
     {
-        KTimer t(ctx, s, WM_K_APPLY);
+        KTimer t(ctx, s, mask == WM_MASK_ME ? WM_K_APPLY : WM_K_APPLY_NVF);
         for (const SubBatch& sb : pl.embed) {
             ea.b0 = sb.b0; ea.nblk_base = sb.base; ea.nblk_extra = sb.extra;
             launch_apply(vi.dtype, vo.dtype, kmask, vi.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmI, tmW, ea);
@@ -522,6 +553,7 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     View v;
     int rc;
     if ((rc = make_view(ctx, img, &v, false))) return rc;
+    if ((rc = resolve_stride(ctx, v, batch, &img_stride, "image"))) return rc;
     CU(cudaSetDevice(ctx->device));
     Slot& s = ctx->slots[slot];
     const Geo g = geo(v.L, v.P);
@@ -549,7 +581,7 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     if (tma) tma = make_tmap(&tmZ, v.dtype, v.ptr, g.P, g.L, batch, v.ld, img_stride, SW, TL + 4) &&
                    make_tmap(&tmW, WM_F32, W, g.P, g.L, 1, g.P, 0, SW, TL + 2);
     {
-        KTimer t(ctx, s, WM_K_DETECT);
+        KTimer t(ctx, s, mask == WM_MASK_ME ? WM_K_DETECT : WM_K_DETECT_NVF);
         if (planes) {
             if ((rc = enqueue_nvf_planes(ctx, s, v, img_stride, batch, g))) return rc;
             da.maskp = (const float*)s.maskp;
@@ -669,7 +701,7 @@ int create_common(wm_ctx** out, int64_t rows, int64_t cols, int p, float psnr, i
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sms = prop.multiProcessorCount;
     const int rc = init_slots(ctx, stream);
-    if (rc) { g_create_error = ctx->err; delete ctx; return rc; }
+    if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
     *made = ctx;
     (void)rows; (void)cols;
     return WM_OK;
@@ -764,7 +796,7 @@ int wm_create(wm_ctx** out, int64_t rows, int64_t cols, const float* w_host, int
     wm_ctx* ctx = nullptr;
     int rc = create_common(out, rows, cols, p, psnr, device, stream, &ctx);
     if (rc) return rc;
-    if (!w_host) { delete ctx; return fail(nullptr, WM_ERR_ARG, "null W"); }
+    if (!w_host) { wm_destroy(ctx); return fail(nullptr, WM_ERR_ARG, "null W"); }
     rc = upload_w(ctx, rows, cols, w_host);
     if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
     *out = ctx;
@@ -793,6 +825,7 @@ int wm_clone(const wm_ctx* src, wm_ctx** out)
     ctx->p = src->p; ctx->psnr = src->psnr; ctx->strength = src->strength;
     ctx->w = src->w;
     ctx->opt_fp16 = src->opt_fp16; ctx->opt_mma = src->opt_mma; ctx->opt_split_cost = src->opt_split_cost; ctx->opt_timing = src->opt_timing; ctx->opt_tma = src->opt_tma;
+    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run;
     const int rc = init_slots(ctx, nullptr);
     if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
     *out = ctx;
@@ -840,6 +873,8 @@ int wm_set_option(wm_ctx* ctx, int option, int value)
     case WM_OPT_SERIAL_SLOTS: ctx->opt_serial = value != 0; return WM_OK;
     case WM_OPT_CUDA_GRAPHS: ctx->opt_graphs = value != 0; return WM_OK;
     case WM_OPT_MMA_ACCUM: ctx->opt_mma = value != 0; return WM_OK;
+    case WM_OPT_HOST_RUN_FRAMES: ctx->opt_host_run = std::max(1, std::min(value, 64)); return WM_OK;
+    case WM_OPT_F32_SOLVE: ctx->opt_f32_solve = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_SPLIT_COST: ctx->opt_split_cost = value < 0 ? 1 << 28 : value; return WM_OK;
     default: return fail(ctx, WM_ERR_ARG, "unknown option");
     }
@@ -889,7 +924,7 @@ int wm_detect_batch(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stri
 int wm_embed(wm_ctx* ctx, const wm_image* in, const wm_image* base, wm_image* out, int mask, float* a_host)
 {
     if (!ctx) return WM_ERR_ARG;
-    const std::string key = "E" + std::to_string(mask) + image_key(in) + image_key(base) + image_key(out) + std::to_string(ctx->opt_fp16 + 2 * ctx->opt_mma) +
+    const std::string key = "E" + std::to_string(mask) + image_key(in) + image_key(base) + image_key(out) + std::to_string(ctx->opt_fp16 + 2 * ctx->opt_mma + 4 * ctx->opt_f32_solve) +
                             std::to_string(ctx->opt_tma);
     return run_sync(ctx, key, 1, a_host, [&]() { return do_embed(ctx, 0, in, base, out, 0, 0, 0, 1, mask); });
 }
@@ -897,64 +932,139 @@ int wm_embed(wm_ctx* ctx, const wm_image* in, const wm_image* base, wm_image* ou
 int wm_detect(wm_ctx* ctx, const wm_image* img, int mask, float* corr_host)
 {
     if (!ctx) return WM_ERR_ARG;
-    const std::string key = "D" + std::to_string(mask) + image_key(img) + std::to_string(ctx->opt_fp16 + 2 * ctx->opt_mma) + std::to_string(ctx->opt_tma);
+    const std::string key = "D" + std::to_string(mask) + image_key(img) + std::to_string(ctx->opt_fp16 + 2 * ctx->opt_mma + 4 * ctx->opt_f32_solve) + std::to_string(ctx->opt_tma);
     return run_sync(ctx, key, 2, corr_host, [&]() { return do_detect(ctx, 0, img, 0, 1, mask); });
 }
 
-static size_t image_bytes(const wm_image* im, int64_t* elems_per_plane)
+// ---- host-buffer form.  Host images may be strided views (ld > contiguous dimension, padded planes): every plane is staged
+// DENSELY on the device with one 2-D copy (width = the contiguous dimension, source pitch = ld), exactly the repack the reference does
+// row by row (main.cpp:348-353), and results are copied back the same way, so neither copy touches a byte outside the image's
+// pixels — the caller's row and plane padding stays as it was.
+struct HostGeo { int64_t L, P, ld, ps; int ch; size_t es; };
+static int host_geo(wm_ctx* ctx, const wm_image* im, HostGeo* g)
 {
+    if (!im || !im->data) return fail(ctx, WM_ERR_ARG, "null image");
+    if (im->layout != WM_COL_MAJOR && im->layout != WM_ROW_MAJOR) return fail(ctx, WM_ERR_ARG, "bad layout");
+    if (im->dtype != WM_F32 && im->dtype != WM_U8) return fail(ctx, WM_ERR_ARG, "bad dtype");
     const bool tr = im->layout == WM_COL_MAJOR;
-    const int64_t L = tr ? im->cols : im->rows, P = tr ? im->rows : im->cols;
-    const int64_t ld = im->ld > 0 ? im->ld : P;
-    const int ch = im->channels <= 0 ? 1 : im->channels;
-    const int64_t ps = im->plane_stride > 0 ? im->plane_stride : L * ld;
-    if (elems_per_plane) *elems_per_plane = ps;
-    return (size_t)(ps * (ch - 1) + L * ld) * (im->dtype == WM_F32 ? 4 : 1);
+    g->L = tr ? im->cols : im->rows; g->P = tr ? im->rows : im->cols;
+    g->ld = im->ld > 0 ? im->ld : g->P;
+    if (g->L < 1 || g->P < 1 || g->ld < g->P) return fail(ctx, WM_ERR_ARG, "ld smaller than the contiguous dimension");
+    g->ch = im->channels <= 0 ? 1 : im->channels;
+    g->ps = im->plane_stride > 0 ? im->plane_stride : g->L * g->ld;
+    g->es = im->dtype == WM_F32 ? 4 : 1;
+    return WM_OK;
+}
+static size_t dense_bytes(const HostGeo& g) { return (size_t)(g.L * g.P * g.ch) * g.es; }
+// dense device planes <-> strided host planes
+static cudaError_t copy_planes(void* dev, void* host, const HostGeo& g, bool to_device, cudaStream_t st)
+{
+    for (int c = 0; c < g.ch; c++) {
+        char* d = (char*)dev + (size_t)c * (size_t)(g.L * g.P) * g.es;
+        char* h = (char*)host + (size_t)c * (size_t)g.ps * g.es;
+        const cudaError_t e = to_device ? cudaMemcpy2DAsync(d, (size_t)g.P * g.es, h, (size_t)g.ld * g.es, (size_t)g.P * g.es, (size_t)g.L, cudaMemcpyHostToDevice, st)
+                                        : cudaMemcpy2DAsync(h, (size_t)g.ld * g.es, d, (size_t)g.P * g.es, (size_t)g.P * g.es, (size_t)g.L, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+static wm_image dense_desc(const wm_image* im, void* dev)
+{
+    wm_image d = *im;
+    d.data = dev; d.ld = 0; d.plane_stride = 0;
+    return d;
+}
+
+// staging of a batch: image b of a strided host batch <-> image b of a dense device batch
+static cudaError_t copy_batch(void* dev, void* host, const HostGeo& g, int64_t host_stride, int batch, bool to_device, cudaStream_t st)
+{
+    const int64_t hs = host_stride > 0 ? host_stride : g.ps * g.ch;
+    for (int b = 0; b < batch; b++) {
+        const cudaError_t e = copy_planes((char*)dev + (size_t)b * dense_bytes(g), (char*)host + (size_t)b * (size_t)hs * g.es, g, to_device, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+// a slot's staging buffer may only be replaced when nothing queued on the slot still uses it
+static int grow_stage(wm_ctx* ctx, Slot& s, void** p, size_t* cap, size_t bytes)
+{
+    if (bytes <= *cap) return WM_OK;
+    if (!s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+    CU(cudaStreamSynchronize(s.stream));
+    return ensure_stage(ctx, p, cap, bytes);
+}
+
+int wm_embed_host_batch(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm_image* out, int64_t in_stride, int64_t base_stride,
+                        int64_t out_stride, int batch, int mask, float* a_host, int* status_host)
+{
+    if (!ctx || !in || !out || !in->data || !out->data) return WM_ERR_ARG;
+    if (slot < 0 || slot >= NSLOTS) return fail(ctx, WM_ERR_ARG, "bad slot");
+    if (batch < 1 || batch > 65535) return fail(ctx, WM_ERR_ARG, "batch must be 1..65535");
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slots[slot];
+    const wm_image* b = base ? base : in;
+    HostGeo gi, gb, go;
+    int rc;
+    if ((rc = host_geo(ctx, in, &gi)) || (rc = host_geo(ctx, b, &gb)) || (rc = host_geo(ctx, out, &go))) return rc;
+    if (gi.ch != 1) return fail(ctx, WM_ERR_ARG, "the gray input has one channel");
+    if ((rc = grow_stage(ctx, s, &s.stage_in, &s.stage_in_cap, dense_bytes(gi) * batch))) return rc;
+    if ((rc = grow_stage(ctx, s, &s.stage_out, &s.stage_out_cap, dense_bytes(go) * batch))) return rc;
+    const bool base_is_in = b->data == in->data && gb.ch == 1 && gb.ld == gi.ld && b->dtype == in->dtype && b->layout == in->layout &&
+                            (batch == 1 || base_stride == in_stride);
+    if (!base_is_in && (rc = grow_stage(ctx, s, &s.stage_base, &s.stage_base_cap, dense_bytes(gb) * batch))) return rc;
+    CU(copy_batch(s.stage_in, in->data, gi, in_stride, batch, true, s.stream));
+    wm_image din = dense_desc(in, s.stage_in), dbase, dout = dense_desc(out, s.stage_out);
+    if (base_is_in) dbase = din;
+    else {
+        CU(copy_batch(s.stage_base, b->data, gb, base_stride, batch, true, s.stream));
+        dbase = dense_desc(b, s.stage_base);
+    }
+    rc = do_embed(ctx, slot, &din, &dbase, &dout, 0, 0, 0, batch, mask);
+    if (rc) return rc;
+    s.queue.back().scalar = a_host;
+    s.queue.back().status = status_host;
+    CU(copy_batch(s.stage_out, out->data, go, out_stride, batch, false, s.stream));
+    return WM_OK;
+}
+
+int wm_detect_host_batch(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, int batch, int mask, float* corr_host, int* status_host)
+{
+    if (!ctx || !img || !img->data) return WM_ERR_ARG;
+    if (slot < 0 || slot >= NSLOTS) return fail(ctx, WM_ERR_ARG, "bad slot");
+    if (batch < 1 || batch > 65535) return fail(ctx, WM_ERR_ARG, "batch must be 1..65535");
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slots[slot];
+    HostGeo g;
+    int rc;
+    if ((rc = host_geo(ctx, img, &g))) return rc;
+    if (g.ch != 1) return fail(ctx, WM_ERR_ARG, "detect takes a one-channel image");
+    if ((rc = grow_stage(ctx, s, &s.stage_in, &s.stage_in_cap, dense_bytes(g) * batch))) return rc;
+    CU(copy_batch(s.stage_in, img->data, g, img_stride, batch, true, s.stream));
+    wm_image d = dense_desc(img, s.stage_in);
+    rc = do_detect(ctx, slot, &d, 0, batch, mask);
+    if (rc) return rc;
+    s.queue.back().scalar = corr_host;
+    s.queue.back().status = status_host;
+    return WM_OK;
 }
 
 int wm_embed_host(wm_ctx* ctx, const wm_image* in, const wm_image* base, wm_image* out, int mask, float* a_host)
 {
-    if (!ctx || !in || !out || !in->data || !out->data) return WM_ERR_ARG;
-    CU(cudaSetDevice(ctx->device));
+    if (!ctx) return WM_ERR_ARG;
     Slot& s = ctx->slots[0];
     if (!s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
-    const wm_image* b = base ? base : in;
-    const size_t nin = image_bytes(in, nullptr), nb = image_bytes(b, nullptr), nout = image_bytes(out, nullptr);
-    int rc;
-    if ((rc = ensure_stage(ctx, &s.stage_in, &s.stage_in_cap, nin))) return rc;
-    if ((rc = ensure_stage(ctx, &s.stage_out, &s.stage_out_cap, nout))) return rc;
-    CU(cudaMemcpyAsync(s.stage_in, in->data, nin, cudaMemcpyHostToDevice, s.stream));
-    wm_image din = *in, dbase = *b, dout = *out;
-    din.data = s.stage_in;
-    if (b->data == in->data) dbase.data = s.stage_in;
-    else {
-        if ((rc = ensure_stage(ctx, &s.stage_base, &s.stage_base_cap, nb))) return rc;
-        CU(cudaMemcpyAsync(s.stage_base, b->data, nb, cudaMemcpyHostToDevice, s.stream));
-        dbase.data = s.stage_base;
-    }
-    dout.data = s.stage_out;
-    rc = do_embed(ctx, 0, &din, &dbase, &dout, 0, 0, 0, 1, mask);
+    const int rc = wm_embed_host_batch(ctx, 0, in, base, out, 0, 0, 0, 1, mask, a_host, nullptr);
     if (rc) return rc;
-    s.queue.back().scalar = a_host;
-    CU(cudaMemcpyAsync(out->data, s.stage_out, nout, cudaMemcpyDeviceToHost, s.stream));
     return finish_slot(ctx, s);
 }
 
 int wm_detect_host(wm_ctx* ctx, const wm_image* img, int mask, float* corr_host)
 {
-    if (!ctx || !img || !img->data) return WM_ERR_ARG;
-    CU(cudaSetDevice(ctx->device));
+    if (!ctx) return WM_ERR_ARG;
     Slot& s = ctx->slots[0];
     if (!s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
-    const size_t n = image_bytes(img, nullptr);
-    int rc;
-    if ((rc = ensure_stage(ctx, &s.stage_in, &s.stage_in_cap, n))) return rc;
-    CU(cudaMemcpyAsync(s.stage_in, img->data, n, cudaMemcpyHostToDevice, s.stream));
-    wm_image d = *img;
-    d.data = s.stage_in;
-    rc = do_detect(ctx, 0, &d, 0, 1, mask);
+    const int rc = wm_detect_host_batch(ctx, 0, img, 0, 1, mask, corr_host, nullptr);
     if (rc) return rc;
-    s.queue.back().scalar = corr_host;
     return finish_slot(ctx, s);
 }
 
@@ -1067,10 +1177,11 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
 {
     if (!v || !v->watermark || !frames) return WM_ERR_ARG;
     wm_ctx* ctx = v->watermark;
-    if (mode != WM_VIDEO_EMBED && mode != WM_VIDEO_DETECT) return fail(ctx, WM_ERR_ARG, "bad mode");
+    if (mode != WM_VIDEO_EMBED && mode != WM_VIDEO_DETECT && mode != WM_VIDEO_EMBED_VERIFY) return fail(ctx, WM_ERR_ARG, "bad mode");
+    const bool embed_mode = mode != WM_VIDEO_DETECT;
     if (v->height != ctx->rows || v->width != ctx->cols) return fail(ctx, WM_ERR_DIMS, "frame dims != watermark dims");
     if (v->watermark_interval < 1) return fail(ctx, WM_ERR_ARG, "watermark_interval must be >= 1");
-    if (mode == WM_VIDEO_EMBED && !out) return fail(ctx, WM_ERR_ARG, "embed needs an output buffer");
+    if (embed_mode && !out) return fail(ctx, WM_ERR_ARG, "embed needs an output buffer");
     const int64_t H = v->height, Wd = v->width;
     const int64_t linesize = v->linesize > 0 ? v->linesize : Wd;
     if (linesize < Wd) return fail(ctx, WM_ERR_ARG, "linesize < width");
@@ -1085,11 +1196,13 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
     const int64_t i0 = (K - first_index % K) % K;  // first gated frame: (first_index + i) % K == 0 (main.cpp:346,395: global index)
     const int64_t ngated = i0 < n_frames ? (n_frames - i0 + K - 1) / K : 0;
     const cudaMemcpyKind through = v->frames_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToHost;
-    // frames between the gated ones: copied through without the row padding (main.cpp:362-366), no scalar
+    // every scalar starts as NaN: frames between the gated ones have none, and an unsolvable frame leaves `a` untouched
+    // (Watermark.cpp:164-165) — the caller sees NaN there, never an uninitialised float
+    if (scalars) for (int64_t i = 0; i < (mode == WM_VIDEO_EMBED_VERIFY ? 2 * n_frames : n_frames); i++) scalars[i] = nanv;
+    // frames between the gated ones: copied through without the row padding (main.cpp:362-366)
     for (int64_t i = 0; i < n_frames; i++) {
         if ((first_index + i) % K == 0) continue;
-        if (scalars) scalars[i] = nanv;
-        if (mode == WM_VIDEO_EMBED)
+        if (embed_mode)
             CU(cudaMemcpy2DAsync(out + i * ostride, Wd, frames + i * fstride, linesize, Wd, H, through, ctx->slots[i % NSLOTS].stream));
     }
     // gated frames: equally spaced in memory, so a run of them is ONE batched launch sequence (image index in
@@ -1097,7 +1210,7 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
     const int64_t fbytes = H * Wd;
     // frames per run: big enough to amortise a launch's ramp and second-stage tail, small enough that several runs are in
     // flight on different slots (4K u8: 4 / 7 / 10 / 19 / 37 frames per run gave 17.1k / 18.2k / 19.0k / 18.5k / 18.2k frames/s)
-    int64_t B = v->frames_on_device ? std::max<int64_t>(1, std::min<int64_t>(32, (96LL << 20) / fbytes)) : 4;
+    int64_t B = v->frames_on_device ? std::max<int64_t>(1, std::min<int64_t>(32, (96LL << 20) / fbytes)) : ctx->opt_host_run;
     // even runs (37 frames at 7 per run: 7,6,6,6,6,6 rather than 7,7,7,7,7,2)
     const int64_t nruns = ngated > 0 ? (ngated + B - 1) / B : 0;
     const int64_t run_base = nruns ? ngated / nruns : 0, run_extra = nruns ? ngated % nruns : 0;
@@ -1124,7 +1237,7 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
             fin.data = s.stage_in; fin.ld = Wd;
             in_stride = fbytes;
         }
-        if (mode == WM_VIDEO_EMBED) {
+        if (embed_mode) {
             wm_image fout = fin;
             fout.ld = Wd;
             int64_t out_stride;
@@ -1136,10 +1249,19 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
             }
             rc = do_embed(ctx, si, &fin, &fin, &fout, in_stride, in_stride, out_stride, nb, WM_MASK_ME);  // main.cpp:356,380
             if (rc) return rc;
+            s.queue.back().scalar = scalars ? scalars + i : nullptr;
+            s.queue.back().sstride = K;
             if (!v->frames_on_device)
                 for (int j = 0; j < nb; j++)
                     CU(cudaMemcpyAsync(out + (i + j * K) * ostride, (uint8_t*)s.stage_out + j * fbytes, (size_t)fbytes,
                                        cudaMemcpyDeviceToHost, s.stream));
+            if (mode == WM_VIDEO_EMBED_VERIFY) {  // detect on the frame just written, where it lies on the device
+                rc = do_detect(ctx, si, &fout, out_stride, nb, WM_MASK_ME);
+                if (rc) return rc;
+                s.queue.back().scalar = scalars ? scalars + n_frames + i : nullptr;
+                s.queue.back().sstride = K;
+            }
+            continue;
         } else {
             rc = do_detect(ctx, si, &fin, in_stride, nb, WM_MASK_ME);  // main.cpp:406
             if (rc) return rc;
@@ -1149,6 +1271,45 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
     }
     for (int i = 0; i < NSLOTS; i++) { const int r = finish_slot(ctx, ctx->slots[i]); if (r < 0) return r; }
     return n_frames;
+}
+
+
+// ---- multi-GPU video driver: frames are independent, so the global index range is cut into contiguous chunks, one
+// per context / device, each driven by its own host thread; the interval gate sees the GLOBAL index (main.cpp:346,395), every scalar
+// lands in one array indexed by (global frame - first_index).  No collective: nothing but per-frame scalars leaves a GPU.
+void wm_shard_frames(int64_t n_frames, int rank, int world, int64_t* first, int64_t* count)
+{
+    if (world < 1) world = 1;
+    const int64_t base = n_frames / world, rem = n_frames % world;
+    if (first) *first = rank * base + std::min<int64_t>(rank, rem);
+    if (count) *count = base + (rank < rem ? 1 : 0);
+}
+
+int64_t wm_process_frames_multi(const wm_video_ctx* const* v, int ngpus, int mode, const uint8_t* const* chunk_frames, uint8_t* const* chunk_out,
+                                int64_t first_index, int64_t n_frames, float* scalars)
+{
+    if (!v || ngpus < 1 || !chunk_frames) return WM_ERR_ARG;
+    for (int g = 0; g < ngpus; g++)
+        if (!v[g] || !v[g]->watermark) return WM_ERR_ARG;
+    std::vector<int64_t> done((size_t)ngpus, 0);
+    std::vector<std::thread> th;
+    th.reserve((size_t)ngpus);
+    for (int g = 0; g < ngpus; g++) {
+        th.emplace_back([&, g]() {
+            int64_t first = 0, count = 0;
+            wm_shard_frames(n_frames, g, ngpus, &first, &count);
+            if (count == 0) { done[(size_t)g] = 0; return; }
+            done[(size_t)g] = wm_process_frames(v[g], mode, chunk_frames[g], chunk_out ? chunk_out[g] : nullptr, first_index + first, count,
+                                                scalars ? scalars + first : nullptr);
+        });
+    }
+    for (auto& t : th) t.join();
+    int64_t total = 0;
+    for (int g = 0; g < ngpus; g++) {
+        if (done[(size_t)g] < 0) return done[(size_t)g];  // the failing context keeps the message (wm_last_error)
+        total += done[(size_t)g];
+    }
+    return total;
 }
 
 // ---- helpers ----

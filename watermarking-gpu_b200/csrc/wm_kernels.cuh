@@ -693,6 +693,7 @@ struct SweepArgs {
     int b0;              // first image of this launch (a batch may be launched as sub-batches, see wm_api.cu: partition)
     int nblk_base, nblk_extra;  // CTAs per image = nblk_base + (image < nblk_extra)
     int vec_ok, transposed;
+    int solve_f32;       // WM_OPT_F32_SOLVE: the 8x8 system is rounded to f32 and solved by an f32 LU (af::solve on f32 arrays, Watermark.cpp:203)
     double* part;        // [batch][nsweep][NTOT]
     unsigned* counter;   // [batch]
     Scal* scal;          // [batch]
@@ -701,8 +702,25 @@ struct SweepArgs {
 
 __device__ __forceinline__ int lag_index(int dl, int dp) { return dl == 0 ? dp : (dl == 1 ? 5 + dp : 10 + dp); }
 
+// exactly rounded arithmetic of the LU in either precision (no contraction, so the f64 form is bit-reproducible against a plain C LU in the same order)
+struct OpsF64 {
+    using T = double;
+    static __device__ __forceinline__ T div(T a, T b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ T mulsub(T a, T f, T b) { return __dsub_rn(a, __dmul_rn(f, b)); }
+    static __device__ __forceinline__ T tol(double amax) { return 1e-12 * amax; }
+};
+struct OpsF32 {
+    using T = float;
+    static __device__ __forceinline__ T div(T a, T b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ T mulsub(T a, T f, T b) { return __fsub_rn(a, __fmul_rn(f, b)); }
+    static __device__ __forceinline__ T tol(double amax) { return 1e-6f * (float)amax; }
+};
+// Singularity rule (the reference leaves it to af::solve throwing, Watermark.cpp:205-208): a pivot not larger than
+// 1e-12 max|Rx| (f64 LU) / 1e-6 max|Rx| (f32 LU), or a zero / non-finite system, is "unsolvable" -> status 1.
+template <typename Ops>
 static __device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* sc, ScalDbg* dbg, int transposed, double* M /* smem [8][9] */)
 {
+    using T = typename Ops::T;
     // internal (line, pixel) raster order of the 8 neighbours
     const int DLc[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
     const int DPc[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
@@ -727,53 +745,53 @@ static __device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* s
         if (b < 8) dbg->Rx[a * 8 + b] = v; else dbg->rx[a] = v;
     }
     __syncwarp();
-    double A[9];
+    T A[9];
     const bool rowlane = lane < 8;
 #pragma unroll
-    for (int j = 0; j < 9; j++) A[j] = rowlane ? M[lane * 9 + j] : 0.0;
+    for (int j = 0; j < 9; j++) A[j] = rowlane ? (T)M[lane * 9 + j] : (T)0;
     double amax = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) amax = fmax(amax, fabs(A[j]));
+    for (int j = 0; j < 8; j++) amax = fmax(amax, fabs(rowlane ? M[lane * 9 + j] : 0.0));
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     amax = __shfl_sync(0xffffffffu, amax, 0);
     int singular = (!(amax > 0.0)) || !isfinite(amax);
-    const double tol = 1e-12 * amax;
+    const T tol = Ops::tol(amax);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         // first maximal |A[i][k]|, i >= k
-        double v = (rowlane && lane >= k) ? fabs(A[k]) : -1.0;
+        T v = (rowlane && lane >= k) ? (T)fabs(A[k]) : (T)-1;
         int idx = lane;
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const T ov = __shfl_xor_sync(0xffffffffu, v, o);
             const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
             if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
         }
         const int piv = __shfl_sync(0xffffffffu, idx, 0);
-        const double pv = __shfl_sync(0xffffffffu, v, 0);
+        const T pv = __shfl_sync(0xffffffffu, v, 0);
         if (!(pv > tol)) singular = 1;
-        double pr[9];
+        T pr[9];
 #pragma unroll
         for (int j = 0; j < 9; j++) {
-            const double rk = __shfl_sync(0xffffffffu, A[j], k);
-            const double rp = __shfl_sync(0xffffffffu, A[j], piv & 7);
+            const T rk = __shfl_sync(0xffffffffu, A[j], k);
+            const T rp = __shfl_sync(0xffffffffu, A[j], piv & 7);
             if (lane == k) A[j] = rp; else if (lane == piv) A[j] = rk;
             pr[j] = rp;  // row k after the swap
         }
         if (rowlane && lane > k) {
-            const double f = __ddiv_rn(A[k], pr[k]);
+            const T f = Ops::div(A[k], pr[k]);
 #pragma unroll
-            for (int j = k; j < 9; j++) A[j] = __dsub_rn(A[j], __dmul_rn(f, pr[j]));
+            for (int j = k; j < 9; j++) A[j] = Ops::mulsub(A[j], f, pr[j]);
         }
     }
-    double cc[8];
+    T cc[8];
 #pragma unroll
     for (int i = 7; i >= 0; i--) {
-        double s = A[8];
+        T s = A[8];
 #pragma unroll
-        for (int j = i + 1; j < 8; j++) s = __dsub_rn(s, __dmul_rn(A[j], cc[j]));
-        const double ci = __ddiv_rn(s, A[i]);
+        for (int j = i + 1; j < 8; j++) s = Ops::mulsub(s, A[j], cc[j]);
+        const T ci = Ops::div(s, A[i]);
         cc[i] = __shfl_sync(0xffffffffu, ci, i);
     }
     if (lane == 0) {
@@ -1288,7 +1306,10 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
     __shared__ double M[72];
     block_column_reduce<NTOT, 64, NTOT>(part, nblk, tot, reinterpret_cast<double*>(dsm));
     if (threadIdx.x == 0) ts4 = gtime();
-    if (w == 0) solve_system(tot, a.scal + b, a.dbg + b, a.transposed, M);
+    if (w == 0) {
+        if (a.solve_f32) solve_system<OpsF32>(tot, a.scal + b, a.dbg + b, a.transposed, M);
+        else solve_system<OpsF64>(tot, a.scal + b, a.dbg + b, a.transposed, M);
+    }
     if (threadIdx.x == 0) {
         unsigned long long* ts = a.dbg[b].ts;
         ts[0] = ts0; ts[1] = ts1; ts[2] = ts2; ts[3] = ts3; ts[4] = ts4; ts[5] = gtime(); ts[6] = 0; ts[7] = 0;
