@@ -137,11 +137,16 @@ int wm_rgb2gray(wm_ctx *ctx, const wm_image *rgb, wm_image *gray, float wr, floa
  *   WM_DBG_PHASES  8 doubles  timeline of the last Rx sweep's last CTA, ns since that CTA started: [1] tiles done, [2] frame
  *                             ring done, [3] elected last, [4] second-stage sums done, [5] 8x8 system solved (profiling aid)
  * wm_debug_set_coeffs injects coefficients: the next call skips the Rx sweep + solve (staged parity).
- * wm_debug_planes computes e_z (or NVF mask when what == WM_DBG_MASK_NVF) for an image into dst_dev. */
-enum { WM_DBG_RX = 0, WM_DBG_RXVEC = 1, WM_DBG_COEFFS = 2, WM_DBG_SCALARS = 3, WM_DBG_ERRSEQ = 4, WM_DBG_MASK_NVF = 5, WM_DBG_PHASES = 6 };
+ * wm_debug_plane computes e_z (WM_DBG_ERRSEQ), the NVF mask (WM_DBG_MASK_NVF) or the prediction-error mask |e| / max|e|
+ * (WM_DBG_MASK_ME, Watermark.cpp:213-214) of an image into dst_dev.
+ * wm_debug_detect_planes runs detectWatermark's own kernel on an f32 image and also writes the two planes it never materialises:
+ * u = mask.W (Watermark.cpp:248; for the ME mask the kernel's u is |e_z|.W — the 1 / max|e| scale cancels in the correlation and is
+ * dropped) and e_u = u - prediction(u) with u clamped to the edge (Watermark.cpp:221-225), dense, same layout as the image. */
+enum { WM_DBG_RX = 0, WM_DBG_RXVEC = 1, WM_DBG_COEFFS = 2, WM_DBG_SCALARS = 3, WM_DBG_ERRSEQ = 4, WM_DBG_MASK_NVF = 5, WM_DBG_PHASES = 6, WM_DBG_MASK_ME = 7 };
 int wm_debug_get(wm_ctx *ctx, int what, void *dst_host);
 int wm_debug_set_coeffs(wm_ctx *ctx, const float *coeffs8_or_null);
 int wm_debug_plane(wm_ctx *ctx, const wm_image *img, int what, float *dst_dev /* same layout, dense */);
+int wm_debug_detect_planes(wm_ctx *ctx, const wm_image *img, int mask_type, float *u_dev, float *eu_dev, float *corr_host);
 
 /* per-kernel device time (ms) accumulated since the last reset, when WM_OPT_KERNEL_TIMING is on.
  * names: 0 rx_sweep(+solve) 1 me_stats 2 nvf_stats 3 me_apply 4 me_detect 5 nvf_apply 6 nvf_detect.  Returns the number of timed brackets

@@ -352,3 +352,39 @@ def test_detector_sums_individually(wmb, oracle, rows, cols, layout):
         assert abs(corr - od["corr"]) / max(abs(od["corr"]), 1e-30) <= 1e-4
         wm.debug_set_coeffs(None)
     wm.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the detector's never-materialised planes (u, e_u) and the ME mask, bit for bit with injected coefficients (MASK, U, EU)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("rows,cols", [(3, 3), (5, 7), (33, 129), (64, 64), (67, 131), (130, 260), (512, 512)])
+def test_detector_planes_bit_exact(wmb, oracle, rows, cols, layout):
+    img = util.natural_image(rows, cols, seed=1000 + rows * 3 + cols) if rows != 512 else util.load_512_gray(oracle)
+    W = util.normal_w(rows, cols) if rows != 512 else util.load_w512()
+    wm = _mk(wmb, rows, cols, W)
+    d = wmb.DeviceArray.from_numpy(wm, img, layout)
+    for mask in (wmb.NVF, wmb.ME):
+        od = oracle.detect(img, W, mask)
+        if od["status"] != 0:
+            continue
+        wm.debug_set_coeffs(od["coef"])
+        u, eu, corr = wm.debug_detect_planes(d, mask)
+        if mask == wmb.NVF:
+            want_u = od["u"]
+        else:
+            want_u = (np.abs(od["ez"]) * W).astype(np.float32)  # the kernel keeps |e_z|.W: the 1 / max|e| scale cancels in the correlation
+        want_eu = (want_u - oracle.scaled_neighbors(want_u, od["coef"])).astype(np.float32)
+        report("detector planes %dx%d layout=%d mask=%d: u maxdiff %.3g, e_u maxdiff %.3g" % (
+            rows, cols, layout, mask, np.abs(u - want_u).max(), np.abs(eu - want_eu).max()))
+        assert np.array_equal(u, want_u)
+        assert np.array_equal(eu, want_eu)
+        if mask == wmb.NVF:
+            assert np.array_equal(eu, od["eu"])
+        assert abs(corr - od["corr"]) / max(abs(od["corr"]), 1e-30) <= 1e-4
+        if mask == wmb.ME:
+            pm = oracle.pred_error_mask(img)
+            m = wm.debug_plane(d, wmb.DBG_MASK_ME)
+            assert np.array_equal(m, pm["mask"])
+        wm.debug_set_coeffs(None)
+    wm.close()

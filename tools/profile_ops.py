@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--no-tma", action="store_true")
     a = ap.parse_args()
     pkg = importlib.import_module("watermarking-gpu_b200")
-    rows, cols, _, kind, dtype = bench.WORKLOADS[a.workload]
+    rows, cols, _, _, kind, dtype = bench.WORKLOADS[a.workload]
     frames, W = bench.make_inputs(rows, cols, a.batch, dtype)
     wm = pkg.Watermark(rows, cols, W, 3, 40.0)
     if a.no_tma:

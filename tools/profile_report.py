@@ -1,7 +1,7 @@
 """Turn ncu captures (read here, no GPU) into the tracked summaries under profiles/.
 
 usage: python tools/profile_report.py <round-tag> <full.ncu-rep> <frames-in-capture> <workload> [<launches.csv>]
-writes profiles/<round-tag>_<workload>_ncu_summary.md, updates profiles/traffic.json (DRAM bytes per frame and kernel),
+writes profiles/<round-tag>_<workload>_ncu_summary.md, updates profiles/r2_traffic.json (DRAM bytes per frame and kernel),
 and (with a launch list) profiles/<round-tag>_<workload>_launches.md with each kernel's share of the step."""
 import collections
 import csv
@@ -14,8 +14,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KMAP = [("k_sweep", "rx_sweep"), ("k_stats<float, 0", "me_stats"), ("k_stats<unsigned char, 0", "me_stats"),
-        ("k_stats<float, 1", "nvf_stats"), ("k_stats<unsigned char, 1", "nvf_stats"), ("k_apply", "embed_apply"),
-        ("k_detect", "detect_apply")]
+        ("k_stats<float, 1", "nvf_stats"), ("k_stats<unsigned char, 1", "nvf_stats"),
+        ("k_apply<float, float, 0", "me_apply"), ("k_apply<unsigned char, unsigned char, 0", "me_apply"),
+        ("k_apply<float, float, 1", "nvf_apply"), ("k_apply<unsigned char, unsigned char, 1", "nvf_apply"),
+        ("k_detect<float, 0", "me_detect"), ("k_detect<unsigned char, 0", "me_detect"),
+        ("k_detect<float, 1", "nvf_detect"), ("k_detect<unsigned char, 1", "nvf_detect")]
 
 
 def kname(full):
@@ -98,7 +101,7 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", "%s_%s_ncu_summary.md" % (tag, wl)), "w") as f:
         f.write("\n".join(lines) + "\n")
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     t = json.load(open(tpath)) if os.path.exists(tpath) else {}
     t[wl] = {"unit": "DRAM bytes (read+write) per frame per launch, from ncu --set full", "source": tag,
              "per_frame": {k: sum(v) / len(v) for k, v in traffic.items()}}

@@ -23,7 +23,7 @@ F32, U8 = 0, 1
 OK, SINGULAR, ZERO_MASK = 0, 1, 2
 OPT_FP16_PRODUCTS, OPT_KERNEL_TIMING, OPT_USE_TMA, OPT_SERIAL_SLOTS, OPT_CUDA_GRAPHS, OPT_MMA_ACCUM, OPT_SPLIT_COST = 1, 2, 3, 4, 5, 6, 7
 OPT_F32_SOLVE, OPT_HOST_RUN_FRAMES = 8, 9
-DBG_RX, DBG_RXVEC, DBG_COEFFS, DBG_SCALARS, DBG_ERRSEQ, DBG_MASK_NVF, DBG_PHASES = range(7)
+DBG_RX, DBG_RXVEC, DBG_COEFFS, DBG_SCALARS, DBG_ERRSEQ, DBG_MASK_NVF, DBG_PHASES, DBG_MASK_ME = range(8)
 KERNEL_NAMES = ["rx_sweep", "me_stats", "nvf_stats", "me_apply", "me_detect", "nvf_apply", "nvf_detect"]
 VIDEO_EMBED, VIDEO_DETECT, VIDEO_EMBED_VERIFY = 0, 1, 2
 
@@ -33,7 +33,7 @@ EXPORTS = [
     "wm_set_option", "wm_last_error", "wm_strength_factor", "wm_embed", "wm_detect", "wm_num_slots", "wm_get_stream",
     "wm_embed_batch", "wm_detect_batch", "wm_sync", "wm_embed_host", "wm_detect_host", "wm_embed_host_batch",
     "wm_detect_host_batch", "wm_shard_frames", "wm_process_frames_multi", "wm_rgb2gray", "wm_debug_get",
-    "wm_debug_set_coeffs", "wm_debug_plane", "wm_get_kernel_times", "wm_launch_count", "wm_process_frames",
+    "wm_debug_set_coeffs", "wm_debug_plane", "wm_debug_detect_planes", "wm_get_kernel_times", "wm_launch_count", "wm_process_frames",
     "wm_dev_alloc", "wm_dev_free", "wm_dev_upload", "wm_dev_download", "wm_host_alloc_pinned",
     "wm_host_free_pinned", "wm_device_count", "wm_version",
 ]
@@ -110,6 +110,7 @@ def lib():
     L.wm_debug_get.argtypes = [vp, i32, vp]
     L.wm_debug_set_coeffs.argtypes = [vp, fp]
     L.wm_debug_plane.argtypes = [vp, imp, i32, vp]
+    L.wm_debug_detect_planes.argtypes = [vp, imp, i32, vp, vp, fp]
     L.wm_get_kernel_times.argtypes = [vp, i32, C.POINTER(C.c_double), i32]
     L.wm_get_kernel_times.restype = i64
     L.wm_launch_count.argtypes = [vp]
@@ -393,6 +394,18 @@ class Watermark:
         r = dst.numpy()
         dst.free()
         return r
+
+    def debug_detect_planes(self, image, mask_type):
+        """The detector's own kernel on an f32 DeviceArray, writing the planes it never materialises: -> (u, e_u, corr) as numpy."""
+        du = DeviceArray(self, image.rows, image.cols, image.layout, F32, 1)
+        de = DeviceArray(self, image.rows, image.cols, image.layout, F32, 1)
+        corr = C.c_float(0.0)
+        d = image.desc()
+        self._check(lib().wm_debug_detect_planes(self._h, C.byref(d), mask_type, du.ptr, de.ptr, C.byref(corr)))
+        u, eu = du.numpy(), de.numpy()
+        du.free()
+        de.free()
+        return u, eu, corr.value
 
     def kernel_times(self, reset=True):
         """{name: (launches, total_ms)} accumulated while OPT_KERNEL_TIMING is on."""

@@ -295,10 +295,10 @@ int max_rows(const std::vector<SubBatch>& v)
     for (const SubBatch& sb : v) m = std::max(m, sb.base + (sb.extra > 0 ? 1 : 0));
     return m;
 }
-Plan plan(const wm_ctx* ctx, const Geo& g, int batch)
+Plan plan(const wm_ctx* ctx, const Geo& g, int batch, int dtype)
 {
     Plan p;
-    p.detect = partition(2 * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
+    p.detect = partition(detect_ctas_per_sm(dtype == WM_U8) * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
     p.embed = partition(EMBED_CTAS_PER_SM * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
     p.sweep = partition(SWEEP_CTAS_PER_SM * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
     p.nframe = 0;  // the frame ring is shared by the sweep blocks
@@ -487,7 +487,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     CU(cudaSetDevice(ctx->device));
     Slot& s = ctx->slots[slot];
     const Geo g = geo(vi.L, vi.P);
-    const Plan pl = plan(ctx, g, batch);
+    const Plan pl = plan(ctx, g, batch, vi.dtype);
     if ((rc = ensure_slot(ctx, s, batch, std::max(pl.gx_stats, pl.gx_detect), pl.nsweep, pl.nframe))) return rc;
     const float* W = w_for(ctx, vi.transposed, s.stream, &rc);
     if (rc) return rc;
@@ -544,7 +544,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     return push_result(ctx, s, 1, batch);
 }
 
-int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, int batch, int mask)
+int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, int batch, int mask, float* dbg_u = nullptr, float* dbg_eu = nullptr)
 {
     if (!ctx) return WM_ERR_ARG;
     if (slot < 0 || slot >= NSLOTS) return fail(ctx, WM_ERR_ARG, "bad slot");
@@ -557,7 +557,7 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     CU(cudaSetDevice(ctx->device));
     Slot& s = ctx->slots[slot];
     const Geo g = geo(v.L, v.P);
-    const Plan pl = plan(ctx, g, batch);
+    const Plan pl = plan(ctx, g, batch, v.dtype);
     if ((rc = ensure_slot(ctx, s, batch, std::max(pl.gx_stats, pl.gx_detect), pl.nsweep, pl.nframe))) return rc;
     const float* W = w_for(ctx, v.transposed, s.stream, &rc);
     if (rc) return rc;
@@ -574,6 +574,7 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     da.part = s.part + stats_part_offset(pl, batch);
     da.counter = s.counters + 2 * s.batch_cap;
     da.scal = s.scal; da.dbg = s.dbg;
+    da.dbg_u = dbg_u; da.dbg_eu = dbg_eu;
     CUtensorMap tmZ, tmW;
     memset(&tmZ, 0, sizeof tmZ);
     memset(&tmW, 0, sizeof tmW);
@@ -1124,10 +1125,22 @@ int wm_debug_set_coeffs(wm_ctx* ctx, const float* c)
     return WM_OK;
 }
 
+int wm_debug_detect_planes(wm_ctx* ctx, const wm_image* img, int mask, float* u_dev, float* eu_dev, float* corr_host)
+{
+    if (!ctx || !img || !u_dev || !eu_dev) return WM_ERR_ARG;
+    if (img->dtype != WM_F32 || (mask == WM_MASK_NVF && ctx->p != 3)) return fail(ctx, WM_ERR_ARG, "detector planes: f32 images, 3x3 masks");
+    Slot& s = ctx->slots[0];
+    if (!s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+    const int rc = do_detect(ctx, 0, img, 0, 1, mask, u_dev, eu_dev);
+    if (rc) return rc;
+    s.queue.back().scalar = corr_host;
+    return finish_slot(ctx, s);
+}
+
 int wm_debug_plane(wm_ctx* ctx, const wm_image* img, int what, float* dst_dev)
 {
     if (!ctx || !dst_dev) return WM_ERR_ARG;
-    if (what != WM_DBG_ERRSEQ && what != WM_DBG_MASK_NVF) return fail(ctx, WM_ERR_ARG, "plane must be ERRSEQ or MASK_NVF");
+    if (what != WM_DBG_ERRSEQ && what != WM_DBG_MASK_NVF && what != WM_DBG_MASK_ME) return fail(ctx, WM_ERR_ARG, "plane must be ERRSEQ, MASK_NVF or MASK_ME");
     View v;
     int rc;
     if ((rc = make_view(ctx, img, &v, false))) return rc;
@@ -1135,9 +1148,9 @@ int wm_debug_plane(wm_ctx* ctx, const wm_image* img, int what, float* dst_dev)
     Slot& s = ctx->slots[0];
     if (!s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
     const Geo g = geo(v.L, v.P);
-    const Plan pl = plan(ctx, g, 1);
+    const Plan pl = plan(ctx, g, 1, v.dtype);
     if ((rc = ensure_slot(ctx, s, 1, std::max(pl.gx_stats, pl.gx_detect), pl.nsweep, pl.nframe))) return rc;
-    if (what == WM_DBG_ERRSEQ) {
+    if (what == WM_DBG_ERRSEQ || what == WM_DBG_MASK_ME) {
         if ((rc = enqueue_sweep(ctx, s, v, 0, 1, g, pl))) return rc;
     }
     if (what == WM_DBG_MASK_NVF && ctx->p != 3) {  // the p x p window goes through k_nvfp, straight into the caller's plane
@@ -1153,8 +1166,13 @@ int wm_debug_plane(wm_ctx* ctx, const wm_image* img, int what, float* dst_dev)
     pa.scal = s.scal;
     pa.dst = dst_dev;
     const dim3 grid(std::min(g.ntiles, 3 * ctx->sms));
-    launch_plane(v.dtype, what == WM_DBG_ERRSEQ, v.transposed, grid, s.stream, pa);
+    launch_plane(v.dtype, what != WM_DBG_MASK_NVF, v.transposed, grid, s.stream, pa);
     ctx->launches++;
+    if (what == WM_DBG_MASK_ME) {  // mask = |e| / max|e| (Watermark.cpp:213-214); the counters' first word doubles as the max scratch and is zero again afterwards
+        launch_mask_from_errseq(dst_dev, (long long)g.L * g.P, s.counters, s.stream);
+        CU(cudaMemsetAsync(s.counters, 0, sizeof(unsigned), s.stream));
+        ctx->launches += 2;
+    }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s.stream));
     return WM_OK;

@@ -10,8 +10,16 @@ void launch_detect_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtens
     else if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_detect<PixT, 0, true, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); else WM_LAUNCH((k_detect<PixT, 0, false, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); }
     else { if (tr) WM_LAUNCH((k_detect<PixT, 1, true, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); else WM_LAUNCH((k_detect<PixT, 1, false, TMA>), detect_smem(TMA, sizeof(PixT) == 1), tmZ, tmW, a); }
 }
+// debug instantiations (f32, 3x3 masks): the same kernel also writes its u and e_u planes
+template <bool TMA>
+static void launch_detect_dbg(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
+{
+    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_detect<float, 0, true, TMA, true>), detect_smem(TMA, false), tmZ, tmW, a); else WM_LAUNCH((k_detect<float, 0, false, TMA, true>), detect_smem(TMA, false), tmZ, tmW, a); }
+    else { if (tr) WM_LAUNCH((k_detect<float, 1, true, TMA, true>), detect_smem(TMA, false), tmZ, tmW, a); else WM_LAUNCH((k_detect<float, 1, false, TMA, true>), detect_smem(TMA, false), tmZ, tmW, a); }
+}
 void launch_detect(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
 {
+    if (a.dbg_u) { if (tma) launch_detect_dbg<true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_dbg<false>(mask, tr, grid, st, tmZ, tmW, a); return; }
     if (dtype == WM_F32) { if (tma) launch_detect_t<float, true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_t<float, false>(mask, tr, grid, st, tmZ, tmW, a); }
     else { if (tma) launch_detect_t<uint8_t, true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_t<uint8_t, false>(mask, tr, grid, st, tmZ, tmW, a); }
 }
@@ -23,6 +31,13 @@ void launch_plane(int dtype, int what_errseq, bool tr, dim3 grid, cudaStream_t s
     else { if (tr) k_plane<PIX, 1, true><<<grid, NT, 0, st>>>(a); else k_plane<PIX, 1, false><<<grid, NT, 0, st>>>(a); }
     if (dtype == WM_F32) { WM_PLANE(float) } else { WM_PLANE(uint8_t) }
 #undef WM_PLANE
+}
+
+void launch_mask_from_errseq(float* plane, long long n, unsigned* scratch, cudaStream_t st)
+{
+    cudaMemsetAsync(scratch, 0, sizeof(unsigned), st);
+    k_absmax<<<256, 256, 0, st>>>(plane, n, scratch);
+    k_scale_abs<<<256, 256, 0, st>>>(plane, n, scratch);
 }
 
 void launch_rgb2gray(const float* r, const float* g, const float* b, float* gray, long long ld_in, long long ld_out, int L, int P,

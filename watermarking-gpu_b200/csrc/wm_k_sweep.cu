@@ -6,9 +6,9 @@ namespace wm {
 template <typename PixT, bool TMA>
 static void launch_sweep_t(int acc, int smem, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const SweepArgs& a)
 {
-    if (acc == 2) WM_LAUNCH((k_sweep<PixT, 2, TMA>), smem, tmI, a);
-    else if (acc == 1) WM_LAUNCH((k_sweep<PixT, 1, TMA>), smem, tmI, a);
-    else WM_LAUNCH((k_sweep<PixT, 0, TMA>), smem, tmI, a);
+    if (acc == 2) WM_LAUNCH_T((k_sweep<PixT, 2, TMA>), SNT, smem, tmI, a);
+    else if (acc == 1) WM_LAUNCH_T((k_sweep<PixT, 1, TMA>), SNT, smem, tmI, a);
+    else WM_LAUNCH_T((k_sweep<PixT, 0, TMA>), SNT, smem, tmI, a);
 }
 
 // acc: 0 = f32 products, 1 = fp16-rounded products + FHADD accumulation, 2 = fp16-rounded products + HMMA accumulation

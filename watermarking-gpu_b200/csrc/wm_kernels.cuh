@@ -64,14 +64,22 @@ constexpr int SWEEP_NST = 2, SWEEP_NST_U8 = 4, EMBED_NST = 2, EMBED_NST_U8 = 3, 
 // it landed (rows of U8_ROW bytes, the tile's column 0 at byte U8_OFF) — stats / apply / detect widen the bytes in registers
 template <typename T> struct TileGeo { static constexpr int STRIDE = SW, OFF = 0; };
 template <> struct TileGeo<unsigned char> { static constexpr int STRIDE = U8_ROW, OFF = U8_OFF; };
-constexpr int SWEEP_CTAS_PER_SM = 3;  // the f64 lag accumulators live in smem so that three CTAs (24 warps) fit per SM
-constexpr int SWEEP_ACC = NLAG * NT * 8;  // [NLAG][NT] doubles
+// The sweep runs 128-thread CTAs: 4 warps x 8 lines (SLPT) of the 128 x 32 tile, so that the per-tile costs (tile bookkeeping, TMA
+// issue, barriers, the u8 -> fp16 conversion's addressing) are paid once per 32 pixels of a thread instead of once per 16, and a
+// thread's rolling 3-line window loads 10 lines per 8 instead of 6 per 4.  Four CTAs (16 warps) per SM leave 128 registers per
+// thread: the f64 lag accumulators live in registers.
+constexpr int SNT = 128, SLPT = TL / (SNT / 32);
+constexpr int SWEEP_CTAS_PER_SM = 4;
 constexpr int EMBED_CTAS_PER_SM = 3;  // stats / apply: 2 stages of 35 KB -> three CTAs (24 warps) per SM
 // dynamic shared memory per kernel: [NST stages][work tiles]; with f32 TMA the stage IS the work tile
 __host__ __device__ constexpr int sweep_stage(bool u8) { return u8 ? U8_I34 : SZ_I34; }
 __host__ __device__ constexpr int embed_stage(bool u8) { return (u8 ? U8_I34 : SZ_I34) + SZ_WT; }
 __host__ __device__ constexpr int detect_stage(bool u8) { return (u8 ? U8_I36 : SZ_I36) + SZ_I34; }  // Z (halo 2) + W (halo 1)
-__host__ __device__ constexpr int sweep_smem(bool tma, bool u8) { return (tma ? (u8 ? SWEEP_NST_U8 * sweep_stage(true) + SZ_I34 : SWEEP_NST * sweep_stage(false)) : SZ_I34) + SWEEP_ACC; }
+// u8 TMA: byte stages + two fp16 work tiles (in one SZ_I34 area); plain path: one f32 work tile, at least the frame ring's [NFRM][SNT] f32 reduction buffer
+__host__ __device__ constexpr int sweep_smem(bool tma, bool u8)
+{
+    return tma ? (u8 ? SWEEP_NST_U8 * sweep_stage(true) + SZ_I34 : SWEEP_NST * sweep_stage(false)) : (SZ_I34 > align128(NFRM * SNT * 4) ? SZ_I34 : align128(NFRM * SNT * 4));
+}
 constexpr int embed_smem(bool tma, bool u8) { return tma ? (u8 ? EMBED_NST_U8 : EMBED_NST) * embed_stage(u8) : SZ_I34 + SZ_WT; }
 constexpr int detect_smem(bool tma, bool u8)  // + u tile
 {
@@ -232,9 +240,9 @@ __device__ __forceinline__ uchar4 ld_pinned(const uchar4* p)
 // Register-prefetched variant of the plain loaders: issue() starts the global loads of a tile into registers (before the
 // current tile is computed), commit() converts and stores them to smem one iteration later, so the load latency hides
 // behind a whole tile of arithmetic.  Chunks that cannot be vector-loaded (frame, odd alignment) are read in commit().
-template <typename PixT, int NROWS>
+template <typename PixT, int NROWS, int NTH = NT>
 struct TilePrefetch {
-    static constexpr int CH = SW / 4, NCH = (NROWS * CH + NT - 1) / NT;
+    static constexpr int CH = SW / 4, NCH = (NROWS * CH + NTH - 1) / NTH;
     using Raw = typename std::conditional<sizeof(PixT) == 4, float4, uchar4>::type;
     Raw v[NCH];
     unsigned ok;
@@ -244,7 +252,7 @@ struct TilePrefetch {
         ok = 0; l_org = l_org_; p_org = p_org_;
 #pragma unroll
         for (int k = 0; k < NCH; k++) {
-            const int idx = threadIdx.x + k * NT;
+            const int idx = threadIdx.x + k * NTH;
             if (idx < NROWS * CH) {
                 const int r = idx / CH, c = idx - r * CH;
                 const int l = clampi(l_org + r, 0, L - 1), p = p_org + 4 * c;
@@ -259,7 +267,7 @@ struct TilePrefetch {
     {
 #pragma unroll
         for (int k = 0; k < NCH; k++) {
-            const int idx = threadIdx.x + k * NT;
+            const int idx = threadIdx.x + k * NTH;
             if (idx < NROWS * CH) {
                 float4 f;
                 if ((ok >> k) & 1) {
@@ -313,9 +321,10 @@ struct WTilePrefetch {
 // u8 TMA stage (rows of U8_ROW bytes) -> f32 work tile (rows of SW floats).  Warp w takes rows w, w + 8, ...; lane l takes
 // the 4-pixel chunk l of the row (no index division, conflict-free LDS.32 / STS.128, every load issued before the first
 // conversion); the two chunks beyond 32 lanes (pixels 128..135) of all rows are one extra predicated step.
-template <int NROWS>
+template <int NROWS, int NTH = NT>
 __device__ __forceinline__ void convert_u8_tile(const unsigned char* __restrict__ src, float* __restrict__ dst)
 {
+    constexpr int NT = NTH;  // shadows the CTA-wide default inside this function
     constexpr int NIT = (NROWS + NT / 32 - 1) / (NT / 32);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned char* s0 = src + w * U8_ROW + U8_OFF + 4 * lane;
@@ -350,9 +359,10 @@ __device__ __forceinline__ uint2 u8x4_to_h4(unsigned u)
     o.y = *reinterpret_cast<const unsigned*>(&h1);
     return o;
 }
-template <int NROWS>
+template <int NROWS, int NTH = NT>
 __device__ __forceinline__ void convert_u8_tile_h(const unsigned char* __restrict__ src, __half* __restrict__ dst)
 {
+    constexpr int NT = NTH;
     constexpr int NIT = (NROWS + NT / 32 - 1) / (NT / 32);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned char* s0 = src + w * U8_ROW + U8_OFF + 4 * lane;
@@ -378,9 +388,10 @@ __device__ __forceinline__ bool tile_on_frame(int l_org, int p_org, int L, int P
 {
     return l_org < 0 || l_org + NROWS > L || p_org < 0 || p_org + SW > P;
 }
-template <int NROWS, typename T>
+template <int NROWS, int NTH = NT, typename T>
 __device__ __forceinline__ void fix_border(T* tile, int l_org, int p_org, int L, int P)
 {
+    constexpr int NT = NTH;
     constexpr int ST = TileGeo<T>::STRIDE;
     T* const t0 = tile + TileGeo<T>::OFF;  // column 0 of the tile
     // Only cells within 2 of the image are ever read by a valid pixel's window, so at most 2 lines above, 2 below,
@@ -421,9 +432,10 @@ __device__ __forceinline__ float warp_max(float v)
 }
 
 // block-level sum of NV doubles per thread -> red[0..NV) (valid for thread t < NV at red[t]); red: [8][NV] doubles
-template <int NV>
+template <int NV, int NTH = NT>
 __device__ __forceinline__ void block_sum(const double (&v)[NV], double* red)
 {
+    constexpr int NT = NTH;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
@@ -441,9 +453,10 @@ __device__ __forceinline__ void block_sum(const double (&v)[NV], double* red)
 }
 
 // same for f32 partials (widened one at a time, so no second register array is live)
-template <int NV>
+template <int NV, int NTH = NT>
 __device__ __forceinline__ void block_sum_f32(const float (&v)[NV], double* red)
 {
+    constexpr int NT = NTH;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
@@ -480,9 +493,10 @@ __device__ __forceinline__ bool last_block(unsigned* counter, unsigned nblocks)
 // doubles of a row (coalesced) and every thread keeps 16 independent L2 loads in flight, so the whole array streams in a
 // few L2 round trips instead of one per row.  Columns >= MAXV0 are combined with max (non-negative values), the rest
 // with +.  out[v] (smem, NV entries) is valid for all threads after the call; scratch: NT doubles of smem.
-template <int NV, int NVP, int MAXV0>
+template <int NV, int NVP, int MAXV0, int NTH = NT>
 __device__ __forceinline__ void block_column_reduce(const double* __restrict__ part, int nblk, double* out, double* scratch)
 {
+    constexpr int NT = NTH;
     static_assert(NVP >= NV && (NVP & (NVP - 1)) == 0 && NVP <= NT, "NVP: power of two >= NV");
     constexpr int G = NT / NVP, U = 16;
     const int v = threadIdx.x & (NVP - 1), g = threadIdx.x / NVP;
@@ -802,13 +816,13 @@ static __device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* s
     }
 }
 
-// the 13-lag products of one thread's 4 px x 4 lines; FULL = every pixel of the tile is a core pixel
+// the 13-lag products of one thread's 4 px x SLPT lines; FULL = every pixel of the tile is a core pixel
 template <bool FP16, bool FULL>
 __device__ __forceinline__ void sweep_tile(const float* __restrict__ tile, int l0, int p0, int L, int P,
                                            float (&e0)[NLAG], float (&e1)[NLAG])
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const float* base = tile + (4 * w) * SW + 4 * lane + 2;  // window col 0 = pixel (p0 + 4*lane) - 2
+    const float* base = tile + (SLPT * w) * SW + 4 * lane + 2;  // window col 0 = pixel (p0 + 4*lane) - 2
     const int pb = p0 + 4 * lane;
     bool vp[4];
 #pragma unroll
@@ -823,9 +837,9 @@ __device__ __forceinline__ void sweep_tile(const float* __restrict__ tile, int l
     loadrow(A, base);
     loadrow(B, base + SW);
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
+    for (int r = 0; r < SLPT; r++) {
         loadrow(C, base + (r + 2) * SW);
-        const int l = l0 + 4 * w + r;
+        const int l = l0 + SLPT * w + r;
         const bool vl = FULL || ((l >= 1) && (l <= L - 2));
 #pragma unroll
         for (int jj = 0; jj < 4; jj += 2) {
@@ -852,7 +866,7 @@ __device__ __forceinline__ void sweep_tile_mma(const float* __restrict__ tile, i
                                                float (&c)[NACC], const MmaSel& sel)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const float* base = tile + (4 * w) * SW + 4 * lane + 2;
+    const float* base = tile + (SLPT * w) * SW + 4 * lane + 2;
     const int pb = p0 + 4 * lane;
     bool vp[4];
 #pragma unroll
@@ -868,9 +882,9 @@ __device__ __forceinline__ void sweep_tile_mma(const float* __restrict__ tile, i
     loadrow(B, base + SW);
     unsigned q12[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
+    for (int r = 0; r < SLPT; r++) {
         loadrow(C, base + (r + 2) * SW);
-        const int l = l0 + 4 * w + r;
+        const int l = l0 + SLPT * w + r;
         const bool vl = FULL || ((l >= 1) && (l <= L - 2));
 #pragma unroll
         for (int jj = 0; jj < 4; jj += 2) {
@@ -902,37 +916,38 @@ __device__ __forceinline__ void acc2_h2(float& a0, float& a1, unsigned x2, unsig
         : "+f"(a0), "+f"(a1)
         : "r"(x2), "r"(y2));
 }
+// one line of a thread's fp16 window: pixels p-2 .. p+5 = 4 aligned pairs h[0..3] = (-2,-1) (0,1) (2,3) (4,5) + 3 odd pairs s[0..2] = (-1,0) (1,2) (3,4)
+struct RowH { unsigned h[4], s[3]; };
+__device__ __forceinline__ void load_rowh(RowH& r, const __half* q)
+{
+    r.h[0] = *reinterpret_cast<const unsigned*>(q);
+    const uint2 mid = *reinterpret_cast<const uint2*>(q + 2);
+    r.h[1] = mid.x; r.h[2] = mid.y;
+    r.h[3] = *reinterpret_cast<const unsigned*>(q + 6);
+#pragma unroll
+    for (int i = 0; i < 3; i++) r.s[i] = __byte_perm(r.h[i], r.h[i + 1], 0x5432);  // (hi of h[i], lo of h[i+1])
+}
 template <bool FULL>
 __device__ __forceinline__ void sweep_tile_h2(const __half* __restrict__ tile, int l0, int p0, int L, int P,
                                               float (&e0)[NLAG], float (&e1)[NLAG])
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    // window of 8 pixels (p-2 .. p+5) = 4 aligned pairs h[0..3] = (-2,-1) (0,1) (2,3) (4,5) + 3 odd pairs s[0..2] = (-1,0) (1,2) (3,4)
-    const __half* base = tile + (4 * w) * SW + 4 * lane + 2;
+    const __half* base = tile + (SLPT * w) * SW + 4 * lane + 2;
     const int pb = p0 + 4 * lane;
     unsigned m01 = 0xffffffffu, m23 = 0xffffffffu;  // validity masks of my pixel pairs (all-ones halves)
     if (!FULL) {
         m01 = ((pb >= 1 && pb <= P - 2) ? 0x0000ffffu : 0u) | ((pb + 1 >= 1 && pb + 1 <= P - 2) ? 0xffff0000u : 0u);
         m23 = ((pb + 2 >= 1 && pb + 2 <= P - 2) ? 0x0000ffffu : 0u) | ((pb + 3 >= 1 && pb + 3 <= P - 2) ? 0xffff0000u : 0u);
     }
-    struct Row { unsigned h[4], s[3]; };
-    auto loadrow = [](Row& r, const __half* q) {
-        r.h[0] = *reinterpret_cast<const unsigned*>(q);
-        const uint2 mid = *reinterpret_cast<const uint2*>(q + 2);
-        r.h[1] = mid.x; r.h[2] = mid.y;
-        r.h[3] = *reinterpret_cast<const unsigned*>(q + 6);
+    RowH A, B, C;
+    load_rowh(A, base);
+    load_rowh(B, base + SW);
 #pragma unroll
-        for (int i = 0; i < 3; i++) r.s[i] = __byte_perm(r.h[i], r.h[i + 1], 0x5432);  // (hi of h[i], lo of h[i+1])
-    };
-    Row A, B, C;
-    loadrow(A, base);
-    loadrow(B, base + SW);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        loadrow(C, base + (r + 2) * SW);
+    for (int r = 0; r < SLPT; r++) {
+        load_rowh(C, base + (r + 2) * SW);
         unsigned x01 = A.h[1], x23 = A.h[2];
         if (!FULL) {
-            const int l = l0 + 4 * w + r;
+            const int l = l0 + SLPT * w + r;
             const bool vl = (l >= 1) && (l <= L - 2);
             x01 = vl ? (x01 & m01) : 0u;
             x23 = vl ? (x23 & m23) : 0u;
@@ -952,32 +967,23 @@ __device__ __forceinline__ void sweep_tile_h2_mma(const __half* __restrict__ til
                                                   float (&c)[NACC], const MmaSel& sel)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const __half* base = tile + (4 * w) * SW + 4 * lane + 2;
+    const __half* base = tile + (SLPT * w) * SW + 4 * lane + 2;
     const int pb = p0 + 4 * lane;
     unsigned m01 = 0xffffffffu, m23 = 0xffffffffu;
     if (!FULL) {
         m01 = ((pb >= 1 && pb <= P - 2) ? 0x0000ffffu : 0u) | ((pb + 1 >= 1 && pb + 1 <= P - 2) ? 0xffff0000u : 0u);
         m23 = ((pb + 2 >= 1 && pb + 2 <= P - 2) ? 0x0000ffffu : 0u) | ((pb + 3 >= 1 && pb + 3 <= P - 2) ? 0xffff0000u : 0u);
     }
-    struct Row { unsigned h[4], s[3]; };
-    auto loadrow = [](Row& r, const __half* q) {
-        r.h[0] = *reinterpret_cast<const unsigned*>(q);
-        const uint2 mid = *reinterpret_cast<const uint2*>(q + 2);
-        r.h[1] = mid.x; r.h[2] = mid.y;
-        r.h[3] = *reinterpret_cast<const unsigned*>(q + 6);
-#pragma unroll
-        for (int i = 0; i < 3; i++) r.s[i] = __byte_perm(r.h[i], r.h[i + 1], 0x5432);
-    };
-    Row A, B, C;
-    loadrow(A, base);
-    loadrow(B, base + SW);
+    RowH A, B, C;
+    load_rowh(A, base);
+    load_rowh(B, base + SW);
     unsigned q12[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        loadrow(C, base + (r + 2) * SW);
+    for (int r = 0; r < SLPT; r++) {
+        load_rowh(C, base + (r + 2) * SW);
         unsigned x01 = A.h[1], x23 = A.h[2];
         if (!FULL) {
-            const int l = l0 + 4 * w + r;
+            const int l = l0 + SLPT * w + r;
             const bool vl = (l >= 1) && (l <= L - 2);
             x01 = vl ? (x01 & m01) : 0u;
             x23 = vl ? (x23 & m23) : 0u;
@@ -998,10 +1004,11 @@ __device__ __forceinline__ void sweep_tile_h2_mma(const __half* __restrict__ til
 
 // FP16: 0 = f32 products (FFMA), 1 = products rounded to fp16, FHADD accumulation, 2 = rounded, HMMA accumulation
 template <typename PixT, int FP16, bool TMA>
-__global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_constant__ CUtensorMap tmI, const SweepArgs a)
+__global__ void __launch_bounds__(SNT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_constant__ CUtensorMap tmI, const SweepArgs a)
 {
+    constexpr int NT = SNT;  // every NT below is the sweep's own CTA size
     extern __shared__ __align__(128) unsigned char dsm[];
-    __shared__ double red[8 * NFRM];
+    __shared__ double red[(NT / 32) * NFRM];
     __shared__ __align__(8) uint64_t bars[SWEEP_NST_U8];
     constexpr bool U8T = TMA && sizeof(PixT) == 1;
     const int b = blockIdx.y + a.b0;
@@ -1024,36 +1031,40 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
             mbar_expect_tx(&bars[s], U8T ? (TL + 2) * U8_ROW : (TL + 2) * SW * 4);
             tma_load_3d(stage(s), &tmI, tp * TP - (U8T ? U8_LEFT : HP), tl * TL, b, &bars[s]);
         };
-        TileIter it(sb, step, a.tiles_p);
+        // three walkers over this CTA's tiles: `it` = the tile being computed, `nx` = the next one, `pf` = the one whose TMA load
+        // is issued this iteration (NST - 1 ahead); all advance incrementally
+        TileIter it(sb, step, a.tiles_p), nx(sb, step, a.tiles_p), pf(sb, step, a.tiles_p);
+        nx.next();
         if constexpr (TMA) {
             if (threadIdx.x == 0) {
                 for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
                 fence_barrier_init();
             }
             __syncthreads();
-            if (threadIdx.x == 0)
-                for (int s = 0; s < NST - 1; s++)
-                    if (sb + s * step < a.ntiles) { int ptl, ptp; it.peek(s, ptl, ptp); issue(ptl, ptp, s); }
+            for (int s = 0; s < NST - 1; s++) {
+                if (threadIdx.x == 0 && pf.t < a.ntiles) issue(pf.tl, pf.tp, s);
+                pf.next();
+            }
         }
-        // f64 accumulators of the 13 lags: one column per thread in smem ([v][thread], conflict-free), so they cost no
-        // registers; the f32 pair (e0, e1) is flushed into them every 8 tiles (64 px per accumulator: exact for integers)
-        double* const dsh = reinterpret_cast<double*>(dsm + sweep_smem(TMA, sizeof(PixT) == 1) - SWEEP_ACC) + threadIdx.x;
+        // f64 accumulators of the 13 lags in registers; the f32 partials are flushed into them every 4 tiles
+        // (HMMA accumulators: 4 x 32 = 128 products each between flushes, FHADD pairs 64: exact for integer-valued pixels)
+        double dacc[NLAG];
         float e0[NLAG], e1[NLAG];  // even / odd pixel accumulators (FP16 modes 0, 1)
-        float cm[NACC];            // HMMA accumulators (mode 2): 128 products each between flushes (128 * 65504 < 2^24)
+        float cm[NACC];            // HMMA accumulators (mode 2)
         const MmaSel sel = mma_selector();
 #pragma unroll
-        for (int v = 0; v < NLAG; v++) { dsh[v * NT] = 0.0; e0[v] = 0.0f; e1[v] = 0.0f; }
+        for (int v = 0; v < NLAG; v++) { dacc[v] = 0.0; e0[v] = 0.0f; e1[v] = 0.0f; }
 #pragma unroll
         for (int v = 0; v < NACC; v++) cm[v] = 0.0f;
         auto flush = [&]() {
             if constexpr (FP16 == 2) {
 #pragma unroll
-                for (int v = 0; v < NLAG - 1; v++) { dsh[v * NT] += (double)cm[v]; cm[v] = 0.0f; }
-                dsh[(NLAG - 1) * NT] += (double)__fadd_rn(__fadd_rn(cm[12], cm[13]), __fadd_rn(cm[14], cm[15]));
+                for (int v = 0; v < NLAG - 1; v++) { dacc[v] += (double)cm[v]; cm[v] = 0.0f; }
+                dacc[NLAG - 1] += (double)__fadd_rn(__fadd_rn(cm[12], cm[13]), __fadd_rn(cm[14], cm[15]));
                 cm[12] = cm[13] = cm[14] = cm[15] = 0.0f;
             } else {
 #pragma unroll
-                for (int v = 0; v < NLAG; v++) { dsh[v * NT] += (double)__fadd_rn(e0[v], e1[v]); e0[v] = 0.0f; e1[v] = 0.0f; }
+                for (int v = 0; v < NLAG; v++) { dacc[v] += (double)__fadd_rn(e0[v], e1[v]); e0[v] = 0.0f; e1[v] = 0.0f; }
             }
         };
         StagePos<NST> pos;
@@ -1062,31 +1073,25 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
             // u8 frames: fp16 work tiles + packed-half products.  Software pipeline with ONE barrier per tile: while tile k
             // is computed from work tile k&1, tile k+1 (already landed) is widened into the other work tile; the TMA
             // of tile k+NST-1 is issued at the top, so loads, conversion and arithmetic of three different tiles overlap.
+            // The byte stages are only ever written by TMA, so no proxy fence is needed before refilling one.
             __half* const wk0 = reinterpret_cast<__half*>(work);
             __half* const wk1 = wk0 + (TL + 2) * SW;  // 2 x 9248 B fit the SZ_I34 work area
             if (it.t < a.ntiles) {  // prologue: tile 0
                 mbar_wait(&bars[pos.s], pos.ph);
-                convert_u8_tile_h<TL + 2>(stage(pos.s), wk0);
+                convert_u8_tile_h<TL + 2, NT>(stage(pos.s), wk0);
                 pos.next();
                 __syncthreads();
-                if (tile_on_frame<TL + 2>(it.tl * TL, it.tp * TP - HP, L, P)) { fix_border<TL + 2>(wk0, it.tl * TL, it.tp * TP - HP, L, P); __syncthreads(); }
+                if (tile_on_frame<TL + 2>(it.tl * TL, it.tp * TP - HP, L, P)) { fix_border<TL + 2, NT>(wk0, it.tl * TL, it.tp * TP - HP, L, P); __syncthreads(); }
             }
-            for (; it.t < a.ntiles; it.next(), k++) {
+            for (; it.t < a.ntiles; it.next(), nx.next(), pf.next(), k++) {
                 const int l0 = it.tl * TL, p0 = it.tp * TP;
                 __half* const cur = (k & 1) ? wk1 : wk0;
                 __half* const nxt = (k & 1) ? wk0 : wk1;
-                const bool has_next = it.t + step < a.ntiles;
-                int ntl = 0, ntp = 0;
-                if (threadIdx.x == 0 && it.t + (NST - 1) * step < a.ntiles) {
-                    int ptl, ptp;
-                    it.peek(NST - 1, ptl, ptp);
-                    fence_proxy_async();
-                    issue(ptl, ptp, pos.ahead(NST - 2));  // pos is one tile ahead of k
-                }
+                const bool has_next = nx.t < a.ntiles;
+                if (threadIdx.x == 0 && pf.t < a.ntiles) issue(pf.tl, pf.tp, pos.ahead(NST - 2));  // pos is one tile ahead of k
                 if (has_next) {
-                    it.peek(1, ntl, ntp);
                     mbar_wait(&bars[pos.s], pos.ph);
-                    convert_u8_tile_h<TL + 2>(stage(pos.s), nxt);
+                    convert_u8_tile_h<TL + 2, NT>(stage(pos.s), nxt);
                     pos.next();
                 }
                 const bool full = l0 >= 1 && l0 + TL <= L - 1 && p0 >= 1 && p0 + TP <= P - 1;
@@ -1097,35 +1102,35 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
                     if (full) sweep_tile_h2<true>(cur, l0, p0, L, P, e0, e1);
                     else sweep_tile_h2<false>(cur, l0, p0, L, P, e0, e1);
                 }
-                if ((k & 7) == 7) flush();
+                if ((k & 3) == 3) flush();
                 __syncthreads();  // nxt complete, cur free, the stage just converted may be refilled
-                if (has_next && tile_on_frame<TL + 2>(ntl * TL, ntp * TP - HP, L, P)) { fix_border<TL + 2>(nxt, ntl * TL, ntp * TP - HP, L, P); __syncthreads(); }
+                if (has_next && tile_on_frame<TL + 2>(nx.tl * TL, nx.tp * TP - HP, L, P)) { fix_border<TL + 2, NT>(nxt, nx.tl * TL, nx.tp * TP - HP, L, P); __syncthreads(); }
             }
         } else {
-        TilePrefetch<PixT, TL + 2> pre;
+        TilePrefetch<PixT, TL + 2, NT> pre;
         if constexpr (!TMA) { if (it.t < a.ntiles) pre.issue(img, a.ld, L, P, it.tl * TL, it.tp * TP - HP, a.vec_ok != 0); }
-        for (; it.t < a.ntiles; it.next(), k++) {
+        bool patched = false;  // the stage consumed by the previous tile was patched by fix_border (generic-proxy writes)
+        for (; it.t < a.ntiles; it.next(), nx.next(), pf.next(), k++) {
             const int l0 = it.tl * TL, p0 = it.tp * TP;
             const float* tile;
             if constexpr (TMA) {
-                if (threadIdx.x == 0 && it.t + (NST - 1) * step < a.ntiles) {
-                    int ptl, ptp;
-                    it.peek(NST - 1, ptl, ptp);
-                    fence_proxy_async();
-                    issue(ptl, ptp, pos.ahead(NST - 1));
+                if (threadIdx.x == 0 && pf.t < a.ntiles) {
+                    if (patched && !U8T) fence_proxy_async();  // TMA is about to overwrite cells this CTA wrote through the generic proxy
+                    issue(pf.tl, pf.tp, pos.ahead(NST - 1));
                 }
                 mbar_wait(&bars[pos.s], pos.ph);
                 float* tw;
-                if constexpr (U8T) { tw = work; convert_u8_tile<TL + 2>(stage(pos.s), tw); __syncthreads(); }
+                if constexpr (U8T) { tw = work; convert_u8_tile<TL + 2, NT>(stage(pos.s), tw); __syncthreads(); }
                 else tw = reinterpret_cast<float*>(stage(pos.s));
-                if (tile_on_frame<TL + 2>(l0, p0 - HP, L, P)) { fix_border<TL + 2>(tw, l0, p0 - HP, L, P); __syncthreads(); }
+                patched = tile_on_frame<TL + 2>(l0, p0 - HP, L, P);
+                if (patched) { fix_border<TL + 2, NT>(tw, l0, p0 - HP, L, P); __syncthreads(); }
                 tile = tw;
                 pos.next();
             } else {
                 __syncthreads();
                 pre.commit(work, img, a.ld, L, P);
                 __syncthreads();
-                if (it.t + step < a.ntiles) { int ptl, ptp; it.peek(1, ptl, ptp); pre.issue(img, a.ld, L, P, ptl * TL, ptp * TP - HP, a.vec_ok != 0); }
+                if (nx.t < a.ntiles) pre.issue(img, a.ld, L, P, nx.tl * TL, nx.tp * TP - HP, a.vec_ok != 0);
                 tile = work;
             }
             const bool full = l0 >= 1 && l0 + TL <= L - 1 && p0 >= 1 && p0 + TP <= P - 1;
@@ -1136,16 +1141,13 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
                 if (full) sweep_tile<FP16 != 0, true>(tile, l0, p0, L, P, e0, e1);
                 else sweep_tile<FP16 != 0, false>(tile, l0, p0, L, P, e0, e1);
             }
-            if ((k & 7) == 7) flush();
+            if ((k & 3) == 3) flush();
             if constexpr (TMA) __syncthreads();  // the stage just read may be refilled from the next iteration on
         }
         }
         flush();
-        double dacc[NLAG];
-#pragma unroll
-        for (int v = 0; v < NLAG; v++) dacc[v] = dsh[v * NT];
         __syncthreads();
-        block_sum<NLAG>(dacc, red);
+        block_sum<NLAG, NT>(dacc, red);
         if (threadIdx.x < NLAG) part[(size_t)sb * NTOT + threadIdx.x] = red[threadIdx.x];
         __syncthreads();
     }
@@ -1257,7 +1259,7 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
             }
             if (per_thread && ++chunks == 64) {  // block-uniform: keeps the f32 partials exact for integer pixels (64 * 65504 < 2^24)
                 __syncthreads();
-                block_sum_f32<NFRM>(tacc, red);
+                block_sum_f32<NFRM, NT>(tacc, red);
                 if (threadIdx.x < NFRM) ftot += red[threadIdx.x];
 #pragma unroll
                 for (int v = 0; v < NFRM; v++) tacc[v] = 0.0f;
@@ -1267,20 +1269,21 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
         __syncthreads();
         if (per_thread) {
             // block reduction through smem (the tile stages and lag accumulators are idle by now): [NFRM][NT] floats, then
-            // four threads per partial sum 64 columns each in f64 (column index rotated by the thread id: conflict-free)
+            // NT / 64 threads per partial sum 64 columns each in f64 (column index rotated by the thread id: conflict-free)
             float* redf = reinterpret_cast<float*>(dsm);
 #pragma unroll
             for (int v = 0; v < NFRM; v++) redf[v * NT + threadIdx.x] = tacc[v];
             __syncthreads();
             static_assert(NFRM * NT * 4 <= sweep_smem(false, false), "ring reduction buffer must fit the smallest sweep smem");
-            if (threadIdx.x < ((4 * NFRM + 31) & ~31)) {  // whole warps (shuffles below); the surplus lanes redo the last partial
-                const float* col = redf + min((int)threadIdx.x >> 2, NFRM - 1) * NT + (threadIdx.x & 3) * (NT / 4);
+            constexpr int TPP = NT / 64;  // threads per partial, 64 columns each
+            if (threadIdx.x < ((TPP * NFRM + 31) & ~31)) {  // whole warps (shuffles below); the surplus lanes redo the last partial
+                const float* col = redf + min((int)threadIdx.x / TPP, NFRM - 1) * NT + (threadIdx.x % TPP) * 64;
                 double sacc = 0.0;
 #pragma unroll 8
-                for (int k = 0; k < NT / 4; k++) sacc += (double)col[(k + threadIdx.x) & (NT / 4 - 1)];
-                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-                if ((threadIdx.x & 3) == 0 && threadIdx.x < 4 * NFRM) red[threadIdx.x >> 2] = sacc;
+                for (int k = 0; k < 64; k++) sacc += (double)col[(k + threadIdx.x) & 63];
+#pragma unroll
+                for (int o = 1; o < TPP; o <<= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                if ((threadIdx.x % TPP) == 0 && threadIdx.x < TPP * NFRM) red[threadIdx.x / TPP] = sacc;
             }
             __syncthreads();
             if (threadIdx.x < NFRM) part[(size_t)fb * NTOT + NLAG + threadIdx.x] = ftot + red[threadIdx.x];
@@ -1304,7 +1307,7 @@ __global__ void __launch_bounds__(NT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_co
     if (threadIdx.x == 0) ts3 = gtime();
     __shared__ double tot[NTOT];
     __shared__ double M[72];
-    block_column_reduce<NTOT, 64, NTOT>(part, nblk, tot, reinterpret_cast<double*>(dsm));
+    block_column_reduce<NTOT, 64, NTOT, NT>(part, nblk, tot, reinterpret_cast<double*>(dsm));
     if (threadIdx.x == 0) ts4 = gtime();
     if (w == 0) {
         if (a.solve_f32) solve_system<OpsF32>(tot, a.scal + b, a.dbg + b, a.transposed, M);
@@ -1655,13 +1658,18 @@ struct DetectArgs {
     unsigned* counter;
     Scal* scal;
     ScalDbg* dbg;
+    float* dbg_u;       // DBG instantiations only: dense L x P planes of u = mask.W (ME: |e_z|.W, the 1 / max|e| scale dropped) and e_u
+    float* dbg_eu;
 };
+// CTAs per SM of the detector (2 x 38 KB of f32 stages + the u tile allow two; three for u8 frames fit but were measured slower)
+__host__ __device__ constexpr int detect_ctas_per_sm(bool) { return 2; }
 
 // one tile of the detector; FULL = the tile lies completely inside the image (its 1-pixel ring may not)
-template <int MASK, bool TR, bool FULL, typename ZT>
-__device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const float* __restrict__ wt, float* __restrict__ ut,
+template <int MASK, bool TR, bool FULL, bool DBG, typename ZT>
+__device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* __restrict__ wt, float* __restrict__ ut,
                                             const float (&c)[8], int l0, int p0,
-                                            int L, int P, float& fd, float& fz, float& fu, const float* __restrict__ mplane = nullptr)
+                                            int L, int P, float& fd, float& fz, float& fu, const float* __restrict__ mplane = nullptr,
+                                            float* __restrict__ dbg_u = nullptr, float* __restrict__ dbg_eu = nullptr)
 {
     // MASK == 2: the NVF mask (p > 3) was computed into a dense L x P plane beforehand
     auto plane_at = [&](int l, int p) { return (l < L && p < P) ? __ldg(mplane + (long long)l * P + p) : 0.0f; };
@@ -1670,7 +1678,8 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const flo
     const int scol = 4 * lane + HP;
     constexpr int ZS = TileGeo<ZT>::STRIDE, ZO = TileGeo<ZT>::OFF;
     float ez[4][4];
-    // ---- phase 1a: my 4 x 4 pixels ----
+    // ---- phase 1a: my 4 x 4 pixels.  (Parking e_z in the W tile's dead cells instead of 16 registers, with three CTAs per SM for
+    // u8 frames, was measured 3-6 % SLOWER: the detector is short of issue slots, not of registers.) ----
     {
         const ZT* zb = zt + (4 * w + 1) * ZS;  // smem line of image line l-1 for r = 0
         float r0[6], r1[6], r2[6];
@@ -1693,6 +1702,11 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const flo
                 uu[j] = __fmul_rn(m, wq[j]);
             }
             *reinterpret_cast<float4*>(ut + (4 * w + r + 1) * SW + scol) = make_float4(uu[0], uu[1], uu[2], uu[3]);
+            if constexpr (DBG) {
+                const int l = l0 + 4 * w + r;
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (l < L && pb + j < P) dbg_u[(long long)l * P + pb + j] = uu[j];
+            }
 #pragma unroll
             for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
         }
@@ -1778,6 +1792,7 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const flo
                 fd = __fmaf_rn(eu, e, fd);
                 fz = __fmaf_rn(e, e, fz);
                 fu = __fmaf_rn(eu, eu, fu);
+                if constexpr (DBG) { if (ok) dbg_eu[(long long)(l0 + 4 * w + r) * P + pb + j] = eu; }
             }
 #pragma unroll
             for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
@@ -1785,8 +1800,8 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, const flo
     }
 }
 
-template <typename PixT, int MASK, bool TR, bool TMA>
-__global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW,
+template <typename PixT, int MASK, bool TR, bool TMA, bool DBG = false>
+__global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_detect(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW,
                                                   const DetectArgs a)
 {
     extern __shared__ __align__(128) unsigned char dsm[];
@@ -1865,8 +1880,8 @@ __global__ void __launch_bounds__(NT, 2) k_detect(const __grid_constant__ CUtens
             }
         }
         float fd = 0.0f, fz = 0.0f, fu = 0.0f;
-        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr);
-        else detect_tile<MASK, TR, false>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr);
+        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true, DBG>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr, a.dbg_u, a.dbg_eu);
+        else detect_tile<MASK, TR, false, DBG>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr, a.dbg_u, a.dbg_eu);
         ddot += (double)fd; dnz += (double)fz; dnu += (double)fu;
         if constexpr (TMA) __syncthreads();  // ut and the stage are rewritten from the next iteration on
     }
@@ -1987,6 +2002,21 @@ __global__ void __launch_bounds__(NT) k_nvfp(const NvfpArgs a)
             }
         }
     }
+}
+
+// debug only (WM_DBG_MASK_ME): max|e| of a dense plane (non-negative floats order like their bit patterns), then mask = |e| / max|e|
+// with the same exact division k_apply uses (Watermark.cpp:213-214)
+static __global__ void k_absmax(const float* __restrict__ e, long long n, unsigned* __restrict__ out)
+{
+    float m = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(e[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+static __global__ void k_scale_abs(float* __restrict__ e, long long n, const unsigned* __restrict__ mx_bits)
+{
+    const float mx = __uint_as_float(*mx_bits), rmx = __frcp_rn(mx);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) e[i] = div_by(fabsf(e[i]), mx, rmx);
 }
 
 // af::rgb2gray(rgb, 0.299, 0.587, 0.114) on planar f32 (main.cpp:142-154,196-197): element-wise, each op rounded
