@@ -250,7 +250,7 @@ def main():
     ap.add_argument("--split-cost", type=int, default=None, help="WM_OPT_SPLIT_COST (A/B: -1 = never partition an unbalanced batch)")
     ap.add_argument("--fhadd", action="store_true", help="sum the rounded Rx/rx products with the FHADD chain instead of HMMA (A/B)")
     ap.add_argument("--host-run", type=int, default=0, help="WM_OPT_HOST_RUN_FRAMES for the e2e video path (A/B)")
-    ap.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e pass (0 = 128 for video, 32 for images)")
+    ap.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e pass (0 = 128 for video, 96 for images)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -574,7 +574,7 @@ def run_e2e(args, pkg, torch, dist, dev, wm, wl, d_in, a_host, c_host, first, wo
     esz = 1 if dtype == "u8" else 4
     dt_code = pkg.U8 if dtype == "u8" else pkg.F32
     layout = pkg.ROW_MAJOR if kind == "video" else pkg.COL_MAJOR
-    n = args.e2e_frames or (128 if kind == "video" else 32)
+    n = args.e2e_frames or (128 if kind == "video" else 96)
     n = min(n, d_in.shape[0])
     L_, P_ = d_in.shape[1], d_in.shape[2]
     if kind == "video":
