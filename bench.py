@@ -645,7 +645,8 @@ def check_sharding(pkg, torch, dist, dev, wm, vctx, base_t, dtype, kind, layout,
                    a_mine, c_mine, d_out):
     """After the timed region: gather the per-frame scalars of all ranks into one array indexed by GLOBAL frame, then prove the sharding:
     (1) rank 0 regenerates the first two frames of every other rank's chunk from their global indices, runs them itself and must get the
-    same scalars bit for bit; (2) video: a detect pass with watermark_interval = 2 must gate on the GLOBAL index across chunk boundaries."""
+    same scalars (to 1e-6 relative: two frames per launch get a different CTA split than a run of eleven, so the f64 sums of the
+    second stage are added in another order); (2) video: a detect pass with watermark_interval = 2 must gate on the GLOBAL index across chunk boundaries."""
     npx = rows * cols
     mine = torch.from_numpy(np.stack([a_mine, c_mine])).to(dev)
     parts = [torch.empty_like(mine) for _ in range(world)]
@@ -665,7 +666,7 @@ def check_sharding(pkg, torch, dist, dev, wm, vctx, base_t, dtype, kind, layout,
         gate = bool(np.all(np.isnan(g2[idx % 2 == 1])) and np.array_equal(g2[idx % 2 == 0], glob[1][idx % 2 == 0]))
         res["interval2_gates_on_global_index"] = gate
     if rank == 0:
-        same = True
+        worst = 0.0
         checked = 0
         for r in range(1, world):
             f_r, _ = pkg.shard_frames(total, r, world)
@@ -681,10 +682,12 @@ def check_sharding(pkg, torch, dist, dev, wm, vctx, base_t, dtype, kind, layout,
                 wm.embed_batch(0, di, di, do, npx, npx, npx, 2, pkg.ME, a2)
                 wm.detect_batch(0, do, npx, 2, pkg.ME, c2)
                 wm.sync(0)
-            same = same and np.array_equal(a2, glob[0][f_r:f_r + 2]) and np.array_equal(c2, glob[1][f_r:f_r + 2])
+            for got, want in ((a2, glob[0][f_r:f_r + 2]), (c2, glob[1][f_r:f_r + 2])):
+                worst = max(worst, float(np.max(np.abs(got - want) / np.abs(want))))
             checked += 2
         res["other_ranks_frames_rerun_on_rank0"] = checked
-        res["gathered_scalars_equal_single_rank_run"] = bool(same)
+        res["rerun_max_rel_diff"] = worst
+        res["gathered_scalars_match_single_rank_run"] = bool(worst <= 1e-6)
         res["a_me_mean"] = float(np.nanmean(glob[0]))
         res["corr_me_mean"] = float(np.nanmean(glob[1]))
     return res
