@@ -660,6 +660,20 @@ __device__ __forceinline__ float nvf_mask(const float* r0, const float* r1, cons
 // The two halo pixels come from the neighbouring lanes' vectors (shuffles) instead of two scalar LDS whose 16-byte
 // lane stride makes them 4-way bank conflicted; only lanes 0 and 31 read their halo from smem (one LDS for both).
 // Must be called by all 32 lanes of a warp.
+__device__ __forceinline__ float lds_f32_if(const float* p, bool pred)
+{
+    float v = 0.0f;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.shared.f32 %0, [%1];\n\t}" : "+f"(v) : "r"(smem_u32(p)), "r"((unsigned)pred));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u8_if(const unsigned char* p, bool pred)
+{
+    unsigned v = 0u;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.shared.u8 %0, [%1];\n\t}" : "+r"(v) : "r"(smem_u32(p)), "r"((unsigned)pred));
+    return v;
+}
+// Must be called by all 32 lanes of a warp.  (A predicated edge load instead of the divergent `if` — see the u8 overload — was measured
+// 1-4 % slower here: as an asm volatile it pins the schedule of the surrounding vector loads.)
 __device__ __forceinline__ void load_win6(float (&w)[6], const float* line, int sc)
 {
     const int lane = threadIdx.x & 31;
@@ -674,6 +688,8 @@ __device__ __forceinline__ void load_win6(float (&w)[6], const float* line, int 
 }
 
 // the same window from a u8 TMA stage line (`line` = row start; the tile's column sc sits at byte U8_OFF + sc, 4-byte aligned)
+// u8 frames: the edge lanes' halo byte is a PREDICATED load (no divergent BSSY / BRA / BSYNC region on every line) followed by two
+// selects on lane constants: +5 % on the u8 apply kernel
 __device__ __forceinline__ void load_win6(float (&w)[6], const unsigned char* line, int sc)
 {
     const int lane = threadIdx.x & 31;
@@ -682,10 +698,10 @@ __device__ __forceinline__ void load_win6(float (&w)[6], const unsigned char* li
     u8x4_to_f32(u, x0, x1, x2, x3);
     float l = __shfl_up_sync(0xffffffffu, x3, 1);
     float r = __shfl_down_sync(0xffffffffu, x0, 1);
-    if (lane == 0 || lane == 31) {
-        const float h = px_f32(line[U8_OFF + sc + (lane == 0 ? -1 : 4)]);
-        if (lane == 0) l = h; else r = h;
-    }
+    const unsigned hb = lds_u8_if(line + U8_OFF + sc + (lane == 0 ? -1 : 4), lane == 0 || lane == 31);
+    const float h = __fadd_rn(__uint_as_float(0x4b000000u | hb), -8388608.0f);
+    l = lane == 0 ? h : l;
+    r = lane == 31 ? h : r;
     w[0] = l; w[1] = x0; w[2] = x1; w[3] = x2; w[4] = x3; w[5] = r;
 }
 
@@ -1363,17 +1379,20 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
         tma_load_3d(stage(s), tmI, tp * TP - (U8T ? U8_LEFT : HP), tl * TL - 1, b, &bars[s]);
         tma_load_3d(stage(s) + IPART, tmW, tp * TP, tl * TL, 0, &bars[s]);
     };
-    TileIter it(blockIdx.x, step, a.tiles_p);
+    // `it` = the tile being processed, `pf` = the tile whose loads are issued this iteration (NST - 1 ahead with TMA, 1 ahead with the
+    // register-prefetched loaders); both advance incrementally (no per-tile division or search loop)
+    TileIter it(blockIdx.x, step, a.tiles_p), pf(blockIdx.x, step, a.tiles_p);
     if constexpr (TMA) {
         if (threadIdx.x == 0) {
             for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
             fence_barrier_init();
         }
         __syncthreads();
-        if (threadIdx.x == 0)
-            for (int s = 0; s < NST - 1; s++)
-                if ((int)blockIdx.x + s * step < a.ntiles) { int ptl, ptp; it.peek(s, ptl, ptp); issue(ptl, ptp, s); }
-    }
+        for (int s = 0; s < NST - 1; s++) {
+            if (threadIdx.x == 0 && pf.t < a.ntiles) issue(pf.tl, pf.tp, s);
+            pf.next();
+        }
+    } else pf.next();
     StagePos<NST> pos;
     TilePrefetch<PixT, TL + 2> pre;
     WTilePrefetch wpre;
@@ -1383,16 +1402,14 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
             wpre.issue(a.W, a.L, a.P, it.tl * TL, it.tp * TP, a.w_vec_ok != 0);
         }
     }
-    for (; it.t < a.ntiles; it.next()) {
+    for (; it.t < a.ntiles; it.next(), pf.next()) {
         const int l0 = it.tl * TL, p0 = it.tp * TP;
         TileT* tile;
         float* wtile;
         if constexpr (TMA) {
-            if (threadIdx.x == 0 && it.t + (NST - 1) * step < a.ntiles) {
-                int ptl, ptp;
-                it.peek(NST - 1, ptl, ptp);
+            if (threadIdx.x == 0 && pf.t < a.ntiles) {
                 fence_proxy_async();
-                issue(ptl, ptp, pos.ahead(NST - 1));
+                issue(pf.tl, pf.tp, pos.ahead(NST - 1));
             }
             mbar_wait(&bars[pos.s], pos.ph);
             wtile = reinterpret_cast<float*>(stage(pos.s) + IPART);
@@ -1406,11 +1423,9 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
             pre.commit(tile, img, a.ld, a.L, a.P);
             wpre.commit(wtile);
             __syncthreads();
-            if (it.t + step < a.ntiles) {
-                int ptl, ptp;
-                it.peek(1, ptl, ptp);
-                pre.issue(img, a.ld, a.L, a.P, ptl * TL - 1, ptp * TP - HP, a.vec_ok != 0);
-                wpre.issue(a.W, a.L, a.P, ptl * TL, ptp * TP, a.w_vec_ok != 0);
+            if (pf.t < a.ntiles) {
+                pre.issue(img, a.ld, a.L, a.P, pf.tl * TL - 1, pf.tp * TP - HP, a.vec_ok != 0);
+                wpre.issue(a.W, a.L, a.P, pf.tl * TL, pf.tp * TP, a.w_vec_ok != 0);
             }
         }
         body(tile, wtile, l0, p0);
@@ -1834,17 +1849,18 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
         tma_load_3d(stage(s), &tmZ, tp * TP - (U8T ? U8_LEFT : HP), tl * TL - 2, b, &bars[s]);
         tma_load_3d(stage(s) + ZPART, &tmW, tp * TP - HP, tl * TL - 1, 0, &bars[s]);
     };
-    TileIter it(blockIdx.x, step, a.tiles_p);
+    TileIter it(blockIdx.x, step, a.tiles_p), pf(blockIdx.x, step, a.tiles_p);  // current tile / tile whose loads are issued now
     if constexpr (TMA) {
         if (threadIdx.x == 0) {
             for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
             fence_barrier_init();
         }
         __syncthreads();
-        if (threadIdx.x == 0)
-            for (int s = 0; s < NST - 1; s++)
-                if ((int)blockIdx.x + s * step < a.ntiles) { int ptl, ptp; it.peek(s, ptl, ptp); issue(ptl, ptp, s); }
-    }
+        for (int s = 0; s < NST - 1; s++) {
+            if (threadIdx.x == 0 && pf.t < a.ntiles) issue(pf.tl, pf.tp, s);
+            pf.next();
+        }
+    } else pf.next();
     double ddot = 0.0, dnz = 0.0, dnu = 0.0;
     StagePos<NST> pos;
     TilePrefetch<PixT, TL + 4> zpre;
@@ -1855,16 +1871,14 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
             wpre.issue(a.W, P, L, P, it.tl * TL - 1, it.tp * TP - HP, a.w_vec_ok != 0);
         }
     }
-    for (; it.t < a.ntiles; it.next()) {
+    for (; it.t < a.ntiles; it.next(), pf.next()) {
         const int l0 = it.tl * TL, p0 = it.tp * TP;
         ZT* zt;     // (TL+4) lines from l0-2
         float* wt;  // (TL+2) x SW lines l0-1 ..
         if constexpr (TMA) {
-            if (threadIdx.x == 0 && it.t + (NST - 1) * step < a.ntiles) {
-                int ptl, ptp;
-                it.peek(NST - 1, ptl, ptp);
+            if (threadIdx.x == 0 && pf.t < a.ntiles) {
                 fence_proxy_async();
-                issue(ptl, ptp, pos.ahead(NST - 1));
+                issue(pf.tl, pf.tp, pos.ahead(NST - 1));
             }
             mbar_wait(&bars[pos.s], pos.ph);
             wt = reinterpret_cast<float*>(stage(pos.s) + ZPART);
@@ -1878,11 +1892,9 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
             zpre.commit(zt, img, a.ld, L, P);
             wpre.commit(wt, a.W, P, L, P);
             __syncthreads();
-            if (it.t + step < a.ntiles) {
-                int ptl, ptp;
-                it.peek(1, ptl, ptp);
-                zpre.issue(img, a.ld, L, P, ptl * TL - 2, ptp * TP - HP, a.vec_ok != 0);
-                wpre.issue(a.W, P, L, P, ptl * TL - 1, ptp * TP - HP, a.w_vec_ok != 0);
+            if (pf.t < a.ntiles) {
+                zpre.issue(img, a.ld, L, P, pf.tl * TL - 2, pf.tp * TP - HP, a.vec_ok != 0);
+                wpre.issue(a.W, P, L, P, pf.tl * TL - 1, pf.tp * TP - HP, a.w_vec_ok != 0);
             }
         }
         float fd = 0.0f, fz = 0.0f, fu = 0.0f;
