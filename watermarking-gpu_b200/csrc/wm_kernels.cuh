@@ -1402,20 +1402,22 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
             wpre.issue(a.W, a.L, a.P, it.tl * TL, it.tp * TP, a.w_vec_ok != 0);
         }
     }
+    bool patched = false;  // the previous tile's stage was patched by fix_border (generic-proxy writes): fence before TMA refills it
     for (; it.t < a.ntiles; it.next(), pf.next()) {
         const int l0 = it.tl * TL, p0 = it.tp * TP;
         TileT* tile;
         float* wtile;
         if constexpr (TMA) {
             if (threadIdx.x == 0 && pf.t < a.ntiles) {
-                fence_proxy_async();
+                if (patched) fence_proxy_async();
                 issue(pf.tl, pf.tp, pos.ahead(NST - 1));
             }
             mbar_wait(&bars[pos.s], pos.ph);
             wtile = reinterpret_cast<float*>(stage(pos.s) + IPART);
             tile = reinterpret_cast<TileT*>(stage(pos.s));
             pos.next();
-            if (tile_on_frame<TL + 2>(l0 - 1, p0 - HP, a.L, a.P)) { fix_border<TL + 2>(tile, l0 - 1, p0 - HP, a.L, a.P); __syncthreads(); }
+            patched = tile_on_frame<TL + 2>(l0 - 1, p0 - HP, a.L, a.P);
+            if (patched) { fix_border<TL + 2>(tile, l0 - 1, p0 - HP, a.L, a.P); __syncthreads(); }
         } else {
             tile = reinterpret_cast<TileT*>(dsm);
             wtile = reinterpret_cast<float*>(dsm) + SZ_I34 / 4;
@@ -1632,7 +1634,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
                         bv[0] = r1[1]; bv[1] = r1[2]; bv[2] = r1[3]; bv[3] = r1[4];
                     } else {
                         const PixT* br = bas + (long long)ch * a.base_pstride + (long long)l * a.base_ld + pb;
-                        if (base_vec && (FULL || nvalid >= 4)) {
+                        if (FULL || (base_vec && nvalid >= 4)) {
                             if constexpr (sizeof(PixT) == 4) {
                                 const float4 v = __ldg(reinterpret_cast<const float4*>(br));
                                 bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
@@ -1648,12 +1650,14 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
 #pragma unroll
                     for (int j = 0; j < 4; j++) ov[j] = fminf(fmaxf(__fmaf_rn(au[j], av, bv[j]), 0.0f), 255.0f);  // af::clamp
                     OutT* orow = out + (long long)ch * a.out_pstride + (long long)l * a.out_ld + pb;
-                    store4<OutT>(orow, ov, out_vec && (FULL || nvalid >= 4), nvalid);
+                    store4<OutT>(orow, ov, FULL || (out_vec && nvalid >= 4), nvalid);
                 }
             }, MASK == 2 ? MaskSrc{a.maskp + (long long)b * a.mask_bstride + (long long)(l0 + 4 * w) * P + pb, P, L - (l0 + 4 * w), P - pb}
                          : MaskSrc{nullptr, 0, 0, 0});
         };
-        if (l0 + TL <= L && p0 + TP <= P) run(BoolTag<true>{}); else run(BoolTag<false>{});
+        // the fast variant (FULL) has every test folded at compile time: the tile lies inside the image AND base / out rows can be accessed as
+        // vectors (before, the per-line `vec` tests kept both the vector and the byte-wise stores, and a branch between them, in the hot loop)
+        if (l0 + TL <= L && p0 + TP <= P && out_vec && (SB || base_vec)) run(BoolTag<true>{}); else run(BoolTag<false>{});
     });
 }
 
@@ -1871,20 +1875,22 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
             wpre.issue(a.W, P, L, P, it.tl * TL - 1, it.tp * TP - HP, a.w_vec_ok != 0);
         }
     }
+    bool patched = false;  // the previous tile's stage was patched by fix_border: fence before TMA refills it
     for (; it.t < a.ntiles; it.next(), pf.next()) {
         const int l0 = it.tl * TL, p0 = it.tp * TP;
         ZT* zt;     // (TL+4) lines from l0-2
         float* wt;  // (TL+2) x SW lines l0-1 ..
         if constexpr (TMA) {
             if (threadIdx.x == 0 && pf.t < a.ntiles) {
-                fence_proxy_async();
+                if (patched) fence_proxy_async();
                 issue(pf.tl, pf.tp, pos.ahead(NST - 1));
             }
             mbar_wait(&bars[pos.s], pos.ph);
             wt = reinterpret_cast<float*>(stage(pos.s) + ZPART);
             zt = reinterpret_cast<ZT*>(stage(pos.s));
             pos.next();
-            if (tile_on_frame<TL + 4>(l0 - 2, p0 - HP, L, P)) { fix_border<TL + 4>(zt, l0 - 2, p0 - HP, L, P); __syncthreads(); }
+            patched = tile_on_frame<TL + 4>(l0 - 2, p0 - HP, L, P);
+            if (patched) { fix_border<TL + 4>(zt, l0 - 2, p0 - HP, L, P); __syncthreads(); }
         } else {
             zt = reinterpret_cast<ZT*>(dsm);
             wt = reinterpret_cast<float*>(dsm) + SZ_I36 / 4;
