@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--no-tma", action="store_true", help="plain register-prefetched tile loaders instead of TMA (A/B)")
     ap.add_argument("--split-cost", type=int, default=None, help="WM_OPT_SPLIT_COST (A/B: -1 = never partition an unbalanced batch)")
     ap.add_argument("--fhadd", action="store_true", help="sum the rounded Rx/rx products with the FHADD chain instead of HMMA (A/B)")
+    ap.add_argument("--no-tma-store", action="store_true", help="WM_OPT_TMA_STORE = 0: apply kernel output through per-thread vector stores (A/B)")
     ap.add_argument("--host-run", type=int, default=0, help="WM_OPT_HOST_RUN_FRAMES for the e2e video path (A/B)")
     ap.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e pass (0 = 128 for video, 96 for images)")
     args = ap.parse_args()
@@ -354,6 +355,8 @@ def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, secondary=
         wm.set_option(pkg.OPT_SPLIT_COST, args.split_cost)
     if args.host_run:
         wm.set_option(pkg.OPT_HOST_RUN_FRAMES, args.host_run)
+    if args.no_tma_store:
+        wm.set_option(pkg.OPT_TMA_STORE, 0)
     dt_code = pkg.U8 if dtype == "u8" else pkg.F32
     esz = 1 if dtype == "u8" else 4
     # image workloads: ArrayFire layout (column-major); video: row-major Y planes
@@ -476,6 +479,12 @@ def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, secondary=
     peak, peak_src = peaks()
     traffic, traffic_src = load_traffic()
     tr_frame = traffic.get(wl, {}).get("per_frame", {})
+    in_frame = traffic.get(wl, {}).get("warp_instr_per_frame", {})
+    # the bound the kernels actually sit on: warp-instruction issue.  Peak = 4 schedulers x SMs x SM clock (one warp instruction per
+    # scheduler per clock); achieved = warp instructions ncu counted per frame x frames per launch / the launch's CUDA-event time
+    props = torch.cuda.get_device_properties(dev)
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    issue_peak = 4.0 * props.multi_processor_count * sm_mhz * 1e6
     kern = []
     calls_frames = per_rank * k_steps            # frames one kernel family covered per op kind in the bracketed passes
     for name, (n, tot_ms) in ktimes.items():
@@ -492,6 +501,10 @@ def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, secondary=
         if name in tr_frame:
             rec["traffic"] = tr_frame[name] * frames_per_launch
             rec["frac_dram"] = rec["traffic"] / (avg_ms * 1e-3) / 1e9 / peak
+        if name in in_frame:
+            rec["warp_instr_per_launch"] = in_frame[name] * frames_per_launch
+            rec["issue_frac"] = rec["warp_instr_per_launch"] / (avg_ms * 1e-3) / issue_peak
+            rec["instr_per_px"] = in_frame[name] * 32.0 / npx
         if rec["frac"] > 1.05:
             rec["accounting_error"] = "fraction above the HBM peak: the byte count is wrong"
         kern.append(rec)
@@ -501,6 +514,8 @@ def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, secondary=
     if dom:
         roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": dom.get("traffic"), "frac_dram": dom.get("frac_dram"), "peak_source": peak_src,
+                "issue_frac": dom.get("issue_frac"), "instr_per_px": dom.get("instr_per_px"),
+                "issue_peak_winst_per_s": issue_peak,
                 "alg_bytes_per_launch": dom["alg_bytes_per_launch"], "avg_launch_ms": dom["avg_ms"], "frames_per_launch": dom["frames_per_launch"],
                 "traffic_source": traffic_src and traffic_src + " (ncu dram__bytes_read.sum + dram__bytes_write.sum per frame x frames per launch)",
                 "accounting": "image bytes once per frame + W once per launch; kernel time = CUDA-event bracket of one op call",

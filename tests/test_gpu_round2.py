@@ -388,3 +388,42 @@ def test_detector_planes_bit_exact(wmb, oracle, rows, cols, layout):
             assert np.array_equal(m, pm["mask"])
         wm.debug_set_coeffs(None)
     wm.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the apply kernel's two output paths — TMA stores (WM_OPT_TMA_STORE, default) and per-thread vector stores — must give the same bits
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["f32", "u8"])
+@pytest.mark.parametrize("rows,cols,B", [(64, 128, 1), (96, 160, 5), (200, 384, 3), (270, 480, 2), (1080, 1920, 2)])
+def test_tma_store_variant_same_bits(wmb, oracle, rows, cols, B, dtype):
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    imgs = np.stack([util.natural_image(rows, cols, seed=1100 + b, integer=(dtype == "u8")) for b in range(B)])
+    if dtype == "f32":
+        imgs = imgs.astype(np.float32)
+    dt = wmb.U8 if dtype == "u8" else wmb.F32
+    L = wmb.lib()
+    din = L.wm_dev_alloc(wm._h, imgs.nbytes)
+    dout = L.wm_dev_alloc(wm._h, imgs.nbytes)
+    L.wm_dev_upload(wm._h, din, imgs.ctypes.data, imgs.nbytes)
+    di = wmb.image_desc(din, rows, cols, wmb.ROW_MAJOR, dt)
+    do = wmb.image_desc(dout, rows, cols, wmb.ROW_MAJOR, dt)
+    n = rows * cols
+    res = []
+    for ts in (0, 1):
+        wm.set_option(wmb.OPT_TMA_STORE, ts)
+        for mask in (wmb.ME, wmb.NVF):
+            sent = np.full_like(imgs, 7)
+            L.wm_dev_upload(wm._h, dout, sent.ctypes.data, sent.nbytes)
+            a = np.zeros(B, np.float32)
+            wm.embed_batch(0, di, di, do, n, n, n, B, mask, a)
+            wm.sync(0)
+            o = np.zeros_like(imgs)
+            L.wm_dev_download(wm._h, o.ctypes.data, dout, o.nbytes)
+            res.append((a, o))
+    for k in range(2):
+        assert np.array_equal(res[k][0], res[2 + k][0]) and np.array_equal(res[k][1], res[2 + k][1])
+    assert not np.array_equal(res[0][1], imgs)
+    L.wm_dev_free(wm._h, din)
+    L.wm_dev_free(wm._h, dout)
+    wm.close()

@@ -67,6 +67,7 @@ def main():
              "times differ from bench.py's CUDA-event times; DRAM bytes and instruction counts are exact." % os.path.basename(rep), "",
              "| kernel | " + " | ".join(c[1] for c in cols) + " | instr/px | top stalls (per issue) |", "|---|" + "---|" * (len(cols) + 2)]
     traffic = {}
+    instr = {}
     seen = set()
     for r in data:
         full = r[ix["Kernel Name"]]
@@ -85,6 +86,7 @@ def main():
             b = to_bytes(fnum(r[ix["dram__bytes_read.sum"]]), units[ix["dram__bytes_read.sum"]]) + \
                 to_bytes(fnum(r[ix["dram__bytes_write.sum"]]), units[ix["dram__bytes_write.sum"]])
             traffic.setdefault(kn, []).append(b / frames)
+            instr.setdefault(kn, []).append(fnum(r[ix["smsp__inst_executed.sum"]]) / frames)
     # instr/px needs the pixel count: filled by the caller's knowledge of the workload
     px = {"image1080p": 1080 * 1920, "video4k": 2160 * 3840, "image4k": 2160 * 3840, "image512": 512 * 512}.get(wl)
     if px:
@@ -104,7 +106,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     t = json.load(open(tpath)) if os.path.exists(tpath) else {}
     t[wl] = {"unit": "DRAM bytes (read+write) per frame per launch, from ncu --set full", "source": tag,
-             "per_frame": {k: sum(v) / len(v) for k, v in traffic.items()}}
+             "per_frame": {k: sum(v) / len(v) for k, v in traffic.items()},
+             "warp_instr_per_frame": {k: sum(v) / len(v) for k, v in instr.items()}}
     json.dump(t, open(tpath, "w"), indent=1)
     if launches:
         rows = [r for r in csv.reader(open(launches)) if r and not r[0].startswith("==")]

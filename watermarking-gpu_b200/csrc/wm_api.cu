@@ -72,6 +72,7 @@ struct wm_ctx {
     std::shared_ptr<WShared> w;
     Slot slots[NSLOTS];
     int opt_fp16 = 1, opt_timing = 0, opt_tma = 1, opt_serial = 0, opt_mma = 1, opt_f32_solve = 0;
+    int opt_tma_store = 1;   // WM_OPT_TMA_STORE: apply kernel output through TMA stores where the shape allows (+8..10 % on the apply kernel)
     int opt_host_run = 4;    // frames per run of the video driver's host-frame path (WM_OPT_HOST_RUN_FRAMES)
     int opt_split_cost = 8;  // tile-times one more launch is assumed to cost when a batch is partitioned (WM_OPT_SPLIT_COST)
     bool inject_coef = false;
@@ -360,7 +361,7 @@ EncodeTiledFn encode_fn()
 }
 // f32 / u8 tensor (pixel, line, image) with a (boxP x boxL x 1) box; out-of-bounds elements are zero-filled.
 // boxP is given in f32 terms (SW or TP); u8 image boxes are U8_ROW (144) pixels wide so that the row is 16-byte sized.
-bool make_tmap(CUtensorMap* tm, int dtype, const void* ptr, int P, int L, int B, long long ld, long long bstride, int boxP, int boxL)
+bool make_tmap(CUtensorMap* tm, int dtype, const void* ptr, int P, int L, int B, long long ld, long long bstride, int boxP, int boxL, int u8_box = U8_ROW)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
@@ -368,7 +369,7 @@ bool make_tmap(CUtensorMap* tm, int dtype, const void* ptr, int P, int L, int B,
     const cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)L, (cuuint64_t)std::max(B, 1)};
     const long long bs = (B > 1 && bstride > 0) ? bstride : (long long)L * ld;
     const cuuint64_t strides[2] = {(cuuint64_t)ld * es, (cuuint64_t)bs * es};
-    const cuuint32_t box[3] = {(cuuint32_t)(dtype == WM_F32 ? boxP : U8_ROW), (cuuint32_t)boxL, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(dtype == WM_F32 ? boxP : u8_box), (cuuint32_t)boxL, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return fn(tm, dtype == WM_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), dims,
               strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -535,9 +536,16 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     CU(cudaGetLastError());
     {
         KTimer t(ctx, s, mask == WM_MASK_ME ? WM_K_APPLY : WM_K_APPLY_NVF);
+        // WM_OPT_TMA_STORE (default on): gray output of the same dtype, base = input, TMA-loadable input and a TMA-storable output
+        CUtensorMap tmO;
+        memset(&tmO, 0, sizeof tmO);
+        bool ts = ctx->opt_tma_store && tma && ea.same_base && vo.dtype == vi.dtype && vo.channels == 1 && !planes && tma_ok(ctx, vo, out_stride, batch);
+        if (ts) ts = make_tmap(&tmO, vo.dtype, vo.ptr, g.P, g.L, batch, vo.ld, out_stride, TP, TL, TP);
         for (const SubBatch& sb : pl.embed) {
             ea.b0 = sb.b0; ea.nblk_base = sb.base; ea.nblk_extra = sb.extra;
-            launch_apply(vi.dtype, vo.dtype, kmask, vi.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmI, tmW, ea);
+            const dim3 grid(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb);
+            if (ts) launch_apply_ts(vi.dtype, kmask, vi.transposed, grid, s.stream, tmI, tmW, tmO, ea);
+            else launch_apply(vi.dtype, vo.dtype, kmask, vi.transposed, tma, grid, s.stream, tmI, tmW, ea);
         }
     }
     CU(cudaGetLastError());
@@ -826,7 +834,7 @@ int wm_clone(const wm_ctx* src, wm_ctx** out)
     ctx->p = src->p; ctx->psnr = src->psnr; ctx->strength = src->strength;
     ctx->w = src->w;
     ctx->opt_fp16 = src->opt_fp16; ctx->opt_mma = src->opt_mma; ctx->opt_split_cost = src->opt_split_cost; ctx->opt_timing = src->opt_timing; ctx->opt_tma = src->opt_tma;
-    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run;
+    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run; ctx->opt_tma_store = src->opt_tma_store;
     const int rc = init_slots(ctx, nullptr);
     if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
     *out = ctx;
@@ -875,6 +883,7 @@ int wm_set_option(wm_ctx* ctx, int option, int value)
     case WM_OPT_CUDA_GRAPHS: ctx->opt_graphs = value != 0; return WM_OK;
     case WM_OPT_MMA_ACCUM: ctx->opt_mma = value != 0; return WM_OK;
     case WM_OPT_HOST_RUN_FRAMES: ctx->opt_host_run = std::max(1, std::min(value, 64)); return WM_OK;
+    case WM_OPT_TMA_STORE: ctx->opt_tma_store = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_F32_SOLVE: ctx->opt_f32_solve = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_SPLIT_COST: ctx->opt_split_cost = value < 0 ? 1 << 28 : value; return WM_OK;
     default: return fail(ctx, WM_ERR_ARG, "unknown option");

@@ -16,6 +16,16 @@ void launch_apply_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtenso
     if (a.same_base) launch_apply_s<PixT, OutT, TMA, true>(mask, tr, grid, st, tmI, tmW, a);
     else launch_apply_s<PixT, OutT, TMA, false>(mask, tr, grid, st, tmI, tmW, a);
 }
+// A/B variant with TMA stores (gray, same base, TMA loads, 3x3 masks)
+void launch_apply_ts(int dtype, int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const CUtensorMap& tmO, const EmbedArgs& a)
+{
+#define WM_TS(PIX, SM)                                                                                                                 \
+    if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_apply_ts<PIX, 0, true>), SM, tmI, tmW, tmO, a); else WM_LAUNCH((k_apply_ts<PIX, 0, false>), SM, tmI, tmW, tmO, a); } \
+    else { if (tr) WM_LAUNCH((k_apply_ts<PIX, 1, true>), SM, tmI, tmW, tmO, a); else WM_LAUNCH((k_apply_ts<PIX, 1, false>), SM, tmI, tmW, tmO, a); }
+    if (dtype == WM_F32) { WM_TS(float, embed_smem(true, false)) } else { WM_TS(uint8_t, embed_smem(true, true) + 2 * TL * TP) }
+#undef WM_TS
+}
+
 void launch_apply(int in_dtype, int out_dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmI,
                   const CUtensorMap& tmW, const EmbedArgs& a)
 {

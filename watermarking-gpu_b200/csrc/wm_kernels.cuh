@@ -164,6 +164,15 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
                  : "memory");
 }
 
+// TMA store of a tile (smem -> global, SASS UTMASTG): bulk-group completion; out-of-image cells of the box are clipped by the hardware
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int c1, int c2, const void* src)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src)) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
 // round-robin tile walk t = first, first + step, ... with (tl, tp) kept incrementally (no per-tile division)
 struct TileIter {
     int t, tl, tp, step, step_l, step_p, tiles_p;
@@ -1659,6 +1668,89 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
         // vectors (before, the per-line `vec` tests kept both the vector and the byte-wise stores, and a branch between them, in the hot loop)
         if (l0 + TL <= L && p0 + TP <= P && out_vec && (SB || base_vec)) run(BoolTag<true>{}); else run(BoolTag<false>{});
     });
+}
+
+// ---- k_apply_ts: the apply kernel of the common case (WM_OPT_TMA_STORE, default on) — gray output, base = input, TMA-loaded tiles: the clamped output goes to an
+// smem tile and leaves through a TMA store (cp.async.bulk.tensor smem -> global) instead of per-thread STG.  f32: the output overwrites
+// the W tile's own cells in place (each thread reads its W values, then owns those cells), so no extra smem; u8: two 4 KB byte tiles.
+// Same bits as k_apply, 8-10 % faster (profiles/r2_tma_store_ab.md): the per-line 64-bit store addressing leaves the instruction stream.
+template <typename PixT, int MASK, bool TR>
+__global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply_ts(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
+                                                                    const __grid_constant__ CUtensorMap tmO, const EmbedArgs a)
+{
+    extern __shared__ __align__(128) unsigned char dsm[];
+    __shared__ __align__(8) uint64_t bars[EMBED_NST_U8];
+    constexpr bool U8T = sizeof(PixT) == 1;
+    constexpr int NST = U8T ? EMBED_NST_U8 : EMBED_NST;
+    constexpr int STG = embed_stage(U8T), IPART = U8T ? U8_I34 : SZ_I34;
+    using TileT = typename std::conditional<U8T, unsigned char, float>::type;
+    const int b = blockIdx.y + a.b0;
+    const Scal* sc = a.scal + b;
+    const int step = blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y);
+    if ((int)blockIdx.x >= step) return;
+    if (sc->status != 0) { copy_base_through<PixT, PixT>(a); return; }
+    const int L = a.L, P = a.P;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
+    const float av = sc->a, mx = sc->emax;
+    const float rmx = MASK == 0 ? __frcp_rn(mx) : 0.0f;
+    auto stage = [&](int s) { return dsm + (size_t)s * STG; };
+    unsigned char* const otiles = dsm + (size_t)NST * STG;  // u8 only: 2 x (TL x TP) bytes
+    auto issue = [&](int tl, int tp, int s) {  // thread 0 only
+        mbar_expect_tx(&bars[s], (U8T ? (TL + 2) * U8_ROW : (TL + 2) * SW * 4) + SZ_WT);
+        tma_load_3d(stage(s), &tmI, tp * TP - (U8T ? U8_LEFT : HP), tl * TL - 1, b, &bars[s]);
+        tma_load_3d(stage(s) + IPART, &tmW, tp * TP, tl * TL, 0, &bars[s]);
+    };
+    TileIter it(blockIdx.x, step, a.tiles_p), pf(blockIdx.x, step, a.tiles_p);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    for (int s = 0; s < NST - 1; s++) {
+        if (threadIdx.x == 0 && pf.t < a.ntiles) issue(pf.tl, pf.tp, s);
+        pf.next();
+    }
+    StagePos<NST> pos;
+    int k = 0;
+    for (; it.t < a.ntiles; it.next(), pf.next(), k++) {
+        const int l0 = it.tl * TL, p0 = it.tp * TP;
+        if (threadIdx.x == 0 && pf.t < a.ntiles) {
+            // the stage about to be refilled is the previous tile's: its W cells were the source of that tile's store (f32), and its
+            // image part may have been patched
+            if (!U8T) tma_store_wait_read<0>();
+            fence_proxy_async();
+            issue(pf.tl, pf.tp, pos.ahead(NST - 1));
+        }
+        mbar_wait(&bars[pos.s], pos.ph);
+        float* wtile = reinterpret_cast<float*>(stage(pos.s) + IPART);
+        TileT* tile = reinterpret_cast<TileT*>(stage(pos.s));
+        pos.next();
+        if (tile_on_frame<TL + 2>(l0 - 1, p0 - HP, L, P)) { fix_border<TL + 2>(tile, l0 - 1, p0 - HP, L, P); __syncthreads(); }
+        unsigned char* const ot = otiles + (size_t)(k & 1) * (TL * TP);
+        mask_lines<MASK, TR>(tile, wtile, c, [&](int r, const float (&m)[4], const float (&wq)[4], const float (&r1)[6]) {
+            float ov[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float au = __fmul_rn(MASK == 0 ? div_by(m[j], mx, rmx) : m[j], wq[j]);
+                ov[j] = fminf(fmaxf(__fmaf_rn(au, av, r1[j + 1]), 0.0f), 255.0f);
+            }
+            if constexpr (U8T) {
+                const unsigned u0 = __float_as_uint(__fadd_rz(ov[0], 8388608.0f)), u1 = __float_as_uint(__fadd_rz(ov[1], 8388608.0f));
+                const unsigned u2 = __float_as_uint(__fadd_rz(ov[2], 8388608.0f)), u3 = __float_as_uint(__fadd_rz(ov[3], 8388608.0f));
+                *reinterpret_cast<unsigned*>(ot + (4 * w + r) * TP + 4 * lane) = __byte_perm(__byte_perm(u0, u1, 0x0040), __byte_perm(u2, u3, 0x0040), 0x5410);
+            } else {
+                *reinterpret_cast<float4*>(wtile + (4 * w + r) * TP + 4 * lane) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+            }
+        });
+        fence_proxy_async();  // every writer: generic-proxy smem writes -> visible to the TMA store
+        if (U8T && threadIdx.x == 0) tma_store_wait_read<0>();  // the store of tile k-1 (the other byte tile) has left smem before tile k+1 writes it
+        __syncthreads();
+        if (threadIdx.x == 0) tma_store_3d(&tmO, p0, l0, b, U8T ? (const void*)ot : (const void*)wtile);
+    }
+    if (threadIdx.x == 0) tma_store_wait_read<0>();  // smem must outlive the last store's read
 }
 
 // ================================================================================================
