@@ -42,12 +42,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 WORKLOADS = {
     # name: (rows, cols, frames per API call, calls per step, kind, dtype).  Frames per call divide the resident CTA counts of a launch
     # (3 x 148 for sweep / stats / apply, 2 x 148 for the detector); calls per step make the timed region of a default run >= 1 s.
-    "video4k": (2160, 3840, 1036, 1, "video", "u8"),      # one wm_process_frames call over the rank's whole chunk (runs of 10-11 frames inside)
-    "image1080p": (1080, 1920, 148, 10, "image", "f32"),
-    "image4k": (2160, 3840, 37, 10, "image", "f32"),
-    "image8k": (4320, 7680, 4, 24, "image", "f32"),
-    "image512": (512, 512, 296, 20, "image", "f32"),
-    "batch256": (256, 256, 4096, 3, "image", "f32"),
+    "video4k": (2160, 3840, 1184, 1, "video", "u8"),      # one wm_process_frames call over the rank's whole chunk (runs of 10-11 frames inside)
+    "image1080p": (1080, 1920, 148, 12, "image", "f32"),
+    "image4k": (2160, 3840, 37, 12, "image", "f32"),
+    "image8k": (4320, 7680, 4, 28, "image", "f32"),
+    "image512": (512, 512, 296, 24, "image", "f32"),
+    "batch256": (256, 256, 4096, 4, "image", "f32"),
 }
 # algorithmic (compulsory) bytes per pixel of ONE frame in each kernel family: image bytes read + output bytes written; W (4 B/px) is
 # added once per call, not per frame
