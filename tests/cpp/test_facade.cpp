@@ -96,6 +96,16 @@ int main(int argc, char** argv)
             const float c = detectFrameWatermark(ctx, count, &f, false);
             std::printf("frame_corr_%d %.9g\n", i, c);
         }
+        // the batched in-memory form over two contexts (two "GPUs": both on device 0 here) must reproduce the per-frame results
+        {
+            const Watermark second(watermarkObj);
+            std::vector<unsigned char> marked2((size_t)nframes * rows * cols);
+            std::vector<float> a2((size_t)nframes), c2((size_t)nframes);
+            processFramesInMemory({&watermarkObj, &second}, (int)rows, (int)cols, 2, linesize, WM_VIDEO_EMBED, frames.data(), marked2.data(), 0, nframes, a2.data());
+            processFramesInMemory({&watermarkObj, &second}, (int)rows, (int)cols, 2, (int)cols, WM_VIDEO_DETECT, marked2.data(), nullptr, 0, nframes, c2.data());
+            std::printf("batched_equal_pixels %d\n", (int)(marked2 == marked));
+            for (int i = 0; i < n; i++) std::printf("batched_corr_%d %.9g\n", i, c2[(size_t)i] == c2[(size_t)i] ? c2[(size_t)i] : 0.0f);
+        }
         wm_host_free_pinned(pinned);
     } catch (const std::exception& e) {
         std::cerr << "exception: " << e.what();

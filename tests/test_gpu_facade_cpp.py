@@ -51,3 +51,7 @@ def test_cpp_facade_against_oracle(wmb, oracle, tmp_path):
         else:  # gated off: Y plane passes through with the padding dropped, no detection
             assert int(got["frame_sum_%d" % i]) == int(frames[i, :, :cols].astype(np.int64).sum())
             assert float(got["frame_corr_%d" % i]) == 0.0
+    # processFramesInMemory over two contexts (chunks of the global index, one host thread each) == the per-frame functions
+    assert got["batched_equal_pixels"].strip() == "1"
+    for i in range(nframes):
+        assert float(got["batched_corr_%d" % i]) == float(got["frame_corr_%d" % i])

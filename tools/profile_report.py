@@ -17,6 +17,8 @@ KMAP = [("k_sweep", "rx_sweep"), ("k_stats<float, 0", "me_stats"), ("k_stats<uns
         ("k_stats<float, 1", "nvf_stats"), ("k_stats<unsigned char, 1", "nvf_stats"),
         ("k_apply<float, float, 0", "me_apply"), ("k_apply<unsigned char, unsigned char, 0", "me_apply"),
         ("k_apply<float, float, 1", "nvf_apply"), ("k_apply<unsigned char, unsigned char, 1", "nvf_apply"),
+        ("k_apply_ts<float, 0", "me_apply"), ("k_apply_ts<unsigned char, 0", "me_apply"),
+        ("k_apply_ts<float, 1", "nvf_apply"), ("k_apply_ts<unsigned char, 1", "nvf_apply"),
         ("k_detect<float, 0", "me_detect"), ("k_detect<unsigned char, 0", "me_detect"),
         ("k_detect<float, 1", "nvf_detect"), ("k_detect<unsigned char, 1", "nvf_detect")]
 

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <functional>
 #include <iostream>
+#include <vector>
 
 #include "Watermark.hpp"
 
@@ -92,4 +93,41 @@ inline float detectFrameWatermark(const VideoProcessingContext& data, int& frame
     }
     framesCount++;
     return correlation;
+}
+
+// Batched form of the two frame functions for frames that already sit in HOST memory (a decoded clip): every
+// watermarkInterval-th frame of [firstIndex, firstIndex + nFrames) goes through ME embed (mode WM_VIDEO_EMBED), detection
+// (WM_VIDEO_DETECT) or both (WM_VIDEO_EMBED_VERIFY: scalars[i] = strength, scalars[nFrames + i] = correlation) in runs of several
+// frames per launch sequence with copies and kernels overlapped, on ONE GPU (one Watermark object) or SEVERAL (one object per
+// device: contiguous chunks of the global frame index, one host thread per device, the gate of main.cpp:346,395 on the global
+// index).  `out` receives the Y planes without row padding (gated-off frames copied through), as embedWatermarkFrame writes them.
+inline int64_t processFramesInMemory(const std::vector<const Watermark*>& watermarkPerGpu, const int height, const int width,
+                                     const int watermarkInterval, const int linesize, const int mode, const uint8_t* frames,
+                                     uint8_t* out, const int64_t firstIndex, const int64_t nFrames, float* scalars)
+{
+    const int ngpus = (int)watermarkPerGpu.size();
+    if (ngpus < 1) throw std::runtime_error("processFramesInMemory: no Watermark object\n");
+    if (mode == WM_VIDEO_EMBED_VERIFY && ngpus > 1) throw std::runtime_error("processFramesInMemory: EMBED_VERIFY runs on one GPU per call\n");
+    std::vector<wm_video_ctx> ctx((size_t)ngpus);
+    std::vector<const wm_video_ctx*> pc;
+    std::vector<const uint8_t*> in;
+    std::vector<uint8_t*> ou;
+    for (int g = 0; g < ngpus; g++) {
+        int64_t first = 0, count = 0;
+        wm_shard_frames(nFrames, g, ngpus, &first, &count);
+        ctx[(size_t)g] = wm_video_ctx{watermarkPerGpu[(size_t)g]->handle(), height, width, watermarkInterval, linesize, 0, 0, 0};
+        pc.push_back(&ctx[(size_t)g]);
+        in.push_back(frames + first * (int64_t)height * linesize);
+        ou.push_back(out ? out + first * (int64_t)height * width : nullptr);
+    }
+    const int64_t n = ngpus == 1 ? wm_process_frames(pc[0], mode, in[0], ou[0], firstIndex, nFrames, scalars)
+                                 : wm_process_frames_multi(pc.data(), ngpus, mode, in.data(), out ? ou.data() : nullptr, firstIndex, nFrames, scalars);
+    if (n < 0) {
+        for (int g = 0; g < ngpus; g++) {
+            const char* msg = wm_last_error(watermarkPerGpu[(size_t)g]->handle());
+            if (msg && *msg) throw std::runtime_error(std::string(msg) + "\n");
+        }
+        throw std::runtime_error("processFramesInMemory failed\n");
+    }
+    return n;
 }
