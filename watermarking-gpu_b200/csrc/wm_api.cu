@@ -164,7 +164,7 @@ void clear_graphs(wm_ctx* ctx)
 
 int ensure_slot(wm_ctx* ctx, Slot& s, int batch, int gx_max, int nsweep, int nframe)
 {
-    const size_t need_part = (size_t)batch * ((size_t)nsweep * NTOT + (size_t)gx_max * 3);
+    const size_t need_part = (size_t)batch * ((size_t)nsweep * NTOT + (size_t)gx_max * 3 + (size_t)SMAXG * NTOT);
     if (batch > s.batch_cap || need_part > s.part_cap) clear_graphs(ctx);  // cached graphs point into these buffers
     if ((batch > s.batch_cap || need_part > s.part_cap) && !s.queue.empty()) {
         const int r = finish_slot(ctx, s);  // buffers in use by queued work are about to be replaced
@@ -176,8 +176,8 @@ int ensure_slot(wm_ctx* ctx, Slot& s, int batch, int gx_max, int nsweep, int nfr
         if (s.dbg) cudaFree(s.dbg);
         if (s.scal_host) cudaFreeHost(s.scal_host);
         s.counters = nullptr; s.scal = nullptr; s.dbg = nullptr; s.scal_host = nullptr;
-        CU(cudaMalloc(&s.counters, sizeof(unsigned) * 3 * batch));
-        CU(cudaMemsetAsync(s.counters, 0, sizeof(unsigned) * 3 * batch, s.stream));
+        CU(cudaMalloc(&s.counters, sizeof(unsigned) * (3 + SMAXG) * batch));  // [3][batch] last-block counters + [batch][SMAXG] group counters of the sweep
+        CU(cudaMemsetAsync(s.counters, 0, sizeof(unsigned) * (3 + SMAXG) * batch, s.stream));
         CU(cudaMalloc(&s.scal, sizeof(Scal) * batch));
         CU(cudaMemsetAsync(s.scal, 0, sizeof(Scal) * batch, s.stream));
         CU(cudaMalloc(&s.dbg, sizeof(ScalDbg) * batch));
@@ -417,6 +417,8 @@ int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int ba
     a.solve_f32 = ctx->opt_f32_solve;
     a.part = s.part;
     a.counter = s.counters;
+    a.gcounter = s.counters + 3 * (size_t)s.batch_cap;
+    a.gpart = s.part + (size_t)batch * ((size_t)pl.nsweep * NTOT + (size_t)std::max(pl.gx_stats, pl.gx_detect) * 3);
     a.scal = s.scal; a.dbg = s.dbg;
     CUtensorMap tmI;
     memset(&tmI, 0, sizeof tmI);

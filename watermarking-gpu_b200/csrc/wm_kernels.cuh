@@ -69,6 +69,7 @@ template <> struct TileGeo<unsigned char> { static constexpr int STRIDE = U8_ROW
 // thread's rolling 3-line window loads 10 lines per 8 instead of 6 per 4.  Four CTAs (16 warps) per SM leave 128 registers per
 // thread: the f64 lag accumulators live in registers.
 constexpr int SNT = 128, SLPT = TL / (SNT / 32);
+constexpr int SGRP = 16, SMAXG = 48;  // second stage of the sweep in two levels: groups of 16 partial rows, at most 48 groups (768 CTAs) per image
 constexpr int SWEEP_CTAS_PER_SM = 4;
 constexpr int EMBED_CTAS_PER_SM = 3;  // stats / apply: 2 stages of 35 KB -> three CTAs (24 warps) per SM
 // dynamic shared memory per kernel: [NST stages][work tiles]; with f32 TMA the stage IS the work tile
@@ -734,7 +735,9 @@ struct SweepArgs {
     int vec_ok, transposed;
     int solve_f32;       // WM_OPT_F32_SOLVE: the 8x8 system is rounded to f32 and solved by an f32 LU (af::solve on f32 arrays, Watermark.cpp:203)
     double* part;        // [batch][nsweep][NTOT]
+    double* gpart;       // [batch][SMAXG][NTOT]: sums of groups of SGRP partial rows (two-level second stage)
     unsigned* counter;   // [batch]
+    unsigned* gcounter;  // [batch][SMAXG]
     Scal* scal;          // [batch]
     ScalDbg* dbg;        // [batch]
 };
@@ -796,6 +799,10 @@ static __device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* s
     amax = __shfl_sync(0xffffffffu, amax, 0);
     int singular = (!(amax > 0.0)) || !isfinite(amax);
     const T tol = Ops::tol(amax);
+    __syncwarp();
+    // Rows are exchanged and the pivot row is broadcast through shared memory (M is free once the rows sit in registers): two row
+    // writes + broadcast reads per step instead of 36 double-word shuffles — the one-warp solve was 6.6 us of every sweep's tail.
+    T* const xrow = reinterpret_cast<T*>(M);        // [0..8] = row k before the swap, [9..17] = the pivot row
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         // first maximal |A[i][k]|, i >= k
@@ -807,17 +814,29 @@ static __device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* s
             const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
             if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
         }
-        const int piv = __shfl_sync(0xffffffffu, idx, 0);
+        const int piv = __shfl_sync(0xffffffffu, idx, 0) & 7;
         const T pv = __shfl_sync(0xffffffffu, v, 0);
         if (!(pv > tol)) singular = 1;
+        if (lane == k) {
+#pragma unroll
+            for (int j = 0; j < 9; j++) xrow[j] = A[j];
+        }
+        if (lane == piv) {
+#pragma unroll
+            for (int j = 0; j < 9; j++) xrow[9 + j] = A[j];
+        }
+        __syncwarp();
         T pr[9];
 #pragma unroll
-        for (int j = 0; j < 9; j++) {
-            const T rk = __shfl_sync(0xffffffffu, A[j], k);
-            const T rp = __shfl_sync(0xffffffffu, A[j], piv & 7);
-            if (lane == k) A[j] = rp; else if (lane == piv) A[j] = rk;
-            pr[j] = rp;  // row k after the swap
+        for (int j = 0; j < 9; j++) pr[j] = xrow[9 + j];  // row k after the swap
+        if (lane == k) {
+#pragma unroll
+            for (int j = 0; j < 9; j++) A[j] = pr[j];
+        } else if (lane == piv) {
+#pragma unroll
+            for (int j = 0; j < 9; j++) A[j] = xrow[j];
         }
+        __syncwarp();
         if (rowlane && lane > k) {
             const T f = Ops::div(A[k], pr[k]);
 #pragma unroll
@@ -1327,12 +1346,33 @@ __global__ void __launch_bounds__(SNT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_c
 
     // ---- second stage + solve in the last block ----
     if (threadIdx.x == 0) ts2 = gtime();
-    if (!last_block(a.counter + b, nblk)) return;
-    unsigned long long ts3 = 0, ts4 = 0;
-    if (threadIdx.x == 0) ts3 = gtime();
     __shared__ double tot[NTOT];
     __shared__ double M[72];
-    block_column_reduce<NTOT, 64, NTOT, NT>(part, nblk, tot, reinterpret_cast<double*>(dsm));
+    unsigned long long ts3 = 0, ts4 = 0;
+    if (nblk > SGRP && nblk <= SGRP * SMAXG) {
+        // Two levels (a single image is swept by ~590 CTAs: one CTA streaming 590 x 57 doubles was 8.5 us of serial tail).  Level 1: the
+        // CTA that finishes last within a group of SGRP consecutive partial rows sums them — this happens while other groups still work.
+        // Level 2: the last group to finish sums the <= 48 group rows.  The order of every addition is fixed by the indices alone.
+        const int g = blockIdx.x / SGRP, gsz = min(SGRP, nblk - g * SGRP), ngrp = (nblk + SGRP - 1) / SGRP;
+        if (!last_block(a.gcounter + (size_t)b * SMAXG + g, gsz)) return;
+        if (threadIdx.x < NTOT) {
+            const double* col = part + (size_t)g * SGRP * NTOT + threadIdx.x;
+            double x[SGRP];
+#pragma unroll
+            for (int r = 0; r < SGRP; r++) x[r] = r < gsz ? __ldcg(col + (size_t)r * NTOT) : 0.0;
+            double sg = 0.0;
+#pragma unroll
+            for (int r = 0; r < SGRP; r++) sg += x[r];
+            a.gpart[((size_t)b * SMAXG + g) * NTOT + threadIdx.x] = sg;
+        }
+        if (!last_block(a.counter + b, ngrp)) return;
+        if (threadIdx.x == 0) ts3 = gtime();
+        block_column_reduce<NTOT, 64, NTOT, NT>(a.gpart + (size_t)b * SMAXG * NTOT, ngrp, tot, reinterpret_cast<double*>(dsm));
+    } else {
+        if (!last_block(a.counter + b, nblk)) return;
+        if (threadIdx.x == 0) ts3 = gtime();
+        block_column_reduce<NTOT, 64, NTOT, NT>(part, nblk, tot, reinterpret_cast<double*>(dsm));
+    }
     if (threadIdx.x == 0) ts4 = gtime();
     if (w == 0) {
         if (a.solve_f32) solve_system<OpsF32>(tot, a.scal + b, a.dbg + b, a.transposed, M);
