@@ -623,15 +623,13 @@ def run_e2e(args, pkg, torch, dist, dev, wm, wl, d_in, a_host, c_host, first, wo
                 hin = pkg.image_desc(pin_in[o].data_ptr(), rows, cols, layout, dt_code)
                 for k2, mask in enumerate((pkg.NVF, pkg.ME)):
                     hout = pkg.image_desc(pin_out[k2][o].data_ptr(), rows, cols, layout, dt_code)
-                    wm.embed_host_batch(sl, hin, hin, hout, npx, npx, npx, nb, mask, a_e[k2][o:o + nb])
-                    # detection of the frames just embedded, from the caller's HOST copy (valid once the slot's stream reaches it:
-                    # the D2H copy above and this H2D copy are ordered on the slot's stream)
-                    wm.detect_host_batch(sl, hout, npx, nb, mask, c_e[k2][o:o + nb])
+                    # embed, download the watermarked images, detect on them where they lie on the device (main.cpp:178-217)
+                    wm.embed_verify_host_batch(sl, hin, hin, hout, npx, npx, npx, nb, mask, a_e[k2][o:o + nb], c_e[k2][o:o + nb])
             wm.sync(-1)
 
-        h2d, d2h = 4 * n * npx * esz, 2 * n * npx * esz + 4 * 4 * n
-        api = ("wm_embed_host_batch / wm_detect_host_batch on rotating slots: pinned host images in, watermarked images + scalars out, "
-               "detection re-reads the watermarked HOST image (%d frames per call)" % chunk)
+        h2d, d2h = 2 * n * npx * esz, 2 * n * npx * esz + 4 * 4 * n
+        api = ("wm_embed_verify_host_batch on rotating slots (%d frames per call): pinned host images in (once per mask type), watermarked "
+               "images + strengths + correlations out" % chunk)
         same = lambda: bool(np.allclose(a_e[1], a_host[1][:n], rtol=1e-6) and np.allclose(c_e[1], c_host[1][:n], rtol=1e-5, atol=1e-7))
     one_pass()  # warm-up: staging buffers, pinned result rings
     torch.cuda.synchronize(dev)

@@ -127,6 +127,12 @@ int wm_embed_host_batch(wm_ctx *ctx, int slot, const wm_image *in_gray_host, con
                         float *a_host, int *status_host);
 int wm_detect_host_batch(wm_ctx *ctx, int slot, const wm_image *img_host, int64_t img_stride, int batch, int mask_type,
                          float *corr_host, int *status_host);
+/* embed + verify: wm_embed_host_batch, then detectWatermark on each watermarked image while it is still in the slot's device staging buffer
+ * (gray output of the input's dtype): the embed / detect pair of the reference's testForImage flow (main.cpp:178-217) with one upload and one
+ * download per image.  corr_host[b] = correlation of image b. */
+int wm_embed_verify_host_batch(wm_ctx *ctx, int slot, const wm_image *in_gray_host, const wm_image *base_host, wm_image *out_host,
+                               int64_t in_stride, int64_t base_stride, int64_t out_stride, int batch, int mask_type,
+                               float *a_host, float *corr_host, int *status_host);
 
 /* ---- af::rgb2gray(rgb, wr, wg, wb) of the reference's image flow (main.cpp:142-154,196-197): planar f32 RGB -> gray ---- */
 int wm_rgb2gray(wm_ctx *ctx, const wm_image *rgb, wm_image *gray, float wr, float wg, float wb);

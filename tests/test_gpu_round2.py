@@ -427,3 +427,27 @@ def test_tma_store_variant_same_bits(wmb, oracle, rows, cols, B, dtype):
     L.wm_dev_free(wm._h, din)
     L.wm_dev_free(wm._h, dout)
     wm.close()
+
+
+def test_host_embed_verify_batch(wmb, oracle):
+    rows, cols, B = 96, 128, 4
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    imgs = np.stack([util.natural_image(rows, cols, seed=1300 + b) for b in range(B)])
+    npx = rows * cols
+    for mask in (wmb.NVF, wmb.ME):
+        outs = np.zeros_like(imgs)
+        a, c, a2, c2 = (np.zeros(B, np.float32) for _ in range(4))
+        hin = wmb.image_desc(imgs.ctypes.data, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+        hout = wmb.image_desc(outs.ctypes.data, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+        wm.embed_verify_host_batch(3, hin, hin, hout, npx, npx, npx, B, mask, a, c)
+        wm.sync(3)
+        outs2 = np.zeros_like(imgs)
+        hout2 = wmb.image_desc(outs2.ctypes.data, rows, cols, wmb.ROW_MAJOR, wmb.F32)
+        wm.embed_host_batch(4, hin, hin, hout2, npx, npx, npx, B, mask, a2)
+        wm.detect_host_batch(4, hout2, npx, B, mask, c2)
+        wm.sync(4)
+        assert np.array_equal(outs, outs2) and np.array_equal(a, a2) and np.array_equal(c, c2)
+        o = oracle.embed(imgs[1], W, 40.0, mask)
+        assert abs(a[1] - o["a"]) / o["a"] <= 1e-3 and abs(c[1] - oracle.detect(o["out"], W, mask)["corr"]) / abs(c[1]) <= 1e-3
+    wm.close()

@@ -32,7 +32,7 @@ EXPORTS = [
     "wm_create", "wm_create_from_file", "wm_clone", "wm_reinitialize", "wm_reinitialize_from_file", "wm_destroy",
     "wm_set_option", "wm_last_error", "wm_strength_factor", "wm_embed", "wm_detect", "wm_num_slots", "wm_get_stream",
     "wm_embed_batch", "wm_detect_batch", "wm_sync", "wm_embed_host", "wm_detect_host", "wm_embed_host_batch",
-    "wm_detect_host_batch", "wm_shard_frames", "wm_process_frames_multi", "wm_rgb2gray", "wm_debug_get",
+    "wm_detect_host_batch", "wm_embed_verify_host_batch", "wm_shard_frames", "wm_process_frames_multi", "wm_rgb2gray", "wm_debug_get",
     "wm_debug_set_coeffs", "wm_debug_plane", "wm_debug_detect_planes", "wm_get_kernel_times", "wm_launch_count", "wm_process_frames",
     "wm_dev_alloc", "wm_dev_free", "wm_dev_upload", "wm_dev_download", "wm_host_alloc_pinned",
     "wm_host_free_pinned", "wm_device_count", "wm_version",
@@ -102,6 +102,7 @@ def lib():
     L.wm_detect_host.argtypes = [vp, imp, i32, fp]
     L.wm_embed_host_batch.argtypes = [vp, i32, imp, imp, imp, i64, i64, i64, i32, i32, fp, ip]
     L.wm_detect_host_batch.argtypes = [vp, i32, imp, i64, i32, i32, fp, ip]
+    L.wm_embed_verify_host_batch.argtypes = [vp, i32, imp, imp, imp, i64, i64, i64, i32, i32, fp, fp, ip]
     L.wm_shard_frames.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
     L.wm_shard_frames.restype = None
     L.wm_process_frames_multi.argtypes = [C.POINTER(C.POINTER(wm_video_ctx)), i32, i32, C.POINTER(vp), C.POINTER(vp), i64, i64, fp]
@@ -336,6 +337,14 @@ class Watermark:
         self._check(lib().wm_embed_host_batch(
             self._h, slot, C.byref(in_desc), C.byref(base_desc), C.byref(out_desc), in_stride, base_stride, out_stride,
             batch, mask_type, a_out.ctypes.data_as(C.POINTER(C.c_float)),
+            status_out.ctypes.data_as(C.POINTER(C.c_int)) if status_out is not None else None))
+
+    def embed_verify_host_batch(self, slot, in_desc, base_desc, out_desc, in_stride, base_stride, out_stride, batch, mask_type,
+                                a_out, corr_out, status_out=None):
+        """embed_host_batch + detection of the watermarked images where they lie on the device (one upload, one download per image)."""
+        self._check(lib().wm_embed_verify_host_batch(
+            self._h, slot, C.byref(in_desc), C.byref(base_desc), C.byref(out_desc), in_stride, base_stride, out_stride,
+            batch, mask_type, a_out.ctypes.data_as(C.POINTER(C.c_float)), corr_out.ctypes.data_as(C.POINTER(C.c_float)),
             status_out.ctypes.data_as(C.POINTER(C.c_int)) if status_out is not None else None))
 
     def detect_host_batch(self, slot, img_desc, img_stride, batch, mask_type, corr_out, status_out=None):

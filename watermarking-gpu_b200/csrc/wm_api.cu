@@ -1039,6 +1039,25 @@ int wm_embed_host_batch(wm_ctx* ctx, int slot, const wm_image* in, const wm_imag
     return WM_OK;
 }
 
+// embed + verify for host images: wm_embed_host_batch, then detectWatermark on each watermarked image while it still lies in the slot's
+// device staging buffer (gray outputs only) — the pair of operations of the reference's testForImage flow (main.cpp:178-217) with one upload
+// and one download per image instead of a second upload of the watermarked image
+int wm_embed_verify_host_batch(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm_image* out, int64_t in_stride,
+                               int64_t base_stride, int64_t out_stride, int batch, int mask, float* a_host, float* corr_host, int* status_host)
+{
+    if (!ctx || !out) return WM_ERR_ARG;
+    if ((out->channels > 1) || out->dtype != (in ? in->dtype : out->dtype))
+        return fail(ctx, WM_ERR_ARG, "embed + verify needs a gray output of the input's dtype (detectWatermark takes the gray image)");
+    int rc = wm_embed_host_batch(ctx, slot, in, base, out, in_stride, base_stride, out_stride, batch, mask, a_host, status_host);
+    if (rc) return rc;
+    Slot& s = ctx->slots[slot];
+    wm_image d = dense_desc(out, s.stage_out);
+    rc = do_detect(ctx, slot, &d, 0, batch, mask);
+    if (rc) return rc;
+    s.queue.back().scalar = corr_host;
+    return WM_OK;
+}
+
 int wm_detect_host_batch(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, int batch, int mask, float* corr_host, int* status_host)
 {
     if (!ctx || !img || !img->data) return WM_ERR_ARG;
