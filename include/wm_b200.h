@@ -71,6 +71,9 @@ enum {
     WM_OPT_TMA_STORE = 10,    /* 1 (default): where base = input and the output is gray, dense enough and 16-byte aligned, the apply kernel's output leaves through
                                  TMA stores (cp.async.bulk.tensor smem -> global) instead of per-thread vector stores; same bits, +8..10 % on that kernel
                                  (profiles/r2_tma_store_ab.md); 0: always per-thread stores */
+    WM_OPT_PDL = 11,          /* 1 (default): the 2nd / 3rd kernel of an op is launched with programmatic stream serialization: it becomes resident, initialises
+                                 its barriers and issues its first tile loads while the previous kernel's last block still reduces / solves, and executes
+                                 griddepcontrol.wait before reading that kernel's results; 0: plain stream order */
     WM_OPT_HOST_RUN_FRAMES = 9, /* frames per run (one batched launch sequence + its copies) of wm_process_frames when frames are in HOST memory; default 4 */
     WM_OPT_F32_SOLVE = 8      /* 0 (default): the 8x8 system is summed and solved in f64 (pivot cut 1e-12 max|Rx|); 1: Rx / rx are rounded to f32
                                  and solved by an f32 LU (pivot cut 1e-6 max|Rx|) like af::solve on the reference's f32 arrays

@@ -7,6 +7,7 @@
 #include "wm_launch.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -60,6 +61,11 @@ struct Slot {
     void* stage_out = nullptr; size_t stage_out_cap = 0;
     void* maskp = nullptr; size_t maskp_cap = 0;  // NVF mask planes of a batch when p > 3 (k_nvfp)
     std::vector<TimedLaunch> timed;
+    // direct delivery of synchronous single-image ops (slot 0 only): mapped pinned result + device sequence / completion counters
+    HostResult* hres = nullptr;      // pinned host memory
+    HostResult* hres_dev = nullptr;  // its device alias
+    unsigned* dl_words = nullptr;    // device: [0] sequence counter, [1] apply completion counter
+    unsigned dl_expected = 0;        // sequence number the next delivered op will publish
 };
 
 }  // namespace
@@ -72,6 +78,7 @@ struct wm_ctx {
     std::shared_ptr<WShared> w;
     Slot slots[NSLOTS];
     int opt_fp16 = 1, opt_timing = 0, opt_tma = 1, opt_serial = 0, opt_mma = 1, opt_f32_solve = 0;
+    int opt_pdl = 1;         // WM_OPT_PDL: 2nd / 3rd kernel of an op launched with programmatic stream serialization
     int opt_tma_store = 1;   // WM_OPT_TMA_STORE: apply kernel output through TMA stores where the shape allows (+8..10 % on the apply kernel)
     int opt_host_run = 4;    // frames per run of the video driver's host-frame path (WM_OPT_HOST_RUN_FRAMES)
     int opt_split_cost = 8;  // tile-times one more launch is assumed to cost when a batch is partitioned (WM_OPT_SPLIT_COST)
@@ -90,6 +97,12 @@ struct wm_ctx {
 };
 
 namespace {
+
+struct PdlScope {  // launches inside the scope carry the programmatic-serialization attribute (wm_launch.h)
+    bool prev;
+    explicit PdlScope(bool on) : prev(wm::pdl_next()) { wm::pdl_next() = on; }
+    ~PdlScope() { wm::pdl_next() = prev; }
+};
 
 int fail(wm_ctx* c, int code, const std::string& msg)
 {
@@ -463,8 +476,29 @@ int enqueue_nvf_planes(wm_ctx* ctx, Slot& s, const View& v, long long bstride, i
 
 size_t stats_part_offset(const Plan& pl, int batch) { return (size_t)batch * (size_t)pl.nsweep * NTOT; }
 
+// the pieces of a slot that direct delivery needs (created on first use)
+int ensure_direct(wm_ctx* ctx, Slot& s)
+{
+    if (s.hres) return WM_OK;
+    CU(cudaHostAlloc(&s.hres, sizeof(HostResult), cudaHostAllocMapped));
+    memset(s.hres, 0, sizeof(HostResult));
+    CU(cudaHostGetDevicePointer((void**)&s.hres_dev, s.hres, 0));
+    CU(cudaMalloc(&s.dl_words, 2 * sizeof(unsigned)));
+    CU(cudaMemset(s.dl_words, 0, 2 * sizeof(unsigned)));
+    s.dl_expected = 0;
+    return WM_OK;
+}
+Deliver deliver_args(Slot& s, bool direct)
+{
+    Deliver d;
+    d.host = direct ? s.hres_dev : nullptr;
+    d.dev_seq = direct ? s.dl_words : nullptr;
+    d.done = direct ? s.dl_words + 1 : nullptr;
+    return d;
+}
+
 int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm_image* out, int64_t in_stride,
-             int64_t base_stride, int64_t out_stride, int batch, int mask)
+             int64_t base_stride, int64_t out_stride, int batch, int mask, bool direct = false)
 {
     if (!ctx) return WM_ERR_ARG;
     if (slot < 0 || slot >= NSLOTS) return fail(ctx, WM_ERR_ARG, "bad slot");
@@ -516,6 +550,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     ea.out = vo.ptr; ea.out_ld = vo.ld; ea.out_bstride = out_stride; ea.out_pstride = vo.pstride;
     ea.channels = vb.channels;
     ea.same_base = (vb.ptr == vi.ptr && vb.ld == vi.ld && base_stride == in_stride && vb.channels == 1);
+    ea.dl = deliver_args(s, direct && batch == 1);
     ea.base_vec_ok = vec_ok(vb.ptr, vb.ld, base_stride, vb.channels > 1 ? vb.pstride : 0, vb.dtype);
     ea.out_vec_ok = vec_ok(vo.ptr, vo.ld, out_stride, vo.channels > 1 ? vo.pstride : 0, vo.dtype);
     CUtensorMap tmI, tmW;
@@ -530,6 +565,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
             if ((rc = enqueue_nvf_planes(ctx, s, vi, in_stride, batch, g))) return rc;
             ea.maskp = (const float*)s.maskp;
         }
+        PdlScope pdl(ctx->opt_pdl && mask == WM_MASK_ME && !ctx->opt_timing && !ctx->inject_coef);  // the Rx sweep of this op precedes
         for (const SubBatch& sb : pl.embed) {
             ea.b0 = sb.b0; ea.nblk_base = sb.base; ea.nblk_extra = sb.extra;
             launch_stats(vi.dtype, kmask, vi.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmI, tmW, ea);
@@ -541,6 +577,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
         // WM_OPT_TMA_STORE (default on): gray output of the same dtype, base = input, TMA-loadable input and a TMA-storable output
         CUtensorMap tmO;
         memset(&tmO, 0, sizeof tmO);
+        PdlScope pdl(ctx->opt_pdl && !ctx->opt_timing && !planes);  // the stats pass of this op precedes
         bool ts = ctx->opt_tma_store && tma && ea.same_base && vo.dtype == vi.dtype && vo.channels == 1 && !planes && tma_ok(ctx, vo, out_stride, batch);
         if (ts) ts = make_tmap(&tmO, vo.dtype, vo.ptr, g.P, g.L, batch, vo.ld, out_stride, TP, TL, TP);
         for (const SubBatch& sb : pl.embed) {
@@ -551,10 +588,12 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
         }
     }
     CU(cudaGetLastError());
+    if (direct && batch == 1) return WM_OK;  // the apply kernel's last CTA publishes the scalars itself
     return push_result(ctx, s, 1, batch);
 }
 
-int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, int batch, int mask, float* dbg_u = nullptr, float* dbg_eu = nullptr)
+int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, int batch, int mask, float* dbg_u = nullptr, float* dbg_eu = nullptr,
+              bool direct = false)
 {
     if (!ctx) return WM_ERR_ARG;
     if (slot < 0 || slot >= NSLOTS) return fail(ctx, WM_ERR_ARG, "bad slot");
@@ -585,6 +624,7 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     da.counter = s.counters + 2 * s.batch_cap;
     da.scal = s.scal; da.dbg = s.dbg;
     da.dbg_u = dbg_u; da.dbg_eu = dbg_eu;
+    da.dl = deliver_args(s, direct && batch == 1);
     CUtensorMap tmZ, tmW;
     memset(&tmZ, 0, sizeof tmZ);
     memset(&tmW, 0, sizeof tmW);
@@ -597,12 +637,14 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
             if ((rc = enqueue_nvf_planes(ctx, s, v, img_stride, batch, g))) return rc;
             da.maskp = (const float*)s.maskp;
         }
+        PdlScope pdl(ctx->opt_pdl && !ctx->opt_timing && !planes && !ctx->inject_coef);  // the Rx sweep of this op precedes
         for (const SubBatch& sb : pl.detect) {
             da.b0 = sb.b0; da.nblk_base = sb.base; da.nblk_extra = sb.extra;
             launch_detect(v.dtype, planes ? 2 : mask, v.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmZ, tmW, da);
         }
     }
     CU(cudaGetLastError());
+    if (direct && batch == 1) return WM_OK;  // k_detect's last CTA publishes the scalars itself
     return push_result(ctx, s, 2, batch);
 }
 
@@ -686,6 +728,8 @@ void free_slot(Slot& s)
     if (s.stage_base) cudaFree(s.stage_base);
     if (s.stage_out) cudaFree(s.stage_out);
     if (s.maskp) cudaFree(s.maskp);
+    if (s.hres) cudaFreeHost(s.hres);
+    if (s.dl_words) cudaFree(s.dl_words);
     for (auto& t : s.timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
@@ -728,6 +772,31 @@ std::string image_key(const wm_image* im)
              im->channels, im->layout, im->dtype, (long long)im->plane_stride);
     return b;
 }
+// wait for the op that was just launched with direct delivery: poll the mapped sequence word; the stream is only consulted every few
+// thousand polls so that a failed launch cannot spin forever
+int wait_direct(wm_ctx* ctx, Slot& s, int kind, float* scalar_host)
+{
+    const unsigned want = ++s.dl_expected;
+    volatile unsigned* seq = &s.hres->seq;
+    for (unsigned spins = 0; *seq != want; spins++) {
+        if ((spins & 0x3fff) == 0x3fff) {
+            const cudaError_t q = cudaStreamQuery(s.stream);
+            if (q == cudaSuccess) { if (*seq != want) return fail(ctx, WM_ERR_CUDA, "direct delivery: the op finished without publishing its result"); break; }
+            if (q != cudaErrorNotReady) return fail(ctx, WM_ERR_CUDA, std::string("direct delivery: ") + cudaGetErrorString(q));
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const Scal h = s.hres->s;
+    if (scalar_host) {
+        if (kind == 1) { if (h.status != WM_SINGULAR) *scalar_host = h.a; }  // untouched when unsolvable (Watermark.cpp:164-165)
+        else *scalar_host = h.status == 0 ? h.corr : 0.0f;                  // Watermark.cpp:246-247
+    }
+    return h.status;
+}
+
+// Synchronous single-image calls.  The second call with identical arguments captures the launch sequence into a CUDA graph; from the
+// third on the graph is replayed: one launch instead of 3-4, and the result comes back through direct delivery (no copy node, no
+// stream synchronisation).  enqueue(direct) issues the op's kernels.
 template <typename Enqueue>
 int run_sync(wm_ctx* ctx, const std::string& key, int kind, float* scalar_host, Enqueue enqueue)
 {
@@ -747,16 +816,16 @@ int run_sync(wm_ctx* ctx, const std::string& key, int kind, float* scalar_host, 
         CU(cudaSetDevice(ctx->device));
         CU(cudaGraphLaunch(ge->exec, s.stream));
         ctx->launches += ge->launches;
-        s.queue.push_back({kind, 1, scalar_host, nullptr, 0, 1});
-        s.host_used = 1;
-        return finish_slot(ctx, s);
+        return wait_direct(ctx, s, kind, scalar_host);
     }
     if (ge && ge->seen >= 1) {  // second sighting: buffers exist, attributes are set -> capture
         CU(cudaSetDevice(ctx->device));
+        int rc = ensure_direct(ctx, s);
+        if (rc) return rc;
         const int64_t l0 = ctx->launches;
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            const int rc = enqueue();
+            rc = enqueue(true);
             const cudaError_t ce = cudaStreamEndCapture(s.stream, &graph);
             s.queue.clear();
             s.host_used = 0;
@@ -774,13 +843,11 @@ int run_sync(wm_ctx* ctx, const std::string& key, int kind, float* scalar_host, 
         if (ge->exec) {
             CU(cudaGraphLaunch(ge->exec, s.stream));
             ctx->launches += ge->launches;
-            s.queue.push_back({kind, 1, scalar_host, nullptr, 0, 1});
-            s.host_used = 1;
-            return finish_slot(ctx, s);
+            return wait_direct(ctx, s, kind, scalar_host);
         }
     }
     if (ge) ge->seen++;
-    const int rc = enqueue();
+    const int rc = enqueue(false);
     if (rc) return rc;
     s.queue.back().scalar = scalar_host;
     return finish_slot(ctx, s);
@@ -836,7 +903,7 @@ int wm_clone(const wm_ctx* src, wm_ctx** out)
     ctx->p = src->p; ctx->psnr = src->psnr; ctx->strength = src->strength;
     ctx->w = src->w;
     ctx->opt_fp16 = src->opt_fp16; ctx->opt_mma = src->opt_mma; ctx->opt_split_cost = src->opt_split_cost; ctx->opt_timing = src->opt_timing; ctx->opt_tma = src->opt_tma;
-    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run; ctx->opt_tma_store = src->opt_tma_store;
+    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run; ctx->opt_tma_store = src->opt_tma_store; ctx->opt_pdl = src->opt_pdl;
     const int rc = init_slots(ctx, nullptr);
     if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
     *out = ctx;
@@ -886,6 +953,7 @@ int wm_set_option(wm_ctx* ctx, int option, int value)
     case WM_OPT_MMA_ACCUM: ctx->opt_mma = value != 0; return WM_OK;
     case WM_OPT_HOST_RUN_FRAMES: ctx->opt_host_run = std::max(1, std::min(value, 64)); return WM_OK;
     case WM_OPT_TMA_STORE: ctx->opt_tma_store = value != 0; clear_graphs(ctx); return WM_OK;
+    case WM_OPT_PDL: ctx->opt_pdl = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_F32_SOLVE: ctx->opt_f32_solve = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_SPLIT_COST: ctx->opt_split_cost = value < 0 ? 1 << 28 : value; return WM_OK;
     default: return fail(ctx, WM_ERR_ARG, "unknown option");
@@ -938,14 +1006,14 @@ int wm_embed(wm_ctx* ctx, const wm_image* in, const wm_image* base, wm_image* ou
     if (!ctx) return WM_ERR_ARG;
     const std::string key = "E" + std::to_string(mask) + image_key(in) + image_key(base) + image_key(out) + std::to_string(ctx->opt_fp16 + 2 * ctx->opt_mma + 4 * ctx->opt_f32_solve) +
                             std::to_string(ctx->opt_tma);
-    return run_sync(ctx, key, 1, a_host, [&]() { return do_embed(ctx, 0, in, base, out, 0, 0, 0, 1, mask); });
+    return run_sync(ctx, key, 1, a_host, [&](bool direct) { return do_embed(ctx, 0, in, base, out, 0, 0, 0, 1, mask, direct); });
 }
 
 int wm_detect(wm_ctx* ctx, const wm_image* img, int mask, float* corr_host)
 {
     if (!ctx) return WM_ERR_ARG;
     const std::string key = "D" + std::to_string(mask) + image_key(img) + std::to_string(ctx->opt_fp16 + 2 * ctx->opt_mma + 4 * ctx->opt_f32_solve) + std::to_string(ctx->opt_tma);
-    return run_sync(ctx, key, 2, corr_host, [&]() { return do_detect(ctx, 0, img, 0, 1, mask); });
+    return run_sync(ctx, key, 2, corr_host, [&](bool direct) { return do_detect(ctx, 0, img, 0, 1, mask, nullptr, nullptr, direct); });
 }
 
 // ---- host-buffer form.  Host images may be strided views (ld > contiguous dimension, padded planes): every plane is staged

@@ -3,6 +3,12 @@
 
 namespace wm {
 
+bool& pdl_next()
+{
+    static thread_local bool v = false;
+    return v;
+}
+
 template <typename PixT, bool TMA>
 static void launch_sweep_t(int acc, int smem, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const SweepArgs& a)
 {

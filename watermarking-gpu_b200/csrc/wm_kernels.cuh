@@ -95,6 +95,32 @@ struct Scal {
     float emax;      // max|e| (ME embed)
     float corr;
 };
+// Direct delivery of a synchronous single-image op (wm_embed / wm_detect): the op's last CTA copies the image's scalars into mapped pinned
+// host memory and then publishes a sequence number taken from a device counter; the host polls `seq` instead of paying a copy-engine
+// D2H node plus a stream synchronisation (about 10 us of a 50 us op).
+struct HostResult {
+    Scal s;
+    unsigned seq;
+    unsigned pad[3];
+};
+struct Deliver {
+    HostResult* host;    // mapped pinned memory (device alias); nullptr = results go through the stream-ordered copy as before
+    unsigned* dev_seq;   // device counter: ++ per delivered op
+    unsigned* done;      // apply only: CTAs finished (wraps to 0 by itself)
+};
+__device__ __forceinline__ void deliver_result(const Deliver& d, const Scal* sc)
+{
+    static_assert(sizeof(Scal) == 48, "Scal is copied as three 16-byte words");
+    const int4* src = reinterpret_cast<const int4*>(sc);
+    const int4 v0 = __ldcg(src), v1 = __ldcg(src + 1), v2 = __ldcg(src + 2);
+    int4* hs = reinterpret_cast<int4*>(&d.host->s);
+    hs[0] = v0; hs[1] = v1; hs[2] = v2;
+    __threadfence_system();
+    const unsigned q = atomicAdd(d.dev_seq, 1u) + 1u;
+    *reinterpret_cast<volatile unsigned*>(&d.host->seq) = q;
+    __threadfence_system();
+}
+
 // parity/debug side-band (one per batch entry, only read back by wm_debug_get)
 struct ScalDbg {
     double sum2;     // sum (|e| W)^2 or sum (nvf W)^2
@@ -165,6 +191,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
                  : "memory");
 }
 
+// programmatic dependent launch (PDL): let the next kernel of the stream become resident / wait for the previous kernel's results
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // TMA store of a tile (smem -> global, SASS UTMASTG): bulk-group completion; out-of-image cells of the box are clipped by the hardware
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int c1, int c2, const void* src)
 {
@@ -172,6 +202,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int 
                  ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src)) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // round-robin tile walk t = first, first + step, ... with (tl, tp) kept incrementally (no per-tile division)
@@ -1051,6 +1082,7 @@ template <typename PixT, int FP16, bool TMA>
 __global__ void __launch_bounds__(SNT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_constant__ CUtensorMap tmI, const SweepArgs a)
 {
     constexpr int NT = SNT;  // every NT below is the sweep's own CTA size
+    pdl_launch_dependents();
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[(NT / 32) * NFRM];
     __shared__ __align__(8) uint64_t bars[SWEEP_NST_U8];
@@ -1408,12 +1440,15 @@ struct EmbedArgs {
     void* out;          // OutT
     long long out_ld, out_bstride, out_pstride;
     int channels, same_base, base_vec_ok, out_vec_ok;
+    Deliver dl;         // apply only (single-image synchronous ops)
 };
 
 // persistent tile loop shared by k_stats and k_apply: calls body(tile, wtile, l0, p0) once per tile
-template <typename PixT, bool TMA, typename Body>
+// `ready()` runs once, after the barriers are initialised and the first tile loads are in flight: it executes griddepcontrol.wait and reads
+// what the previous kernel produced (coefficients, strength); when it returns false the CTA drains its loads and leaves.
+template <typename PixT, bool TMA, typename Ready, typename Body>
 __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CUtensorMap* tmW, const EmbedArgs& a,
-                                                unsigned char* dsm, uint64_t* bars, Body body)
+                                                unsigned char* dsm, uint64_t* bars, Ready ready, Body body)
 {
     constexpr bool U8T = TMA && sizeof(PixT) == 1;
     constexpr int NST = TMA ? (U8T ? EMBED_NST_U8 : EMBED_NST) : 1;
@@ -1450,6 +1485,13 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
             pre.issue(img, a.ld, a.L, a.P, it.tl * TL - 1, it.tp * TP - HP, a.vec_ok != 0);
             wpre.issue(a.W, a.L, a.P, it.tl * TL, it.tp * TP, a.w_vec_ok != 0);
         }
+    }
+    if (!ready()) {
+        if constexpr (TMA) {  // a CTA must not exit with TMA loads in flight into its shared memory
+            for (int s = 0; s < NST - 1; s++)
+                if ((int)blockIdx.x + s * step < a.ntiles) mbar_wait(&bars[s], 0);
+        }
+        return;
     }
     bool patched = false;  // the previous tile's stage was patched by fix_border (generic-proxy writes): fence before TMA refills it
     for (; it.t < a.ntiles; it.next(), pf.next()) {
@@ -1541,19 +1583,24 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * 2];
     __shared__ __align__(8) uint64_t bars[EMBED_NST_U8];
+    pdl_launch_dependents();
     const int b = blockIdx.y + a.b0;
     Scal* sc = a.scal + b;
-    if (MASK == 0 && sc->status != 0) return;  // singular: a untouched, apply copies base through
     const int L = a.L, P = a.P;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float c[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
     double dsum = 0.0;
     float emax = 0.0f;
     const int nblk = blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y);
     if ((int)blockIdx.x >= nblk) return;
-    embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&](const auto* tile, const float* wt, int l0, int p0) {
+    bool skip = false;
+    embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&]() {
+        pdl_wait();  // the sweep's coefficients (ME) are valid from here on
+        if (MASK == 0 && sc->status != 0) { skip = true; return false; }  // singular: a untouched, apply copies base through
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
+        return true;
+    }, [&](const auto* tile, const float* wt, int l0, int p0) {
         const int pb = p0 + 4 * lane;
         float fs = 0.0f;
         auto run = [&](auto tag) {
@@ -1574,6 +1621,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
         if (l0 + TL <= L && p0 + TP <= P) run(BoolTag<true>{}); else run(BoolTag<false>{});
         dsum += (double)fs;
     });
+    if (skip) return;
     {   // block reduce: sum and max
         const double s = warp_sum(dsum);
         const float m = warp_max(emax);
@@ -1651,22 +1699,28 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
 {
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ __align__(8) uint64_t bars[EMBED_NST_U8];
+    pdl_launch_dependents();
     const int b = blockIdx.y + a.b0;
     const Scal* sc = a.scal + b;
     if ((int)blockIdx.x >= blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y)) return;
-    if (sc->status != 0) { copy_base_through<PixT, OutT>(a); return; }
     const PixT* bas = reinterpret_cast<const PixT*>(a.base) + (long long)b * a.base_bstride;
     OutT* out = reinterpret_cast<OutT*>(a.out) + (long long)b * a.out_bstride;
     const int L = a.L, P = a.P;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float c[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
-    const float av = sc->a, mx = sc->emax;
-    const float rmx = MASK == 0 ? __frcp_rn(mx) : 0.0f;
+    float av = 0.0f, mx = 0.0f, rmx = 0.0f;
     const bool out_vec = a.out_vec_ok != 0, base_vec = a.base_vec_ok != 0;
     const int channels = SB ? 1 : a.channels;
-    embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&](const auto* tile, const float* wt, int l0, int p0) {
+    bool through = false;
+    embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&]() {
+        pdl_wait();  // strength (and, for ME, coefficients and max|e|) of the stats pass are valid from here on
+        if (sc->status != 0) { through = true; return false; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
+        av = sc->a; mx = sc->emax;
+        rmx = MASK == 0 ? __frcp_rn(mx) : 0.0f;
+        return true;
+    }, [&](const auto* tile, const float* wt, int l0, int p0) {
         const int pb = p0 + 4 * lane;
         auto run = [&](auto tag) {
             constexpr bool FULL = decltype(tag)::value;
@@ -1708,6 +1762,15 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
         // vectors (before, the per-line `vec` tests kept both the vector and the byte-wise stores, and a branch between them, in the hot loop)
         if (l0 + TL <= L && p0 + TP <= P && out_vec && (SB || base_vec)) run(BoolTag<true>{}); else run(BoolTag<false>{});
     });
+    if (through) copy_base_through<PixT, OutT>(a);  // unsolvable system / zero mask: the output is the base image
+    if (a.dl.host) {  // last CTA of the image to finish publishes the result (every store of every CTA is fenced before its count)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned n = (unsigned)blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y);
+            if (atomicInc(a.dl.done, n - 1) == n - 1) deliver_result(a.dl, sc);
+        }
+    }
 }
 
 // ---- k_apply_ts: the apply kernel of the common case (WM_OPT_TMA_STORE, default on) — gray output, base = input, TMA-loaded tiles: the clamped output goes to an
@@ -1724,18 +1787,13 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply_ts(const __grid
     constexpr int NST = U8T ? EMBED_NST_U8 : EMBED_NST;
     constexpr int STG = embed_stage(U8T), IPART = U8T ? U8_I34 : SZ_I34;
     using TileT = typename std::conditional<U8T, unsigned char, float>::type;
+    pdl_launch_dependents();
     const int b = blockIdx.y + a.b0;
     const Scal* sc = a.scal + b;
     const int step = blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y);
     if ((int)blockIdx.x >= step) return;
-    if (sc->status != 0) { copy_base_through<PixT, PixT>(a); return; }
     const int L = a.L, P = a.P;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    float c[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
-    const float av = sc->a, mx = sc->emax;
-    const float rmx = MASK == 0 ? __frcp_rn(mx) : 0.0f;
     auto stage = [&](int s) { return dsm + (size_t)s * STG; };
     unsigned char* const otiles = dsm + (size_t)NST * STG;  // u8 only: 2 x (TL x TP) bytes
     auto issue = [&](int tl, int tp, int s) {  // thread 0 only
@@ -1753,6 +1811,28 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply_ts(const __grid
         if (threadIdx.x == 0 && pf.t < a.ntiles) issue(pf.tl, pf.tp, s);
         pf.next();
     }
+    pdl_wait();  // the first tiles are in flight; the stats pass's results are valid from here on
+    auto publish = [&]() {  // single-image synchronous ops: the last CTA to finish hands the scalars to the polling host
+        if (a.dl.host) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                if (atomicInc(a.dl.done, (unsigned)step - 1) == (unsigned)step - 1) deliver_result(a.dl, sc);
+            }
+        }
+    };
+    if (sc->status != 0) {  // unsolvable system / zero mask: out = base; the loads in flight must land before the CTA may leave
+        for (int s = 0; s < NST - 1; s++)
+            if ((int)blockIdx.x + s * step < a.ntiles) mbar_wait(&bars[s], 0);
+        copy_base_through<PixT, PixT>(a);
+        publish();
+        return;
+    }
+    float c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = MASK == 0 ? sc->coef[k] : 0.0f;
+    const float av = sc->a, mx = sc->emax;
+    const float rmx = MASK == 0 ? __frcp_rn(mx) : 0.0f;
     StagePos<NST> pos;
     int k = 0;
     for (; it.t < a.ntiles; it.next(), pf.next(), k++) {
@@ -1790,7 +1870,10 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply_ts(const __grid
         __syncthreads();
         if (threadIdx.x == 0) tma_store_3d(&tmO, p0, l0, b, U8T ? (const void*)ot : (const void*)wtile);
     }
-    if (threadIdx.x == 0) tma_store_wait_read<0>();  // smem must outlive the last store's read
+    if (threadIdx.x == 0) {
+        if (a.dl.host) tma_store_wait_all(); else tma_store_wait_read<0>();  // smem must outlive the last store's read; a published result needs the writes done
+    }
+    publish();
 }
 
 // ================================================================================================
@@ -1815,6 +1898,7 @@ struct DetectArgs {
     unsigned* counter;
     Scal* scal;
     ScalDbg* dbg;
+    Deliver dl;         // single-image synchronous ops
     float* dbg_u;       // DBG instantiations only: dense L x P planes of u = mask.W (ME: |e_z|.W, the 1 / max|e| scale dropped) and e_u
     float* dbg_eu;
 };
@@ -1969,16 +2053,13 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
     constexpr int STG = TMA ? detect_stage(U8T) : SZ_I36 + SZ_I34, ZPART = U8T ? U8_I36 : SZ_I36;
     using ZT = typename std::conditional<U8T, unsigned char, float>::type;  // u8 TMA stages are read where they landed
     float* const ut = reinterpret_cast<float*>(dsm + (size_t)NST * STG);      // (TL+2) x SW, lines l0-1 .. l0+TL
+    pdl_launch_dependents();
     const int b = blockIdx.y + a.b0;
     Scal* sc = a.scal + b;
-    if (sc->status != 0) return;  // singular: corr = 0 was written by the sweep
     const PixT* img = reinterpret_cast<const PixT*>(a.img) + (long long)b * a.bstride;
     const int L = a.L, P = a.P;
     const int step = blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y);
     if ((int)blockIdx.x >= step) return;
-    float c[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) c[k] = sc->coef[k];
     auto stage = [&](int s) { return dsm + (size_t)s * STG; };
     auto issue = [&](int tl, int tp, int s) {  // thread 0 only
         mbar_expect_tx(&bars[s], (U8T ? (TL + 4) * U8_ROW : (TL + 4) * SW * 4) + (TL + 2) * SW * 4);
@@ -2007,6 +2088,18 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
             wpre.issue(a.W, P, L, P, it.tl * TL - 1, it.tp * TP - HP, a.w_vec_ok != 0);
         }
     }
+    pdl_wait();  // the first tiles are in flight; the sweep's coefficients are valid from here on
+    if (sc->status != 0) {  // singular: corr = 0 was written by the sweep; let the loads in flight land, then leave
+        if constexpr (TMA) {
+            for (int s = 0; s < NST - 1; s++)
+                if ((int)blockIdx.x + s * step < a.ntiles) mbar_wait(&bars[s], 0);
+        }
+        if (a.dl.host && blockIdx.x == 0 && threadIdx.x == 0) deliver_result(a.dl, sc);
+        return;
+    }
+    float c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = sc->coef[k];
     bool patched = false;  // the previous tile's stage was patched by fix_border: fence before TMA refills it
     for (; it.t < a.ntiles; it.next(), pf.next()) {
         const int l0 = it.tl * TL, p0 = it.tp * TP;
@@ -2051,6 +2144,7 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
         a.dbg[b].dot = red[0]; a.dbg[b].nz = red[1]; a.dbg[b].nu = red[2];
         const float dotf = (float)red[0];
         sc->corr = dotf / (float)(sqrt(red[1]) * sqrt(red[2]));
+        if (a.dl.host) { __threadfence(); deliver_result(a.dl, sc); }
     }
 }
 

@@ -24,19 +24,25 @@ enum { WM_MASK_ME = 0, WM_MASK_NVF = 1 };
 enum { WM_F32 = 0, WM_U8 = 1 };
 #endif
 
+// Every kernel goes through cudaLaunchKernelEx so that the 2nd / 3rd kernel of an op can be launched with programmatic stream
+// serialization (PDL): it becomes resident while its predecessor's last block is still reducing / solving, initialises its barriers and
+// issues its first TMA loads (the op's input image and W: nothing the predecessor writes), and only then executes
+// griddepcontrol.wait before it reads the predecessor's results.  wm::pdl_next() is set by the host code for exactly those launches.
+namespace wm {
+bool& pdl_next();
+}
 #define WM_LAUNCH_T(KERNEL, THREADS, SMEM, ...)                        \
     do {                                                               \
         static bool done_[64] = {false};                               \
         int dev_ = 0;                                                  \
         cudaGetDevice(&dev_);                                          \
         if (!done_[dev_ & 63]) { cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); done_[dev_ & 63] = true; } \
-        KERNEL<<<grid, THREADS, SMEM, st>>>(__VA_ARGS__);              \
+        cudaLaunchConfig_t cfg_ = {};                                  \
+        cfg_.gridDim = grid; cfg_.blockDim = dim3(THREADS); cfg_.dynamicSmemBytes = SMEM; cfg_.stream = st; \
+        cudaLaunchAttribute at_[1];                                    \
+        at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; \
+        at_[0].val.programmaticStreamSerializationAllowed = 1;         \
+        cfg_.attrs = at_; cfg_.numAttrs = wm::pdl_next() ? 1 : 0;      \
+        cudaLaunchKernelEx(&cfg_, KERNEL, __VA_ARGS__);                \
     } while (0)
-#define WM_LAUNCH(KERNEL, SMEM, ...)                                   \
-    do {                                                               \
-        static bool done_[64] = {false};                               \
-        int dev_ = 0;                                                  \
-        cudaGetDevice(&dev_);                                          \
-        if (!done_[dev_ & 63]) { cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); done_[dev_ & 63] = true; } \
-        KERNEL<<<grid, NT, SMEM, st>>>(__VA_ARGS__);                   \
-    } while (0)
+#define WM_LAUNCH(KERNEL, SMEM, ...) WM_LAUNCH_T(KERNEL, NT, SMEM, __VA_ARGS__)
