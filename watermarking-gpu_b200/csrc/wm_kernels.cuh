@@ -141,7 +141,12 @@ __device__ __forceinline__ unsigned long long gtime()
 // the conversion pipe per warp, tools/microbench/pipes.cu), which made the conversion of the u8 kernels' windows as expensive
 // as their arithmetic.  Instead: byte b -> the half with bits 0x6400 | b (= 1024 + b, exact), one PRMT per PAIR of pixels,
 // then a mixed-precision add of -1024 (FHADD, full rate on the FMA pipe) widens and removes the bias in one exact step.
-__device__ __forceinline__ void u8x4_to_f32(unsigned u, float& x0, float& x1, float& x2, float& x3)
+// `kb` is the -1024 of that add.  As a literal (the default) ptxas re-materialises it, a MOV from a uniform register next to almost every
+// FHADD (38 MOVs per 16 pixels in the detector's first phase); the u8 tile loops therefore pass a value READ FROM SHARED MEMORY (written once
+// per CTA, see u8_bias_init / u8_bias_get), which ptxas cannot see through and so keeps in one register.
+__device__ __forceinline__ void u8_bias_init(float* s_kb) { if (threadIdx.x == 0) *s_kb = -1024.0f; }  // a __syncthreads must follow
+__device__ __forceinline__ float u8_bias_get(const float* s_kb) { return *reinterpret_cast<const volatile float*>(s_kb); }
+__device__ __forceinline__ void u8x4_to_f32(unsigned u, float& x0, float& x1, float& x2, float& x3, float kb = -1024.0f)
 {
     const unsigned lo = __byte_perm(u, 0x64646464u, 0x4140);  // (0x64, b1, 0x64, b0)
     const unsigned hi = __byte_perm(u, 0x64646464u, 0x4342);  // (0x64, b3, 0x64, b2)
@@ -149,7 +154,7 @@ __device__ __forceinline__ void u8x4_to_f32(unsigned u, float& x0, float& x1, fl
         "mov.b32 {a, b}, %4;\n\tmov.b32 {c, d}, %5;\n\t"
         "add.rn.f32.f16 %0, a, %6;\n\tadd.rn.f32.f16 %1, b, %6;\n\t"
         "add.rn.f32.f16 %2, c, %6;\n\tadd.rn.f32.f16 %3, d, %6;\n\t}"
-        : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(lo), "r"(hi), "f"(-1024.0f));
+        : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(lo), "r"(hi), "f"(kb));
 }
 // single pixel: 2^23 + b as an f32 bit pattern, minus 2^23 (LOP3 + FADD)
 __device__ __forceinline__ float px_f32(unsigned char b) { return __fadd_rn(__uint_as_float(0x4b000000u | (unsigned)b), -8388608.0f); }
@@ -715,7 +720,7 @@ __device__ __forceinline__ unsigned lds_u8_if(const unsigned char* p, bool pred)
 }
 // Must be called by all 32 lanes of a warp.  (A predicated edge load instead of the divergent `if` — see the u8 overload — was measured
 // 1-4 % slower here: as an asm volatile it pins the schedule of the surrounding vector loads.)
-__device__ __forceinline__ void load_win6(float (&w)[6], const float* line, int sc)
+__device__ __forceinline__ void load_win6(float (&w)[6], const float* line, int sc, float /*kb*/ = 0.0f)
 {
     const int lane = threadIdx.x & 31;
     const float4 v = *reinterpret_cast<const float4*>(line + sc);
@@ -731,12 +736,12 @@ __device__ __forceinline__ void load_win6(float (&w)[6], const float* line, int 
 // the same window from a u8 TMA stage line (`line` = row start; the tile's column sc sits at byte U8_OFF + sc, 4-byte aligned)
 // u8 frames: the edge lanes' halo byte is a PREDICATED load (no divergent BSSY / BRA / BSYNC region on every line) followed by two
 // selects on lane constants: +5 % on the u8 apply kernel
-__device__ __forceinline__ void load_win6(float (&w)[6], const unsigned char* line, int sc)
+__device__ __forceinline__ void load_win6(float (&w)[6], const unsigned char* line, int sc, float kb = -1024.0f)
 {
     const int lane = threadIdx.x & 31;
     const unsigned u = *reinterpret_cast<const unsigned*>(line + U8_OFF + sc);
     float x0, x1, x2, x3;
-    u8x4_to_f32(u, x0, x1, x2, x3);
+    u8x4_to_f32(u, x0, x1, x2, x3, kb);
     float l = __shfl_up_sync(0xffffffffu, x3, 1);
     float r = __shfl_down_sync(0xffffffffu, x0, 1);
     const unsigned hb = lds_u8_if(line + U8_OFF + sc + (lane == 0 ? -1 : 4), lane == 0 || lane == 31);
@@ -818,70 +823,64 @@ static __device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* s
         if (b < 8) dbg->Rx[a * 8 + b] = v; else dbg->rx[a] = v;
     }
     __syncwarp();
-    T A[9];
-    const bool rowlane = lane < 8;
+    // The 8 x 9 system is spread over the whole warp: lane = (row ri, column group cg) holds A[ri][cg], A[ri][cg + 4] and (redundantly in
+    // the four lanes of a row) the right-hand side A[ri][8].  Per elimination step: column k goes through shared memory, EVERY lane finds the
+    // pivot itself (no shuffle reduction), the pivot row and row k are exchanged through shared memory, and every lane computes its row's
+    // multiplier — one division per step on the critical path instead of a division plus 3 x 3 double-word shuffles plus nine dependent
+    // multiply-subtracts per lane (the old lane = row layout: 6.4 us of every sweep's tail).  Same operations on the same operands in the
+    // oracle's order, so the result is bit-equal to the plain C LU (oracle/wm_oracle.c: wmo_solve8).
+    const int ri = lane >> 2, cg = lane & 3;
+    T e0 = (T)M[ri * 9 + cg], e1 = (T)M[ri * 9 + cg + 4], e2 = (T)M[ri * 9 + 8];
+    double amax = fmax(fabs(M[ri * 9 + cg]), fabs(M[ri * 9 + cg + 4]));
 #pragma unroll
-    for (int j = 0; j < 9; j++) A[j] = rowlane ? (T)M[lane * 9 + j] : (T)0;
-    double amax = 0.0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) amax = fmax(amax, fabs(rowlane ? M[lane * 9 + j] : 0.0));
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    amax = __shfl_sync(0xffffffffu, amax, 0);
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     int singular = (!(amax > 0.0)) || !isfinite(amax);
     const T tol = Ops::tol(amax);
-    __syncwarp();
-    // Rows are exchanged and the pivot row is broadcast through shared memory (M is free once the rows sit in registers): two row
-    // writes + broadcast reads per step instead of 36 double-word shuffles — the one-warp solve was 6.6 us of every sweep's tail.
-    T* const xrow = reinterpret_cast<T*>(M);        // [0..8] = row k before the swap, [9..17] = the pivot row
+    __syncwarp();  // every lane has read its entries of M: the array is reused as exchange buffers from here on
+    T* const colbuf = reinterpret_cast<T*>(M);  // [8]  column k
+    T* const pivrow = colbuf + 8;               // [9]  the pivot row
+    T* const krow = colbuf + 17;                // [9]  row k before the exchange
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        // first maximal |A[i][k]|, i >= k
-        T v = (rowlane && lane >= k) ? (T)fabs(A[k]) : (T)-1;
-        int idx = lane;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            const T ov = __shfl_xor_sync(0xffffffffu, v, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-        }
-        const int piv = __shfl_sync(0xffffffffu, idx, 0) & 7;
-        const T pv = __shfl_sync(0xffffffffu, v, 0);
-        if (!(pv > tol)) singular = 1;
-        if (lane == k) {
-#pragma unroll
-            for (int j = 0; j < 9; j++) xrow[j] = A[j];
-        }
-        if (lane == piv) {
-#pragma unroll
-            for (int j = 0; j < 9; j++) xrow[9 + j] = A[j];
-        }
+        if (cg == (k & 3)) colbuf[ri] = k < 4 ? e0 : e1;
         __syncwarp();
-        T pr[9];
+        // first maximal |A[i][k]|, i >= k (ascending i, strict >: the oracle's pivot)
+        int piv = k;
+        T pv = colbuf[k], pa = (T)fabs(pv);
 #pragma unroll
-        for (int j = 0; j < 9; j++) pr[j] = xrow[9 + j];  // row k after the swap
-        if (lane == k) {
-#pragma unroll
-            for (int j = 0; j < 9; j++) A[j] = pr[j];
-        } else if (lane == piv) {
-#pragma unroll
-            for (int j = 0; j < 9; j++) A[j] = xrow[j];
+        for (int i = k + 1; i < 8; i++) {
+            const T v = colbuf[i], va = (T)fabs(v);
+            if (va > pa) { pa = va; pv = v; piv = i; }
         }
+        if (!(pa > tol)) singular = 1;
+        // my row's column-k entry after the exchange, and its multiplier (used by rows below k only)
+        const T aik = ri == piv ? colbuf[k] : colbuf[ri];
+        const T f = Ops::div(aik, pv);
+        if (ri == piv) { pivrow[cg] = e0; pivrow[cg + 4] = e1; if (cg == 0) pivrow[8] = e2; }
+        if (ri == k) { krow[cg] = e0; krow[cg + 4] = e1; if (cg == 0) krow[8] = e2; }
         __syncwarp();
-        if (rowlane && lane > k) {
-            const T f = Ops::div(A[k], pr[k]);
-#pragma unroll
-            for (int j = k; j < 9; j++) A[j] = Ops::mulsub(A[j], f, pr[j]);
+        const T p0 = pivrow[cg], p1 = pivrow[cg + 4], p2 = pivrow[8];
+        if (ri == k) { e0 = p0; e1 = p1; e2 = p2; }
+        else if (ri == piv) { e0 = krow[cg]; e1 = krow[cg + 4]; e2 = krow[8]; }
+        if (ri > k) {  // columns <= k of the rows below are never read again (the oracle stores a value there that nothing uses)
+            if (cg > k) e0 = Ops::mulsub(e0, f, p0);
+            if (cg + 4 > k) e1 = Ops::mulsub(e1, f, p1);
+            e2 = Ops::mulsub(e2, f, p2);
         }
     }
+    __syncwarp();
+    T* const U = reinterpret_cast<T*>(M);  // [8][9] upper triangle + right-hand side
+    U[ri * 9 + cg] = e0; U[ri * 9 + cg + 4] = e1;
+    if (cg == 0) U[ri * 9 + 8] = e2;
+    __syncwarp();
+    // back substitution: a serial chain by nature (row i needs c[i+1] first); every lane runs it on the shared copy
     T cc[8];
 #pragma unroll
     for (int i = 7; i >= 0; i--) {
-        T s = A[8];
+        T s_ = U[i * 9 + 8];
 #pragma unroll
-        for (int j = i + 1; j < 8; j++) s = Ops::mulsub(s, A[j], cc[j]);
-        const T ci = Ops::div(s, A[i]);
-        cc[i] = __shfl_sync(0xffffffffu, ci, i);
+        for (int j = i + 1; j < 8; j++) s_ = Ops::mulsub(s_, U[i * 9 + j], cc[j]);
+        cc[i] = Ops::div(s_, U[i * 9 + i]);
     }
     if (lane == 0) {
         sc->status = singular ? 1 : 0;
@@ -1543,18 +1542,18 @@ __device__ __forceinline__ void mask_from_plane(float (&m)[4], const MaskSrc& ms
 }
 template <int MASK, bool TR, typename T, typename F>
 __device__ __forceinline__ void mask_lines(const T* __restrict__ tile, const float* __restrict__ wt, const float (&c)[8], F f,
-                                           const MaskSrc ms = MaskSrc{nullptr, 0, 0, 0})
+                                           const MaskSrc ms = MaskSrc{nullptr, 0, 0, 0}, const float kb = -1024.0f)
 {
     constexpr int ST = TileGeo<T>::STRIDE;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const T* tb = tile + (4 * w) * ST;  // smem line of image line l-1 for r = 0
     const int scol = 4 * lane + HP;
     float r0[6], r1[6], r2[6];
-    load_win6(r0, tb, scol);
-    load_win6(r1, tb + ST, scol);
+    load_win6(r0, tb, scol, kb);
+    load_win6(r1, tb + ST, scol, kb);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        load_win6(r2, tb + (r + 2) * ST, scol);
+        load_win6(r2, tb + (r + 2) * ST, scol, kb);
         const float4 wv = *reinterpret_cast<const float4*>(wt + (4 * w + r) * TP + 4 * lane);
         const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
         float m[4];
@@ -1594,7 +1593,11 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
     const int nblk = blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y);
     if ((int)blockIdx.x >= nblk) return;
     bool skip = false;
+    __shared__ float s_kb;
+    float kb = -1024.0f;
+    u8_bias_init(&s_kb);
     embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&]() {
+        if constexpr (TMA && sizeof(PixT) == 1) kb = u8_bias_get(&s_kb);  // after the loop's first __syncthreads
         pdl_wait();  // the sweep's coefficients (ME) are valid from here on
         if (MASK == 0 && sc->status != 0) { skip = true; return false; }  // singular: a untouched, apply copies base through
 #pragma unroll
@@ -1616,7 +1619,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
                     fs = __fmaf_rn(u, u, fs);
                 }
             }, MASK == 2 ? MaskSrc{a.maskp + (long long)b * a.mask_bstride + (long long)(l0 + 4 * w) * P + pb, P, L - (l0 + 4 * w), P - pb}
-                         : MaskSrc{nullptr, 0, 0, 0});
+                         : MaskSrc{nullptr, 0, 0, 0}, kb);
         };
         if (l0 + TL <= L && p0 + TP <= P) run(BoolTag<true>{}); else run(BoolTag<false>{});
         dsum += (double)fs;
@@ -1712,7 +1715,11 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
     const bool out_vec = a.out_vec_ok != 0, base_vec = a.base_vec_ok != 0;
     const int channels = SB ? 1 : a.channels;
     bool through = false;
+    __shared__ float s_kb;
+    float kb = -1024.0f;
+    u8_bias_init(&s_kb);
     embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&]() {
+        if constexpr (TMA && sizeof(PixT) == 1) kb = u8_bias_get(&s_kb);  // after the loop's first __syncthreads
         pdl_wait();  // strength (and, for ME, coefficients and max|e|) of the stats pass are valid from here on
         if (sc->status != 0) { through = true; return false; }
 #pragma unroll
@@ -1756,7 +1763,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
                     store4<OutT>(orow, ov, FULL || (out_vec && nvalid >= 4), nvalid);
                 }
             }, MASK == 2 ? MaskSrc{a.maskp + (long long)b * a.mask_bstride + (long long)(l0 + 4 * w) * P + pb, P, L - (l0 + 4 * w), P - pb}
-                         : MaskSrc{nullptr, 0, 0, 0});
+                         : MaskSrc{nullptr, 0, 0, 0}, kb);
         };
         // the fast variant (FULL) has every test folded at compile time: the tile lies inside the image AND base / out rows can be accessed as
         // vectors (before, the per-line `vec` tests kept both the vector and the byte-wise stores, and a branch between them, in the hot loop)
@@ -1802,11 +1809,14 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply_ts(const __grid
         tma_load_3d(stage(s) + IPART, &tmW, tp * TP, tl * TL, 0, &bars[s]);
     };
     TileIter it(blockIdx.x, step, a.tiles_p), pf(blockIdx.x, step, a.tiles_p);
+    __shared__ float s_kb;
+    u8_bias_init(&s_kb);
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
         fence_barrier_init();
     }
     __syncthreads();
+    const float kb = U8T ? u8_bias_get(&s_kb) : -1024.0f;
     for (int s = 0; s < NST - 1; s++) {
         if (threadIdx.x == 0 && pf.t < a.ntiles) issue(pf.tl, pf.tp, s);
         pf.next();
@@ -1864,7 +1874,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply_ts(const __grid
             } else {
                 *reinterpret_cast<float4*>(wtile + (4 * w + r) * TP + 4 * lane) = make_float4(ov[0], ov[1], ov[2], ov[3]);
             }
-        });
+        }, MaskSrc{nullptr, 0, 0, 0}, kb);
         fence_proxy_async();  // every writer: generic-proxy smem writes -> visible to the TMA store
         if (U8T && threadIdx.x == 0) tma_store_wait_read<0>();  // the store of tile k-1 (the other byte tile) has left smem before tile k+1 writes it
         __syncthreads();
@@ -1910,7 +1920,7 @@ template <int MASK, bool TR, bool FULL, bool DBG, typename ZT>
 __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* __restrict__ wt, float* __restrict__ ut,
                                             const float (&c)[8], int l0, int p0,
                                             int L, int P, float& fd, float& fz, float& fu, const float* __restrict__ mplane = nullptr,
-                                            float* __restrict__ dbg_u = nullptr, float* __restrict__ dbg_eu = nullptr)
+                                            float* __restrict__ dbg_u = nullptr, float* __restrict__ dbg_eu = nullptr, const float kb = -1024.0f)
 {
     // MASK == 2: the NVF mask (p > 3) was computed into a dense L x P plane beforehand
     auto plane_at = [&](int l, int p) { return (l < L && p < P) ? __ldg(mplane + (long long)l * P + p) : 0.0f; };
@@ -1924,11 +1934,11 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* __
     {
         const ZT* zb = zt + (4 * w + 1) * ZS;  // smem line of image line l-1 for r = 0
         float r0[6], r1[6], r2[6];
-        load_win6(r0, zb, scol);
-        load_win6(r1, zb + ZS, scol);
+        load_win6(r0, zb, scol, kb);
+        load_win6(r1, zb + ZS, scol, kb);
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            load_win6(r2, zb + (r + 2) * ZS, scol);
+            load_win6(r2, zb + (r + 2) * ZS, scol, kb);
             const float4 wv = *reinterpret_cast<const float4*>(wt + (4 * w + r + 1) * SW + scol);
             const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
             float uu[4];
@@ -1961,9 +1971,9 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* __
         if (l >= 0 && l < L) {  // warp-uniform
             const ZT* zb = zt + (rl + 1) * ZS;
             float r0[6], r1[6], r2[6];
-            load_win6(r0, zb, scol);
-            load_win6(r1, zb + ZS, scol);
-            load_win6(r2, zb + 2 * ZS, scol);
+            load_win6(r0, zb, scol, kb);
+            load_win6(r1, zb + ZS, scol, kb);
+            load_win6(r2, zb + 2 * ZS, scol, kb);
             const float4 wv = *reinterpret_cast<const float4*>(wt + (rl + 1) * SW + scol);
             const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
             float uu[4];
@@ -2067,12 +2077,16 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
         tma_load_3d(stage(s) + ZPART, &tmW, tp * TP - HP, tl * TL - 1, 0, &bars[s]);
     };
     TileIter it(blockIdx.x, step, a.tiles_p), pf(blockIdx.x, step, a.tiles_p);  // current tile / tile whose loads are issued now
+    __shared__ float s_kb;
+    float kb = -1024.0f;
     if constexpr (TMA) {
+        u8_bias_init(&s_kb);
         if (threadIdx.x == 0) {
             for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
             fence_barrier_init();
         }
         __syncthreads();
+        if constexpr (U8T) kb = u8_bias_get(&s_kb);
         for (int s = 0; s < NST - 1; s++) {
             if (threadIdx.x == 0 && pf.t < a.ntiles) issue(pf.tl, pf.tp, s);
             pf.next();
@@ -2129,8 +2143,8 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
             }
         }
         float fd = 0.0f, fz = 0.0f, fu = 0.0f;
-        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true, DBG>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr, a.dbg_u, a.dbg_eu);
-        else detect_tile<MASK, TR, false, DBG>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr, a.dbg_u, a.dbg_eu);
+        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true, DBG>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr, a.dbg_u, a.dbg_eu, kb);
+        else detect_tile<MASK, TR, false, DBG>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr, a.dbg_u, a.dbg_eu, kb);
         ddot += (double)fd; dnz += (double)fz; dnu += (double)fu;
         if constexpr (TMA) __syncthreads();  // ut and the stage are rewritten from the next iteration on
     }
