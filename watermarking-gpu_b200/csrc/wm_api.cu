@@ -64,8 +64,7 @@ struct Slot {
     // direct delivery of synchronous single-image ops (slot 0 only): mapped pinned result + device sequence / completion counters
     HostResult* hres = nullptr;      // pinned host memory
     HostResult* hres_dev = nullptr;  // its device alias
-    unsigned* dl_words = nullptr;    // device: [0] sequence counter, [1] apply completion counter
-    unsigned dl_expected = 0;        // sequence number the next delivered op will publish
+    unsigned* dl_words = nullptr;    // device: [0] apply completion counter
 };
 
 }  // namespace
@@ -483,17 +482,15 @@ int ensure_direct(wm_ctx* ctx, Slot& s)
     CU(cudaHostAlloc(&s.hres, sizeof(HostResult), cudaHostAllocMapped));
     memset(s.hres, 0, sizeof(HostResult));
     CU(cudaHostGetDevicePointer((void**)&s.hres_dev, s.hres, 0));
-    CU(cudaMalloc(&s.dl_words, 2 * sizeof(unsigned)));
-    CU(cudaMemset(s.dl_words, 0, 2 * sizeof(unsigned)));
-    s.dl_expected = 0;
+    CU(cudaMalloc(&s.dl_words, sizeof(unsigned)));
+    CU(cudaMemset(s.dl_words, 0, sizeof(unsigned)));
     return WM_OK;
 }
 Deliver deliver_args(Slot& s, bool direct)
 {
     Deliver d;
     d.host = direct ? s.hres_dev : nullptr;
-    d.dev_seq = direct ? s.dl_words : nullptr;
-    d.done = direct ? s.dl_words + 1 : nullptr;
+    d.done = direct ? s.dl_words : nullptr;
     return d;
 }
 
@@ -772,26 +769,32 @@ std::string image_key(const wm_image* im)
              im->channels, im->layout, im->dtype, (long long)im->plane_stride);
     return b;
 }
-// wait for the op that was just launched with direct delivery: poll the mapped sequence word; the stream is only consulted every few
-// thousand polls so that a failed launch cannot spin forever
+// direct delivery: the host clears the token, launches, and polls the token; the stream is only consulted every few thousand polls so that a
+// failed launch cannot spin forever
+void arm_direct(Slot& s)
+{
+    s.hres->token = 0;
+    std::atomic_thread_fence(std::memory_order_release);
+}
 int wait_direct(wm_ctx* ctx, Slot& s, int kind, float* scalar_host)
 {
-    const unsigned want = ++s.dl_expected;
-    volatile unsigned* seq = &s.hres->seq;
-    for (unsigned spins = 0; *seq != want; spins++) {
+    volatile unsigned* tok = &s.hres->token;
+    for (unsigned spins = 0; *tok == 0; spins++) {
         if ((spins & 0x3fff) == 0x3fff) {
             const cudaError_t q = cudaStreamQuery(s.stream);
-            if (q == cudaSuccess) { if (*seq != want) return fail(ctx, WM_ERR_CUDA, "direct delivery: the op finished without publishing its result"); break; }
+            if (q == cudaSuccess) { if (*tok == 0) return fail(ctx, WM_ERR_CUDA, "direct delivery: the op finished without publishing its result"); break; }
             if (q != cudaErrorNotReady) return fail(ctx, WM_ERR_CUDA, std::string("direct delivery: ") + cudaGetErrorString(q));
         }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
-    const Scal h = s.hres->s;
+    const volatile HostResult* hr = s.hres;
+    const float a = hr->a, corr = hr->corr;
+    const int status = hr->status;
     if (scalar_host) {
-        if (kind == 1) { if (h.status != WM_SINGULAR) *scalar_host = h.a; }  // untouched when unsolvable (Watermark.cpp:164-165)
-        else *scalar_host = h.status == 0 ? h.corr : 0.0f;                  // Watermark.cpp:246-247
+        if (kind == 1) { if (status != WM_SINGULAR) *scalar_host = a; }  // untouched when unsolvable (Watermark.cpp:164-165)
+        else *scalar_host = status == 0 ? corr : 0.0f;                  // Watermark.cpp:246-247
     }
-    return h.status;
+    return status;
 }
 
 // Synchronous single-image calls.  The second call with identical arguments captures the launch sequence into a CUDA graph; from the
@@ -814,6 +817,7 @@ int run_sync(wm_ctx* ctx, const std::string& key, int kind, float* scalar_host, 
     }
     if (ge && ge->exec) {  // replay
         CU(cudaSetDevice(ctx->device));
+        arm_direct(s);
         CU(cudaGraphLaunch(ge->exec, s.stream));
         ctx->launches += ge->launches;
         return wait_direct(ctx, s, kind, scalar_host);
@@ -841,6 +845,7 @@ int run_sync(wm_ctx* ctx, const std::string& key, int kind, float* scalar_host, 
             if (rc < 0) return rc;
         }
         if (ge->exec) {
+            arm_direct(s);
             CU(cudaGraphLaunch(ge->exec, s.stream));
             ctx->launches += ge->launches;
             return wait_direct(ctx, s, kind, scalar_host);

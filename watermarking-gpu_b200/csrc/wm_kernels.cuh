@@ -95,31 +95,25 @@ struct Scal {
     float emax;      // max|e| (ME embed)
     float corr;
 };
-// Direct delivery of a synchronous single-image op (wm_embed / wm_detect): the op's last CTA copies the image's scalars into mapped pinned
-// host memory and then publishes a sequence number taken from a device counter; the host polls `seq` instead of paying a copy-engine
-// D2H node plus a stream synchronisation (about 10 us of a 50 us op).
+// Direct delivery of a synchronous single-image op (wm_embed / wm_detect): the op's last CTA writes the image's result — strength,
+// correlation, status and a non-zero token — into mapped pinned host memory with ONE 16-byte store; the host clears the token before the
+// launch and polls it, instead of paying a copy-engine D2H node plus a stream synchronisation (about 10 us of a 50 us op).  One store:
+// no system-scope fence between "data" and "flag", no device-side sequence counter.
 struct HostResult {
-    Scal s;
-    unsigned seq;
-    unsigned pad[3];
+    float a, corr;
+    int status;
+    unsigned token;  // 0 = pending (written by the host before the launch), 1 = delivered
 };
 struct Deliver {
     HostResult* host;    // mapped pinned memory (device alias); nullptr = results go through the stream-ordered copy as before
-    unsigned* dev_seq;   // device counter: ++ per delivered op
     unsigned* done;      // apply only: CTAs finished (wraps to 0 by itself)
 };
-__device__ __forceinline__ void deliver_result(const Deliver& d, const Scal* sc)
+__device__ __forceinline__ void deliver_result(const Deliver& d, float a, float corr, int status)
 {
-    static_assert(sizeof(Scal) == 48, "Scal is copied as three 16-byte words");
-    const int4* src = reinterpret_cast<const int4*>(sc);
-    const int4 v0 = __ldcg(src), v1 = __ldcg(src + 1), v2 = __ldcg(src + 2);
-    int4* hs = reinterpret_cast<int4*>(&d.host->s);
-    hs[0] = v0; hs[1] = v1; hs[2] = v2;
-    __threadfence_system();
-    const unsigned q = atomicAdd(d.dev_seq, 1u) + 1u;
-    *reinterpret_cast<volatile unsigned*>(&d.host->seq) = q;
-    __threadfence_system();
+    static_assert(sizeof(HostResult) == 16, "HostResult is delivered as one 16-byte store");
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(d.host), "r"(__float_as_uint(a)), "r"(__float_as_uint(corr)), "r"(status), "r"(1u) : "memory");
 }
+__device__ __forceinline__ void deliver_result(const Deliver& d, const Scal* sc) { deliver_result(d, __ldcg(&sc->a), __ldcg(&sc->corr), __ldcg(&sc->status)); }
 
 // parity/debug side-band (one per batch entry, only read back by wm_debug_get)
 struct ScalDbg {
@@ -799,24 +793,25 @@ template <typename Ops>
 static __device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* sc, ScalDbg* dbg, int transposed, double* M /* smem [8][9] */)
 {
     using T = typename Ops::T;
-    // internal (line, pixel) raster order of the 8 neighbours
-    const int DLc[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
-    const int DPc[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
-    // reference index k -> internal index (identity, or the transpose permutation)
-    const int PERM_T[8] = {0, 3, 5, 1, 6, 2, 4, 7};
+    // internal (line, pixel) raster order of the 8 neighbours: dl = {-1,-1,-1,0,0,1,1,1}, dp = {-1,0,1,-1,1,-1,0,1}; reference index k ->
+    // internal index: identity, or the transpose permutation {0,3,5,1,6,2,4,7}.  Nibble tables in registers (indexed arrays would live in
+    // local memory: this runs on the serial tail of every sweep).
+    auto DLc = [](int k) { return (int)((0x22211000u >> (4 * k)) & 15u) - 1; };
+    auto DPc = [](int k) { return (int)((0x21020210u >> (4 * k)) & 15u) - 1; };
+    auto PERM_T = [](int k) { return (int)((0x74261530u >> (4 * k)) & 15u); };
     const int lane = threadIdx.x & 31;
     // assemble (72 entries over 32 lanes)
     for (int e = lane; e < 72; e += 32) {
         const int a = e / 9, b = e - a * 9;
-        const int ia = transposed ? PERM_T[a] : a;
+        const int ia = transposed ? PERM_T(a) : a;
         double v;
         if (b < 8) {
-            const int ib = transposed ? PERM_T[b] : b;
+            const int ib = transposed ? PERM_T(b) : b;
             const int i = min(ia, ib), j = max(ia, ib);
             const int tri = i * 8 - (i * (i - 1)) / 2 + (j - i);
-            v = tot[lag_index(DLc[j] - DLc[i], DPc[j] - DPc[i])] + tot[NLAG + 8 + tri];
+            v = tot[lag_index(DLc(j) - DLc(i), DPc(j) - DPc(i))] + tot[NLAG + 8 + tri];
         } else {
-            const int lg = ia <= 3 ? lag_index(-DLc[ia], -DPc[ia]) : lag_index(DLc[ia], DPc[ia]);
+            const int lg = ia <= 3 ? lag_index(-DLc(ia), -DPc(ia)) : lag_index(DLc(ia), DPc(ia));
             v = tot[lg] + tot[NLAG + ia];
         }
         M[e] = v;
@@ -2157,8 +2152,9 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
     if (threadIdx.x == 0) {
         a.dbg[b].dot = red[0]; a.dbg[b].nz = red[1]; a.dbg[b].nu = red[2];
         const float dotf = (float)red[0];
-        sc->corr = dotf / (float)(sqrt(red[1]) * sqrt(red[2]));
-        if (a.dl.host) { __threadfence(); deliver_result(a.dl, sc); }
+        const float corr = dotf / (float)(sqrt(red[1]) * sqrt(red[2]));
+        sc->corr = corr;
+        if (a.dl.host) deliver_result(a.dl, 0.0f, corr, 0);
     }
 }
 
