@@ -74,6 +74,10 @@ enum {
     WM_OPT_PDL = 11,          /* 1 (default): the 2nd / 3rd kernel of an op is launched with programmatic stream serialization: it becomes resident, initialises
                                  its barriers and issues its first tile loads while the previous kernel's last block still reduces / solves, and executes
                                  griddepcontrol.wait before reading that kernel's results; 0: plain stream order */
+    WM_OPT_FUSED_SINGLE = 12, /* 0 (default): every op is 2-3 kernels chained with programmatic dependent launch; 1: a synchronous wm_detect on one f32 image
+                                 whose tiles fit the resident CTAs' shared memory (e.g. 1080p) runs as ONE cooperative kernel (k_detect1) that keeps its tiles in
+                                 shared memory across sweep -> solve -> detector.  Same results; measured 3 us SLOWER per op at 1080p (profiles/r2_latency.md:
+                                 the grid-wide hand-over costs more than the second launch it saves), kept as an experiment */
     WM_OPT_HOST_RUN_FRAMES = 9, /* frames per run (one batched launch sequence + its copies) of wm_process_frames when frames are in HOST memory; default 4 */
     WM_OPT_F32_SOLVE = 8      /* 0 (default): the 8x8 system is summed and solved in f64 (pivot cut 1e-12 max|Rx|); 1: Rx / rx are rounded to f32
                                  and solved by an f32 LU (pivot cut 1e-6 max|Rx|) like af::solve on the reference's f32 arrays

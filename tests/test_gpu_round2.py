@@ -451,3 +451,49 @@ def test_host_embed_verify_batch(wmb, oracle):
         o = oracle.embed(imgs[1], W, 40.0, mask)
         assert abs(a[1] - o["a"]) / o["a"] <= 1e-3 and abs(c[1] - oracle.detect(o["out"], W, mask)["corr"]) / abs(c[1]) <= 1e-3
     wm.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# single-image fused kernels (one cooperative launch per synchronous op) == the multi-kernel path
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,cols", [(1080, 1920), (512, 512), (700, 1000)])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_fused_single_image_ops_equal_multi_kernel_path(wmb, oracle, rows, cols, layout):
+    """wm_embed / wm_detect on one resident f32 image, called repeatedly (the reference's loops_for_test protocol, main.cpp:167-223): from the
+    second call on the op is captured / replayed and, with WM_OPT_FUSED_SINGLE = 1, wm_detect runs as ONE cooperative kernel (k_detect1).  Integer-valued pixels: every sum is exact,
+    so the fused op must give the same bits as the default multi-kernel path; the launch counter proves which path ran."""
+    img = util.natural_image(rows, cols, seed=11, integer=True).astype(np.float32)
+    W = util.normal_w(rows, cols)
+    res = {}
+    for fused in (1, 0):
+        wm = wmb.Watermark(rows, cols, W, 3, 40.0)
+        wm.set_option(wmb.OPT_FUSED_SINGLE, fused)
+        d = wmb.DeviceArray.from_numpy(wm, img, layout)
+        out = wmb.DeviceArray(wm, rows, cols, layout, wmb.F32)
+        r = {}
+        for mask in (wmb.ME, wmb.NVF):
+            for _ in range(4):  # 1st: plain, 2nd: capture, 3rd/4th: replay
+                n0 = wm.launch_count
+                _, a, st = wm.makeWatermark(d, d, mask, out=out)
+                ne = wm.launch_count - n0
+            assert st == 0
+            z = out.numpy().copy()
+            for _ in range(4):
+                n0 = wm.launch_count
+                corr, st = wm.detectWatermark(out, mask)
+                nd = wm.launch_count - n0
+            assert st == 0
+            r[mask] = (a, corr, z, ne, nd, wm.debug(wmb.DBG_COEFFS).copy())
+        res[fused] = r
+        wm.close()
+    for mask in (wmb.ME, wmb.NVF):
+        a1, c1, z1, ne1, nd1, k1 = res[1][mask]
+        a0, c0, z0, ne0, nd0, k0 = res[0][mask]
+        assert nd0 == 2 and ne0 == (3 if mask == wmb.ME else 2)
+        assert nd1 == 1, "the fused detector did not run"
+        assert np.array_equal(k1, k0) and c1 == c0, (mask, c1, c0)
+        assert a1 == a0 and np.array_equal(z1, z0)
+        o = oracle.detect(z1, W, mask)
+        assert abs(c1 - o["corr"]) <= 1e-3 * abs(o["corr"])
+        report("fused single-image ops %dx%d layout=%d mask=%d: corr %.7f (multi-kernel %.7f, oracle %.7f), launches embed %d detect %d" % (
+            rows, cols, layout, mask, c1, c0, o["corr"], ne1, nd1))

@@ -64,7 +64,7 @@ struct Slot {
     // direct delivery of synchronous single-image ops (slot 0 only): mapped pinned result + device sequence / completion counters
     HostResult* hres = nullptr;      // pinned host memory
     HostResult* hres_dev = nullptr;  // its device alias
-    unsigned* dl_words = nullptr;    // device: [0] apply completion counter
+    unsigned* dl_words = nullptr;    // device: [0] apply completion counter, [1] generation word of the fused single-image kernels' hand-over
 };
 
 }  // namespace
@@ -78,6 +78,8 @@ struct wm_ctx {
     Slot slots[NSLOTS];
     int opt_fp16 = 1, opt_timing = 0, opt_tma = 1, opt_serial = 0, opt_mma = 1, opt_f32_solve = 0;
     int opt_pdl = 1;         // WM_OPT_PDL: 2nd / 3rd kernel of an op launched with programmatic stream serialization
+    int opt_fused = 0;       // WM_OPT_FUSED_SINGLE: synchronous single-image detect as one cooperative kernel where the image fits (measured slower: off)
+    int fused_failures = 0;  // cooperative launches that were refused (the op then takes the multi-kernel path)
     int opt_tma_store = 1;   // WM_OPT_TMA_STORE: apply kernel output through TMA stores where the shape allows (+8..10 % on the apply kernel)
     int opt_host_run = 4;    // frames per run of the video driver's host-frame path (WM_OPT_HOST_RUN_FRAMES)
     int opt_split_cost = 8;  // tile-times one more launch is assumed to cost when a batch is partitioned (WM_OPT_SPLIT_COST)
@@ -407,6 +409,40 @@ int push_result(wm_ctx* ctx, Slot& s, int kind, int batch)
     return WM_OK;
 }
 
+SweepArgs sweep_args(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int batch, const Geo& g, const Plan& pl)
+{
+    SweepArgs a;
+    memset(&a, 0, sizeof a);
+    a.img = v.ptr; a.ld = v.ld; a.bstride = bstride;
+    a.L = g.L; a.P = g.P; a.tiles_p = g.tiles_p; a.ntiles = g.ntiles;
+    a.nsweep = pl.nsweep; a.nframe = pl.nframe;
+    a.vec_ok = vec_ok(v.ptr, v.ld, bstride, 0, v.dtype);
+    a.transposed = v.transposed;
+    a.solve_f32 = ctx->opt_f32_solve;
+    a.part = s.part;
+    a.counter = s.counters;
+    a.gcounter = s.counters + 3 * (size_t)s.batch_cap;
+    a.gpart = s.part + (size_t)batch * ((size_t)pl.nsweep * NTOT + (size_t)std::max(pl.gx_stats, pl.gx_detect) * 3);
+    a.scal = s.scal; a.dbg = s.dbg;
+    return a;
+}
+
+// Single-image fused kernels (wm_kernels.cuh: k_detect1, k_embed1): `grid` CTAs keep at most `nst` tiles each in shared memory, and their
+// frame-ring slices must stay in the one-warp-per-pixel mode (<= 96 ring pixels per CTA; the per-thread mode needs more scratch than they have)
+bool fused_fits(const Geo& g, int grid, int nst, bool with_ring)
+{
+    if (grid < 1 || (long long)g.ntiles > (long long)nst * grid) return false;
+    if (!with_ring) return true;
+    const long long L = g.L, P = g.P;
+    const long long ntop = std::min(2LL, L), lbot = std::max(2LL, L - 2), nbot = std::max(0LL, L - lbot), nmid = std::max(0LL, L - 4);
+    const long long ncl = std::min(2LL, P), pright = std::max(2LL, P - 2), ncr = std::max(0LL, P - pright);
+    const long long count = (ntop + nbot) * P + nmid * (ncl + ncr);
+    const int nlong = g.ntiles % grid;
+    const bool light_only = nlong != 0 && 2 * (grid - nlong) >= grid;
+    const int nring = light_only ? grid - nlong : grid;
+    return (count + nring - 1) / nring <= 96;
+}
+
 // enqueue the Rx sweep (+ solve), or the injection of debug coefficients
 int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int batch, const Geo& g, const Plan& pl)
 {
@@ -420,18 +456,7 @@ int enqueue_sweep(wm_ctx* ctx, Slot& s, const View& v, long long bstride, int ba
         }
         return WM_OK;
     }
-    SweepArgs a;
-    a.img = v.ptr; a.ld = v.ld; a.bstride = bstride;
-    a.L = g.L; a.P = g.P; a.tiles_p = g.tiles_p; a.ntiles = g.ntiles;
-    a.nsweep = pl.nsweep; a.nframe = pl.nframe;
-    a.vec_ok = vec_ok(v.ptr, v.ld, bstride, 0, v.dtype);
-    a.transposed = v.transposed;
-    a.solve_f32 = ctx->opt_f32_solve;
-    a.part = s.part;
-    a.counter = s.counters;
-    a.gcounter = s.counters + 3 * (size_t)s.batch_cap;
-    a.gpart = s.part + (size_t)batch * ((size_t)pl.nsweep * NTOT + (size_t)std::max(pl.gx_stats, pl.gx_detect) * 3);
-    a.scal = s.scal; a.dbg = s.dbg;
+    SweepArgs a = sweep_args(ctx, s, v, bstride, batch, g, pl);
     CUtensorMap tmI;
     memset(&tmI, 0, sizeof tmI);
     bool tma = tma_ok(ctx, v, bstride, batch);
@@ -482,8 +507,8 @@ int ensure_direct(wm_ctx* ctx, Slot& s)
     CU(cudaHostAlloc(&s.hres, sizeof(HostResult), cudaHostAllocMapped));
     memset(s.hres, 0, sizeof(HostResult));
     CU(cudaHostGetDevicePointer((void**)&s.hres_dev, s.hres, 0));
-    CU(cudaMalloc(&s.dl_words, sizeof(unsigned)));
-    CU(cudaMemset(s.dl_words, 0, sizeof(unsigned)));
+    CU(cudaMalloc(&s.dl_words, 2 * sizeof(unsigned)));
+    CU(cudaMemset(s.dl_words, 0, 2 * sizeof(unsigned)));
     return WM_OK;
 }
 Deliver deliver_args(Slot& s, bool direct)
@@ -607,7 +632,13 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     if ((rc = ensure_slot(ctx, s, batch, std::max(pl.gx_stats, pl.gx_detect), pl.nsweep, pl.nframe))) return rc;
     const float* W = w_for(ctx, v.transposed, s.stream, &rc);
     if (rc) return rc;
-    if ((rc = enqueue_sweep(ctx, s, v, img_stride, batch, g, pl))) return rc;
+    const bool planes = mask == WM_MASK_NVF && ctx->p != 3;
+    bool tma = tma_ok(ctx, v, img_stride, batch);
+    // synchronous single image: sweep + solve + detector as ONE cooperative kernel with the tiles kept in shared memory
+    const int fgrid = std::min(g.ntiles, detect_ctas_per_sm(false) * ctx->sms);
+    const bool fuse = direct && batch == 1 && ctx->opt_fused && tma && v.dtype == WM_F32 && !planes && ctx->opt_fp16 && ctx->opt_mma &&
+                      !ctx->inject_coef && !ctx->opt_timing && !dbg_u && fused_fits(g, fgrid, DETECT_NST, true);
+    if (!fuse && (rc = enqueue_sweep(ctx, s, v, img_stride, batch, g, pl))) return rc;
     DetectArgs da;
     da.img = v.ptr; da.ld = v.ld; da.bstride = img_stride;
     da.W = W;
@@ -615,7 +646,6 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     da.vec_ok = vec_ok(v.ptr, v.ld, img_stride, 0, v.dtype);
     da.w_vec_ok = (g.P % 4 == 0);
     da.pstride = pl.gx_detect;
-    const bool planes = mask == WM_MASK_NVF && ctx->p != 3;
     da.maskp = nullptr; da.mask_bstride = (long long)g.L * g.P;
     da.part = s.part + stats_part_offset(pl, batch);
     da.counter = s.counters + 2 * s.batch_cap;
@@ -625,9 +655,19 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     CUtensorMap tmZ, tmW;
     memset(&tmZ, 0, sizeof tmZ);
     memset(&tmW, 0, sizeof tmW);
-    bool tma = tma_ok(ctx, v, img_stride, batch);
     if (tma) tma = make_tmap(&tmZ, v.dtype, v.ptr, g.P, g.L, batch, v.ld, img_stride, SW, TL + 4) &&
                    make_tmap(&tmW, WM_F32, W, g.P, g.L, 1, g.P, 0, SW, TL + 2);
+    if (fuse) {
+        da.b0 = 0; da.nblk_base = fgrid; da.nblk_extra = 0;
+        const SweepArgs sa = sweep_args(ctx, s, v, img_stride, batch, g, pl);
+        if (tma && launch_detect1(mask, v.transposed, fgrid, s.stream, tmZ, tmW, sa, da, s.dl_words + 1, ctx->sms)) {
+            ctx->launches++;
+            CU(cudaGetLastError());
+            return WM_OK;  // the kernel's last CTA publishes the result itself
+        }
+        ctx->fused_failures++;
+        if ((rc = enqueue_sweep(ctx, s, v, img_stride, batch, g, pl))) return rc;
+    }
     {
         KTimer t(ctx, s, mask == WM_MASK_ME ? WM_K_DETECT : WM_K_DETECT_NVF);
         if (planes) {
@@ -908,7 +948,7 @@ int wm_clone(const wm_ctx* src, wm_ctx** out)
     ctx->p = src->p; ctx->psnr = src->psnr; ctx->strength = src->strength;
     ctx->w = src->w;
     ctx->opt_fp16 = src->opt_fp16; ctx->opt_mma = src->opt_mma; ctx->opt_split_cost = src->opt_split_cost; ctx->opt_timing = src->opt_timing; ctx->opt_tma = src->opt_tma;
-    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run; ctx->opt_tma_store = src->opt_tma_store; ctx->opt_pdl = src->opt_pdl;
+    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run; ctx->opt_tma_store = src->opt_tma_store; ctx->opt_pdl = src->opt_pdl; ctx->opt_fused = src->opt_fused;
     const int rc = init_slots(ctx, nullptr);
     if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
     *out = ctx;
@@ -959,6 +999,7 @@ int wm_set_option(wm_ctx* ctx, int option, int value)
     case WM_OPT_HOST_RUN_FRAMES: ctx->opt_host_run = std::max(1, std::min(value, 64)); return WM_OK;
     case WM_OPT_TMA_STORE: ctx->opt_tma_store = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_PDL: ctx->opt_pdl = value != 0; clear_graphs(ctx); return WM_OK;
+    case WM_OPT_FUSED_SINGLE: ctx->opt_fused = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_F32_SOLVE: ctx->opt_f32_solve = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_SPLIT_COST: ctx->opt_split_cost = value < 0 ? 1 << 28 : value; return WM_OK;
     default: return fail(ctx, WM_ERR_ARG, "unknown option");
@@ -1213,7 +1254,7 @@ int wm_debug_get(wm_ctx* ctx, int what, void* dst)
     }
     case WM_DBG_PHASES: {
         double* o = (double*)dst;
-        for (int i = 0; i < 8; i++) o[i] = (i >= 1 && i <= 5) ? (double)(long long)(d.ts[i] - d.ts[0]) : 0.0;
+        for (int i = 0; i < 8; i++) o[i] = (i >= 1 && d.ts[i] != 0) ? (double)(long long)(d.ts[i] - d.ts[0]) : 0.0;
         return WM_OK;
     }
     default: return fail(ctx, WM_ERR_ARG, "unknown debug item");

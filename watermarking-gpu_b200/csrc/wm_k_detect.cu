@@ -24,6 +24,31 @@ void launch_detect(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream
     else { if (tma) launch_detect_t<uint8_t, true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_t<uint8_t, false>(mask, tr, grid, st, tmZ, tmW, a); }
 }
 
+// cooperative launch of a single-image fused kernel: every CTA must be resident at once (they hand over through a spin-wait)
+template <typename K, typename... Args>
+static bool launch_coop(K kernel, int threads, int smem, int grid_x, int sms, cudaStream_t st, Args... args)
+{
+    // (set on every call: these launches are captured into a CUDA graph once per image, and K is the same type for every instantiation)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm * sms < grid_x) { cudaGetLastError(); return false; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid_x); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kernel, args...) != cudaSuccess) { cudaGetLastError(); return false; }
+    return true;
+}
+bool launch_detect1(int mask, bool tr, int grid_x, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const SweepArgs& sa,
+                    const DetectArgs& a, unsigned* gen, int sms)
+{
+    const int smem = detect_smem(true, false);
+    if (mask == WM_MASK_ME) return tr ? launch_coop(k_detect1<0, true>, NT, smem, grid_x, sms, st, tmZ, tmW, sa, a, gen) : launch_coop(k_detect1<0, false>, NT, smem, grid_x, sms, st, tmZ, tmW, sa, a, gen);
+    return tr ? launch_coop(k_detect1<1, true>, NT, smem, grid_x, sms, st, tmZ, tmW, sa, a, gen) : launch_coop(k_detect1<1, false>, NT, smem, grid_x, sms, st, tmZ, tmW, sa, a, gen);
+}
+
 void launch_plane(int dtype, int what_errseq, bool tr, dim3 grid, cudaStream_t st, const PlaneArgs& a)
 {
 #define WM_PLANE(PIX)                                                                                             \

@@ -551,13 +551,31 @@ __device__ __forceinline__ void block_column_reduce(const double* __restrict__ p
             for (int u = 0; u < U; u++) acc = v >= MAXV0 ? fmax(acc, x[u]) : acc + x[u];
         }
     }
-    scratch[threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        double t = scratch[threadIdx.x];
+    if constexpr (NVP < 32) {
+        // a warp holds 32 / NVP row groups of every column: butterfly over the group bits of the lane first (fixed order), so the
+        // serial part is one value per WARP instead of one per group (stats: 127 dependent f64 adds -> 4 shuffle levels + 7 adds)
+#pragma unroll
+        for (int o = 16; o >= NVP; o >>= 1) {
+            const double y = __shfl_xor_sync(0xffffffffu, acc, o);
+            acc = v >= MAXV0 ? fmax(acc, y) : acc + y;
+        }
+        if ((threadIdx.x & 31) < NVP) scratch[(threadIdx.x >> 5) * NVP + v] = acc;
+        __syncthreads();
+        if (threadIdx.x < NV) {
+            double t = scratch[threadIdx.x];
+#pragma unroll
+            for (int k = 1; k < NT / 32; k++) { const double y = scratch[k * NVP + threadIdx.x]; t = (int)threadIdx.x >= MAXV0 ? fmax(t, y) : t + y; }
+            out[threadIdx.x] = t;
+        }
+    } else {
+        scratch[threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.x < NV) {
+            double t = scratch[threadIdx.x];
 #pragma unroll 4
-        for (int k = 1; k < G; k++) { const double y = scratch[k * NVP + threadIdx.x]; t = (int)threadIdx.x >= MAXV0 ? fmax(t, y) : t + y; }
-        out[threadIdx.x] = t;
+            for (int k = 1; k < G; k++) { const double y = scratch[k * NVP + threadIdx.x]; t = (int)threadIdx.x >= MAXV0 ? fmax(t, y) : t + y; }
+            out[threadIdx.x] = t;
+        }
     }
     __syncthreads();
 }
@@ -930,12 +948,15 @@ __device__ __forceinline__ void sweep_tile(const float* __restrict__ tile, int l
 
 // the same 13 lags with the rounded products summed by HMMA (see mma_acc4): per pixel pair 3 HMMAs take lags 0..11, the
 // four lag-12 pairs of two lines share a fourth
-template <bool FULL>
+// LPT lines per thread (warp w takes lines LPT * w ..), ROW0 = smem row of the tile's line l0 (the single-image fused kernels sweep a
+// stage that starts 1 or 2 lines above the tile with 8 warps x 4 lines)
+template <bool FULL, int LPT = SLPT, int ROW0 = 0>
 __device__ __forceinline__ void sweep_tile_mma(const float* __restrict__ tile, int l0, int p0, int L, int P,
                                                float (&c)[NACC], const MmaSel& sel)
 {
+    static_assert(LPT % 2 == 0, "the lag-12 products of two lines share an HMMA");
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const float* base = tile + (SLPT * w) * SW + 4 * lane + 2;
+    const float* base = tile + (ROW0 + LPT * w) * SW + 4 * lane + 2;
     const int pb = p0 + 4 * lane;
     bool vp[4];
 #pragma unroll
@@ -951,9 +972,9 @@ __device__ __forceinline__ void sweep_tile_mma(const float* __restrict__ tile, i
     loadrow(B, base + SW);
     unsigned q12[4];
 #pragma unroll
-    for (int r = 0; r < SLPT; r++) {
+    for (int r = 0; r < LPT; r++) {
         loadrow(C, base + (r + 2) * SW);
-        const int l = l0 + SLPT * w + r;
+        const int l = l0 + LPT * w + r;
         const bool vl = FULL || ((l >= 1) && (l <= L - 2));
 #pragma unroll
         for (int jj = 0; jj < 4; jj += 2) {
@@ -1069,6 +1090,195 @@ __device__ __forceinline__ void sweep_tile_h2_mma(const __half* __restrict__ til
         if (r & 1) mma_acc4(c + 12, q12[0], q12[1], q12[2], q12[3], sel);
         A = B; B = C;
     }
+}
+
+// ---- frame ring of the sweep: pixels within 2 of the border, naive products guarded by "partner not in core".  CTA `fb` of the image's
+// `nblk` CTAs takes a slice and writes its 44 partials to part[fb][NLAG ..].  scr: shared-memory scratch, NT * 40 bytes (PER_THREAD_OK:
+// at least NFRM * NT * 4); red: [(NT / 32) * NFRM] doubles.  PER_THREAD_OK = false (single-image fused kernels, whose scratch is small)
+// requires at most 96 ring pixels per CTA — the host checks that before choosing such a kernel.
+template <typename PixT, int FP16, int NTH, bool PER_THREAD_OK>
+__device__ __forceinline__ void sweep_ring(const PixT* __restrict__ img, long long ld, int L, int P, int ntiles, int fb, int nblk,
+                                           unsigned char* scr, double* red, double* part)
+{
+    constexpr int NT = NTH;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned char* const dsm = scr;
+    const int ntop = min(2, L), lbot = max(2, L - 2), nbot = L - lbot > 0 ? L - lbot : 0;
+    const int nmid = max(0, L - 4);
+    const int ncl = min(2, P), pright = max(2, P - 2), ncr = P - pright > 0 ? P - pright : 0;
+    const long long n1 = (long long)ntop * P, n2 = n1 + (long long)nbot * P;
+    const long long count = n2 + (long long)nmid * (ncl + ncr);
+    // One warp per ring pixel, one lane per product: lane v (< 32) owns partial v and, for v < 12, partial 32 + v,
+    // so the 44 partials never need a cross-lane reduction (only the 8 warps are summed through smem).
+    // partial t: t < 8 -> rx[t]; t >= 8 -> Rx pair (i, j), i <= j, in row-major upper-triangle order.
+    int pi[2], pj[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int t = lane + 32 * q;
+        int i = 0, j = 0;
+        if (t < 8) { i = t; j = 8; }              // j = 8 stands for the centre pixel
+        else if (t < NFRM) { int r = t - 8; i = 0; while (r >= 8 - i) { r -= 8 - i; i++; } j = i + r; }
+        pi[q] = i; pj[q] = j;
+    }
+    // chunks of NT ring pixels: thread t stages pixel t's 3x3 window (clamped) + its not-in-core bits in smem
+    // (all loads of a chunk in flight together).  Then either
+    //   (a) few ring pixels per block (single image, ~300 CTAs): each WARP walks staged pixels, one lane per product —
+    //       lane v owns partial v (and 32+v), so no cross-lane reduction at all (latency matters here), or
+    //   (b) many ring pixels per block (batched images, few CTAs each): each THREAD takes one staged pixel and all its
+    //       44 products in registers (32x fewer warp instructions per pixel), one block reduction at the end.
+    float* win = reinterpret_cast<float*>(dsm);            // [NT][9]  (the tile stages are idle by now)
+    unsigned* ncm = reinterpret_cast<unsigned*>(win + NT * 9);  // [NT]
+    // The ring is shared by the CTAs that walked one tile fewer than the others (when the tiles do not divide evenly and
+    // at least half of the CTAs are in that group), in equal contiguous slices — so a single image's critical path is
+    // max(2 tiles, 1 tile + ring slice), not 2 tiles + a 256-pixel chunk.
+    const int nlong = ntiles % nblk;  // CTAs 0 .. nlong-1 walked one more tile
+    const bool light_only = nlong != 0 && 2 * (nblk - nlong) >= nblk;
+    const int nring = light_only ? nblk - nlong : nblk;
+    const int rslot = light_only ? fb - nlong : fb;  // < 0: this CTA takes no ring pixels (its partials are zeros)
+    const long long per = (count + nring - 1) / nring;
+    const long long ring_lo = rslot < 0 ? count : min(count, per * rslot), ring_hi = rslot < 0 ? count : min(count, ring_lo + per);
+    const bool per_thread = PER_THREAD_OK && per > 96;
+    double f0 = 0.0, f1 = 0.0;
+    float tacc[NFRM];
+#pragma unroll
+    for (int v = 0; v < NFRM; v++) tacc[v] = 0.0f;
+    int chunks = 0;
+    double ftot = 0.0;  // mode (b): thread t < NFRM keeps the block total of partial t
+    for (long long c0 = ring_lo; c0 < ring_hi; c0 += NT) {
+        const long long idx = c0 + threadIdx.x;
+        __syncthreads();
+        if (idx < ring_hi) {
+            int l, p;
+            if (idx < n1) { l = (int)(idx / P); p = (int)(idx - (long long)l * P); }
+            else if (idx < n2) { const long long i2 = idx - n1; const int q = (int)(i2 / P); l = lbot + q; p = (int)(i2 - (long long)q * P); }
+            else { const long long i3 = idx - n2; const int q = (int)(i3 / (ncl + ncr)); const int c = (int)(i3 - (long long)q * (ncl + ncr)); l = 2 + q; p = c < ncl ? c : pright + (c - ncl); }
+            unsigned m = 0;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {  // raster order, k = 4 is the centre
+                const int ll = l + k / 3 - 1, pp = p + k % 3 - 1;
+                if (!(ll >= 1 && ll <= L - 2 && pp >= 1 && pp <= P - 2)) m |= 1u << k;
+                win[threadIdx.x * 9 + k] = px_f32(img[(long long)clampi(ll, 0, L - 1) * ld + clampi(pp, 0, P - 1)]);
+            }
+            ncm[threadIdx.x] = m;
+        }
+        __syncthreads();
+        const int nhere = (int)min((long long)NT, ring_hi - c0);
+        if (!per_thread) {
+            for (int px = w; px < nhere; px += NT / 32) {
+                const unsigned ncmask = ncm[px];
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int i = pi[q], j = pj[q];
+                    const int li = i < 4 ? i : i + 1, lj = j == 8 ? 4 : (j < 4 ? j : j + 1);  // neighbour index -> window slot
+                    float pr = __fmul_rn(win[px * 9 + li], win[px * 9 + lj]);
+                    if constexpr (FP16 != 0) pr = round_f16(pr);
+                    // rx[i], i <= 3 and every Rx pair: counted when p + o_i is not a core pixel; rx[i], i >= 4: when p is not
+                    const bool use = (j == 8 && i >= 4) ? ((ncmask >> 4) & 1) : ((ncmask >> li) & 1);
+                    if (lane + 32 * q < NFRM && use) { if (q == 0) f0 += (double)pr; else f1 += (double)pr; }
+                }
+            }
+        } else if ((int)threadIdx.x < nhere) {
+            const unsigned ncmask = ncm[threadIdx.x];
+            float n[8], nm[8];  // neighbours, and neighbours zeroed unless "p + o_i not in core"
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int sl = m < 4 ? m : m + 1;
+                n[m] = win[threadIdx.x * 9 + sl];
+                nm[m] = ((ncmask >> sl) & 1) ? n[m] : 0.0f;
+            }
+            const float x = win[threadIdx.x * 9 + 4];
+            const float xm = ((ncmask >> 4) & 1) ? x : 0.0f;
+            // a masked-out operand makes the product 0, which rounds to 0: same sum as skipping the term
+            float pr[NFRM];
+#pragma unroll
+            for (int m = 0; m < 8; m++) pr[m] = m <= 3 ? __fmul_rn(nm[m], x) : __fmul_rn(n[m], xm);
+            {
+                int t = 8;
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = i; j < 8; j++, t++) pr[t] = __fmul_rn(nm[i], n[j]);
+            }
+#pragma unroll
+            for (int t = 0; t < NFRM; t += 2) {
+                if constexpr (FP16 != 0) acc2_f16(tacc[t], tacc[t + 1], pr[t], pr[t + 1]);
+                else { tacc[t] = __fadd_rn(tacc[t], pr[t]); tacc[t + 1] = __fadd_rn(tacc[t + 1], pr[t + 1]); }
+            }
+        }
+        if (per_thread && ++chunks == 64) {  // block-uniform: keeps the f32 partials exact for integer pixels (64 * 65504 < 2^24)
+            __syncthreads();
+            block_sum_f32<NFRM, NT>(tacc, red);
+            if (threadIdx.x < NFRM) ftot += red[threadIdx.x];
+#pragma unroll
+            for (int v = 0; v < NFRM; v++) tacc[v] = 0.0f;
+            chunks = 0;
+        }
+    }
+    __syncthreads();
+    if (per_thread) {
+        // block reduction through smem (the tile stages and lag accumulators are idle by now): [NFRM][NT] floats, then
+        // NT / 64 threads per partial sum 64 columns each in f64 (column index rotated by the thread id: conflict-free)
+        float* redf = reinterpret_cast<float*>(dsm);
+#pragma unroll
+        for (int v = 0; v < NFRM; v++) redf[v * NT + threadIdx.x] = tacc[v];
+        __syncthreads();
+        static_assert(!PER_THREAD_OK || NFRM * NT * 4 <= sweep_smem(false, false), "ring reduction buffer must fit the smallest sweep smem");
+        constexpr int TPP = NT / 64;  // threads per partial, 64 columns each
+        if (threadIdx.x < ((TPP * NFRM + 31) & ~31)) {  // whole warps (shuffles below); the surplus lanes redo the last partial
+            const float* col = redf + min((int)threadIdx.x / TPP, NFRM - 1) * NT + (threadIdx.x % TPP) * 64;
+            double sacc = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < 64; k++) sacc += (double)col[(k + threadIdx.x) & 63];
+#pragma unroll
+            for (int o = 1; o < TPP; o <<= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            if ((threadIdx.x % TPP) == 0 && threadIdx.x < TPP * NFRM) red[threadIdx.x / TPP] = sacc;
+        }
+        __syncthreads();
+        if (threadIdx.x < NFRM) part[(size_t)fb * NTOT + NLAG + threadIdx.x] = ftot + red[threadIdx.x];
+    } else {
+        red[w * NFRM + lane] = f0;
+        if (lane < NFRM - 32) red[w * NFRM + 32 + lane] = f1;
+        __syncthreads();
+        if (threadIdx.x < NFRM) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < NT / 32; k++) sacc += red[k * NFRM + threadIdx.x];
+            part[(size_t)fb * NTOT + NLAG + threadIdx.x] = sacc;
+        }
+    }
+}
+
+// ---- second stage of the sweep: true for the ONE CTA of the image that finishes last, with the 57 column totals in tot (smem) ----
+template <int NTH>
+__device__ __forceinline__ bool sweep_second_stage(const SweepArgs& a, int b, int bx, int nblk, double* part, double* tot, double* scratch,
+                                                   unsigned long long& ts3)
+{
+    constexpr int NT = NTH;
+    if (nblk > SGRP && nblk <= SGRP * SMAXG) {
+        // Two levels (a single image is swept by ~590 CTAs: one CTA streaming 590 x 57 doubles was 8.5 us of serial tail).  Level 1: the
+        // CTA that finishes last within a group of SGRP consecutive partial rows sums them — this happens while other groups still work.
+        // Level 2: the last group to finish sums the <= 48 group rows.  The order of every addition is fixed by the indices alone.
+        const int g = bx / SGRP, gsz = min(SGRP, nblk - g * SGRP), ngrp = (nblk + SGRP - 1) / SGRP;
+        if (!last_block(a.gcounter + (size_t)b * SMAXG + g, gsz)) return false;
+        if (threadIdx.x < NTOT) {
+            const double* col = part + (size_t)g * SGRP * NTOT + threadIdx.x;
+            double x[SGRP];
+#pragma unroll
+            for (int r = 0; r < SGRP; r++) x[r] = r < gsz ? __ldcg(col + (size_t)r * NTOT) : 0.0;
+            double sg = 0.0;
+#pragma unroll
+            for (int r = 0; r < SGRP; r++) sg += x[r];
+            a.gpart[((size_t)b * SMAXG + g) * NTOT + threadIdx.x] = sg;
+        }
+        if (!last_block(a.counter + b, ngrp)) return false;
+        if (threadIdx.x == 0) ts3 = gtime();
+        block_column_reduce<NTOT, 64, NTOT, NT>(a.gpart + (size_t)b * SMAXG * NTOT, ngrp, tot, scratch);
+    } else {
+        if (!last_block(a.counter + b, nblk)) return false;
+        if (threadIdx.x == 0) ts3 = gtime();
+        block_column_reduce<NTOT, 64, NTOT, NT>(part, nblk, tot, scratch);
+    }
+    return true;
 }
 
 // FP16: 0 = f32 products (FFMA), 1 = products rounded to fp16, FHADD accumulation, 2 = rounded, HMMA accumulation
@@ -1222,183 +1432,14 @@ __global__ void __launch_bounds__(SNT, SWEEP_CTAS_PER_SM) k_sweep(const __grid_c
         __syncthreads();
     }
     if (threadIdx.x == 0) ts1 = gtime();
-    {
-        // ---- frame ring: pixels within 2 of the border, naive products guarded by "partner not in core" ----
-        const int fb = blockIdx.x;
-        const int ntop = min(2, L), lbot = max(2, L - 2), nbot = L - lbot > 0 ? L - lbot : 0;
-        const int nmid = max(0, L - 4);
-        const int ncl = min(2, P), pright = max(2, P - 2), ncr = P - pright > 0 ? P - pright : 0;
-        const long long n1 = (long long)ntop * P, n2 = n1 + (long long)nbot * P;
-        const long long count = n2 + (long long)nmid * (ncl + ncr);
-        // One warp per ring pixel, one lane per product: lane v (< 32) owns partial v and, for v < 12, partial 32 + v,
-        // so the 44 partials never need a cross-lane reduction (only the 8 warps are summed through smem).
-        // partial t: t < 8 -> rx[t]; t >= 8 -> Rx pair (i, j), i <= j, in row-major upper-triangle order.
-        int pi[2], pj[2];
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const int t = lane + 32 * q;
-            int i = 0, j = 0;
-            if (t < 8) { i = t; j = 8; }              // j = 8 stands for the centre pixel
-            else if (t < NFRM) { int r = t - 8; i = 0; while (r >= 8 - i) { r -= 8 - i; i++; } j = i + r; }
-            pi[q] = i; pj[q] = j;
-        }
-        // chunks of NT ring pixels: thread t stages pixel t's 3x3 window (clamped) + its not-in-core bits in smem
-        // (all loads of a chunk in flight together).  Then either
-        //   (a) few ring pixels per block (single image, ~300 CTAs): each WARP walks staged pixels, one lane per product —
-        //       lane v owns partial v (and 32+v), so no cross-lane reduction at all (latency matters here), or
-        //   (b) many ring pixels per block (batched images, few CTAs each): each THREAD takes one staged pixel and all its
-        //       44 products in registers (32x fewer warp instructions per pixel), one block reduction at the end.
-        float* win = reinterpret_cast<float*>(dsm);            // [NT][9]  (the tile stages are idle by now)
-        unsigned* ncm = reinterpret_cast<unsigned*>(win + NT * 9);  // [NT]
-        // The ring is shared by the CTAs that walked one tile fewer than the others (when the tiles do not divide evenly and
-        // at least half of the CTAs are in that group), in equal contiguous slices — so a single image's critical path is
-        // max(2 tiles, 1 tile + ring slice), not 2 tiles + a 256-pixel chunk.
-        const int nlong = a.ntiles % nblk;  // CTAs 0 .. nlong-1 walked one more tile
-        const bool light_only = nlong != 0 && 2 * (nblk - nlong) >= nblk;
-        const int nring = light_only ? nblk - nlong : nblk;
-        const int rslot = light_only ? fb - nlong : fb;  // < 0: this CTA takes no ring pixels (its partials are zeros)
-        const long long per = (count + nring - 1) / nring;
-        const long long ring_lo = rslot < 0 ? count : min(count, per * rslot), ring_hi = rslot < 0 ? count : min(count, ring_lo + per);
-        const bool per_thread = per > 96;
-        double f0 = 0.0, f1 = 0.0;
-        float tacc[NFRM];
-#pragma unroll
-        for (int v = 0; v < NFRM; v++) tacc[v] = 0.0f;
-        int chunks = 0;
-        double ftot = 0.0;  // mode (b): thread t < NFRM keeps the block total of partial t
-        for (long long c0 = ring_lo; c0 < ring_hi; c0 += NT) {
-            const long long idx = c0 + threadIdx.x;
-            __syncthreads();
-            if (idx < ring_hi) {
-                int l, p;
-                if (idx < n1) { l = (int)(idx / P); p = (int)(idx - (long long)l * P); }
-                else if (idx < n2) { const long long i2 = idx - n1; const int q = (int)(i2 / P); l = lbot + q; p = (int)(i2 - (long long)q * P); }
-                else { const long long i3 = idx - n2; const int q = (int)(i3 / (ncl + ncr)); const int c = (int)(i3 - (long long)q * (ncl + ncr)); l = 2 + q; p = c < ncl ? c : pright + (c - ncl); }
-                unsigned m = 0;
-#pragma unroll
-                for (int k = 0; k < 9; k++) {  // raster order, k = 4 is the centre
-                    const int ll = l + k / 3 - 1, pp = p + k % 3 - 1;
-                    if (!(ll >= 1 && ll <= L - 2 && pp >= 1 && pp <= P - 2)) m |= 1u << k;
-                    win[threadIdx.x * 9 + k] = px_f32(img[(long long)clampi(ll, 0, L - 1) * a.ld + clampi(pp, 0, P - 1)]);
-                }
-                ncm[threadIdx.x] = m;
-            }
-            __syncthreads();
-            const int nhere = (int)min((long long)NT, ring_hi - c0);
-            if (!per_thread) {
-                for (int px = w; px < nhere; px += NT / 32) {
-                    const unsigned ncmask = ncm[px];
-#pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        const int i = pi[q], j = pj[q];
-                        const int li = i < 4 ? i : i + 1, lj = j == 8 ? 4 : (j < 4 ? j : j + 1);  // neighbour index -> window slot
-                        float pr = __fmul_rn(win[px * 9 + li], win[px * 9 + lj]);
-                        if constexpr (FP16 != 0) pr = round_f16(pr);
-                        // rx[i], i <= 3 and every Rx pair: counted when p + o_i is not a core pixel; rx[i], i >= 4: when p is not
-                        const bool use = (j == 8 && i >= 4) ? ((ncmask >> 4) & 1) : ((ncmask >> li) & 1);
-                        if (lane + 32 * q < NFRM && use) { if (q == 0) f0 += (double)pr; else f1 += (double)pr; }
-                    }
-                }
-            } else if ((int)threadIdx.x < nhere) {
-                const unsigned ncmask = ncm[threadIdx.x];
-                float n[8], nm[8];  // neighbours, and neighbours zeroed unless "p + o_i not in core"
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    const int sl = m < 4 ? m : m + 1;
-                    n[m] = win[threadIdx.x * 9 + sl];
-                    nm[m] = ((ncmask >> sl) & 1) ? n[m] : 0.0f;
-                }
-                const float x = win[threadIdx.x * 9 + 4];
-                const float xm = ((ncmask >> 4) & 1) ? x : 0.0f;
-                // a masked-out operand makes the product 0, which rounds to 0: same sum as skipping the term
-                float pr[NFRM];
-#pragma unroll
-                for (int m = 0; m < 8; m++) pr[m] = m <= 3 ? __fmul_rn(nm[m], x) : __fmul_rn(n[m], xm);
-                {
-                    int t = 8;
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-#pragma unroll
-                        for (int j = i; j < 8; j++, t++) pr[t] = __fmul_rn(nm[i], n[j]);
-                }
-#pragma unroll
-                for (int t = 0; t < NFRM; t += 2) {
-                    if constexpr (FP16 != 0) acc2_f16(tacc[t], tacc[t + 1], pr[t], pr[t + 1]);
-                    else { tacc[t] = __fadd_rn(tacc[t], pr[t]); tacc[t + 1] = __fadd_rn(tacc[t + 1], pr[t + 1]); }
-                }
-            }
-            if (per_thread && ++chunks == 64) {  // block-uniform: keeps the f32 partials exact for integer pixels (64 * 65504 < 2^24)
-                __syncthreads();
-                block_sum_f32<NFRM, NT>(tacc, red);
-                if (threadIdx.x < NFRM) ftot += red[threadIdx.x];
-#pragma unroll
-                for (int v = 0; v < NFRM; v++) tacc[v] = 0.0f;
-                chunks = 0;
-            }
-        }
-        __syncthreads();
-        if (per_thread) {
-            // block reduction through smem (the tile stages and lag accumulators are idle by now): [NFRM][NT] floats, then
-            // NT / 64 threads per partial sum 64 columns each in f64 (column index rotated by the thread id: conflict-free)
-            float* redf = reinterpret_cast<float*>(dsm);
-#pragma unroll
-            for (int v = 0; v < NFRM; v++) redf[v * NT + threadIdx.x] = tacc[v];
-            __syncthreads();
-            static_assert(NFRM * NT * 4 <= sweep_smem(false, false), "ring reduction buffer must fit the smallest sweep smem");
-            constexpr int TPP = NT / 64;  // threads per partial, 64 columns each
-            if (threadIdx.x < ((TPP * NFRM + 31) & ~31)) {  // whole warps (shuffles below); the surplus lanes redo the last partial
-                const float* col = redf + min((int)threadIdx.x / TPP, NFRM - 1) * NT + (threadIdx.x % TPP) * 64;
-                double sacc = 0.0;
-#pragma unroll 8
-                for (int k = 0; k < 64; k++) sacc += (double)col[(k + threadIdx.x) & 63];
-#pragma unroll
-                for (int o = 1; o < TPP; o <<= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-                if ((threadIdx.x % TPP) == 0 && threadIdx.x < TPP * NFRM) red[threadIdx.x / TPP] = sacc;
-            }
-            __syncthreads();
-            if (threadIdx.x < NFRM) part[(size_t)fb * NTOT + NLAG + threadIdx.x] = ftot + red[threadIdx.x];
-        } else {
-            red[w * NFRM + lane] = f0;
-            if (lane < NFRM - 32) red[w * NFRM + 32 + lane] = f1;
-            __syncthreads();
-            if (threadIdx.x < NFRM) {
-                double sacc = 0.0;
-#pragma unroll
-                for (int k = 0; k < NT / 32; k++) sacc += red[k * NFRM + threadIdx.x];
-                part[(size_t)fb * NTOT + NLAG + threadIdx.x] = sacc;
-            }
-        }
-    }
+    sweep_ring<PixT, FP16, NT, true>(img, a.ld, L, P, a.ntiles, blockIdx.x, nblk, dsm, red, part);
 
     // ---- second stage + solve in the last block ----
     if (threadIdx.x == 0) ts2 = gtime();
     __shared__ double tot[NTOT];
     __shared__ double M[72];
     unsigned long long ts3 = 0, ts4 = 0;
-    if (nblk > SGRP && nblk <= SGRP * SMAXG) {
-        // Two levels (a single image is swept by ~590 CTAs: one CTA streaming 590 x 57 doubles was 8.5 us of serial tail).  Level 1: the
-        // CTA that finishes last within a group of SGRP consecutive partial rows sums them — this happens while other groups still work.
-        // Level 2: the last group to finish sums the <= 48 group rows.  The order of every addition is fixed by the indices alone.
-        const int g = blockIdx.x / SGRP, gsz = min(SGRP, nblk - g * SGRP), ngrp = (nblk + SGRP - 1) / SGRP;
-        if (!last_block(a.gcounter + (size_t)b * SMAXG + g, gsz)) return;
-        if (threadIdx.x < NTOT) {
-            const double* col = part + (size_t)g * SGRP * NTOT + threadIdx.x;
-            double x[SGRP];
-#pragma unroll
-            for (int r = 0; r < SGRP; r++) x[r] = r < gsz ? __ldcg(col + (size_t)r * NTOT) : 0.0;
-            double sg = 0.0;
-#pragma unroll
-            for (int r = 0; r < SGRP; r++) sg += x[r];
-            a.gpart[((size_t)b * SMAXG + g) * NTOT + threadIdx.x] = sg;
-        }
-        if (!last_block(a.counter + b, ngrp)) return;
-        if (threadIdx.x == 0) ts3 = gtime();
-        block_column_reduce<NTOT, 64, NTOT, NT>(a.gpart + (size_t)b * SMAXG * NTOT, ngrp, tot, reinterpret_cast<double*>(dsm));
-    } else {
-        if (!last_block(a.counter + b, nblk)) return;
-        if (threadIdx.x == 0) ts3 = gtime();
-        block_column_reduce<NTOT, 64, NTOT, NT>(part, nblk, tot, reinterpret_cast<double*>(dsm));
-    }
+    if (!sweep_second_stage<NT>(a, b, blockIdx.x, nblk, part, tot, reinterpret_cast<double*>(dsm), ts3)) return;
     if (threadIdx.x == 0) ts4 = gtime();
     if (w == 0) {
         if (a.solve_f32) solve_system<OpsF32>(tot, a.scal + b, a.dbg + b, a.transposed, M);
@@ -2155,6 +2196,155 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
         const float corr = dotf / (float)(sqrt(red[1]) * sqrt(red[2]));
         sc->corr = corr;
         if (a.dl.host) deliver_result(a.dl, 0.0f, corr, 0);
+    }
+}
+
+// ================================================================================================
+// Single-image fused kernels (the reference's literal protocol, main.cpp:167-223: ONE resident image, synchronous calls).  A batch of one
+// 1080p image spends most of an op outside the tiles: every kernel boundary costs a launch, a prologue, a reload of tiles that were in
+// shared memory a moment ago, and a last-block election.  Here the whole op is ONE cooperative launch (all CTAs co-resident): every CTA
+// loads its <= NST tiles once and keeps them in shared memory across the phases; the phases are separated by a grid-wide hand-over — the
+// CTA that finishes the second stage (and the solve) bumps a generation word, the others spin on it.  f32 images, TMA-loadable, fp16-rounded
+// products summed by HMMA (the defaults); anything else takes the multi-kernel path.  Same arithmetic and the same fixed summation orders as
+// k_sweep / k_detect; only the number of sweep CTAs differs (so, as for any other split, non-integer f32 pixels agree to ~1e-7 relative
+// and integer-valued pixels bit for bit).
+// ================================================================================================
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// grid-wide hand-over: `winner` (block-uniform) publishes, everybody else waits for the generation to move on from gen0 (read at kernel start)
+__device__ __forceinline__ void grid_handover(unsigned* gen, unsigned gen0, bool winner)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (winner) { __threadfence(); atomicAdd(gen, 1u); }
+        else while (ld_acquire_gpu(gen) == gen0) __nanosleep(64);
+    }
+    __syncthreads();
+}
+
+// k_detect1 = k_sweep + k_detect of one image: sweep phase on the resident Z tiles (8 warps x 4 lines) + frame ring, two-level second
+// stage + solve in the last CTA, hand-over, detector phase on the same tiles, last-block correlation, direct delivery.
+template <int MASK, bool TR>
+__global__ void __launch_bounds__(NT, 2) k_detect1(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW,
+                                                   const SweepArgs sa, const DetectArgs a, unsigned* gen)
+{
+    extern __shared__ __align__(128) unsigned char dsm[];
+    __shared__ double red[(NT / 32) * NFRM];
+    __shared__ double tot[NTOT];
+    __shared__ double M[72];
+    __shared__ __align__(8) uint64_t bars[DETECT_NST];
+    constexpr int NST = DETECT_NST, STG = detect_stage(false), ZPART = SZ_I36;
+    float* const ut = reinterpret_cast<float*>(dsm + (size_t)NST * STG);  // sweep phase: ring / reduction scratch; detector phase: the u tile
+    const int L = a.L, P = a.P;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int bx = blockIdx.x, nblk = gridDim.x;
+    unsigned gen0 = 0;
+    unsigned long long tsk[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // thread 0: timeline of this CTA (kept by the CTA that finishes the op: WM_DBG_PHASES)
+    if (threadIdx.x == 0) {
+        tsk[0] = gtime();
+        gen0 = ld_acquire_gpu(gen);  // before this CTA takes part in any election: the generation cannot have moved yet
+        for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    auto stage = [&](int s) { return dsm + (size_t)s * STG; };
+    TileIter it(bx, nblk, a.tiles_p);
+    int tl_[NST], tp_[NST], nmine = 0;
+#pragma unroll
+    for (int k = 0; k < NST; k++) {
+        tl_[k] = it.tl; tp_[k] = it.tp;
+        if (it.t < a.ntiles) {
+            nmine = k + 1;
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bars[k], (TL + 4) * SW * 4 + (TL + 2) * SW * 4);
+                tma_load_3d(stage(k), &tmZ, it.tp * TP - HP, it.tl * TL - 2, 0, &bars[k]);
+                tma_load_3d(stage(k) + ZPART, &tmW, it.tp * TP - HP, it.tl * TL - 1, 0, &bars[k]);
+            }
+        }
+        it.next();
+    }
+    double* part = sa.part;
+    // ---- sweep phase ----
+    {
+        float cm[NACC];
+#pragma unroll
+        for (int v = 0; v < NACC; v++) cm[v] = 0.0f;
+        const MmaSel sel = mma_selector();
+#pragma unroll
+        for (int k = 0; k < NST; k++) {
+            if (k < nmine) {
+                const int l0 = tl_[k] * TL, p0 = tp_[k] * TP;
+                mbar_wait(&bars[k], 0);
+                if (k == 0 && threadIdx.x == 0) tsk[1] = gtime();
+                float* zt = reinterpret_cast<float*>(stage(k));
+                if (tile_on_frame<TL + 4>(l0 - 2, p0 - HP, L, P)) { fix_border<TL + 4>(zt, l0 - 2, p0 - HP, L, P); __syncthreads(); }
+                const bool full = l0 >= 1 && l0 + TL <= L - 1 && p0 >= 1 && p0 + TP <= P - 1;
+                if (full) sweep_tile_mma<true, 4, 2>(zt, l0, p0, L, P, cm, sel);
+                else sweep_tile_mma<false, 4, 2>(zt, l0, p0, L, P, cm, sel);
+            }
+        }
+        double dacc[NLAG];  // 2 tiles x 4 lines x 4 products per accumulator: far below the exactness bound of the f32 partials
+#pragma unroll
+        for (int v = 0; v < NLAG - 1; v++) dacc[v] = (double)cm[v];
+        dacc[NLAG - 1] = (double)__fadd_rn(__fadd_rn(cm[12], cm[13]), __fadd_rn(cm[14], cm[15]));
+        __syncthreads();
+        block_sum<NLAG, NT>(dacc, red);
+        if (threadIdx.x < NLAG) part[(size_t)bx * NTOT + threadIdx.x] = red[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tsk[2] = gtime();
+    sweep_ring<float, 2, NT, false>(reinterpret_cast<const float*>(sa.img), sa.ld, L, P, a.ntiles, bx, nblk, reinterpret_cast<unsigned char*>(ut), red, part);
+    if (threadIdx.x == 0) tsk[3] = gtime();
+    unsigned long long ts3 = 0;
+    const bool last = sweep_second_stage<NT>(sa, 0, bx, nblk, part, tot, reinterpret_cast<double*>(ut), ts3);
+    if (last && w == 0) {
+        if (sa.solve_f32) solve_system<OpsF32>(tot, sa.scal, sa.dbg, sa.transposed, M);
+        else solve_system<OpsF64>(tot, sa.scal, sa.dbg, sa.transposed, M);
+    }
+    grid_handover(gen, gen0, last);
+    if (threadIdx.x == 0) tsk[4] = gtime();
+    // ---- detector phase on the resident tiles ----
+    Scal* sc = a.scal;
+    if (__ldcg(&sc->status) != 0) {  // singular: corr = 0 was written by the solve
+        if (a.dl.host && bx == 0 && threadIdx.x == 0) deliver_result(a.dl, 0.0f, 0.0f, __ldcg(&sc->status));
+        return;
+    }
+    float c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = __ldcg(&sc->coef[k]);
+    double ddot = 0.0, dnz = 0.0, dnu = 0.0;
+#pragma unroll
+    for (int k = 0; k < NST; k++) {
+        if (k < nmine) {
+            const int l0 = tl_[k] * TL, p0 = tp_[k] * TP;
+            float* zt = reinterpret_cast<float*>(stage(k));
+            float* wt = reinterpret_cast<float*>(stage(k) + ZPART);
+            float fd = 0.0f, fz = 0.0f, fu = 0.0f;
+            if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true, false>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu);
+            else detect_tile<MASK, TR, false, false>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu);
+            ddot += (double)fd; dnz += (double)fz; dnu += (double)fu;
+            __syncthreads();  // ut is rewritten by the next tile
+        }
+    }
+    if (threadIdx.x == 0) tsk[5] = gtime();
+    const double v3[3] = {ddot, dnz, dnu};
+    block_sum<3>(v3, red);
+    if (threadIdx.x < 3) a.part[(size_t)bx * 3 + threadIdx.x] = red[threadIdx.x];
+    if (!last_block(a.counter, nblk)) return;
+    if (threadIdx.x == 0) tsk[6] = gtime();
+    block_column_reduce<3, 4, 3>(a.part, nblk, red, reinterpret_cast<double*>(ut));
+    if (threadIdx.x == 0) {
+        a.dbg->dot = red[0]; a.dbg->nz = red[1]; a.dbg->nu = red[2];
+        const float dotf = (float)red[0];
+        const float corr = dotf / (float)(sqrt(red[1]) * sqrt(red[2]));
+        sc->corr = corr;
+        if (a.dl.host) deliver_result(a.dl, 0.0f, corr, 0);
+        tsk[7] = gtime();
+        for (int i = 0; i < 8; i++) a.dbg->ts[i] = tsk[i];
     }
 }
 
