@@ -619,9 +619,11 @@ def run_e2e(args, pkg, torch, dist, dev, wm, wl, d_in, a_host, c_host, first, wo
         def one_pass():
             for ci, o in enumerate(range(0, n, chunk)):
                 nb = min(chunk, n - o)
-                sl = ci % NS
                 hin = pkg.image_desc(pin_in[o].data_ptr(), rows, cols, layout, dt_code)
                 for k2, mask in enumerate((pkg.NVF, pkg.ME)):
+                    # consecutive calls go to different slots (streams): on one slot the second upload would queue behind the first
+                    # call's download and detector, and the copy engines (FIFO in submission order) would alternate instead of overlapping
+                    sl = (2 * ci + k2) % NS
                     hout = pkg.image_desc(pin_out[k2][o].data_ptr(), rows, cols, layout, dt_code)
                     # embed, download the watermarked images, detect on them where they lie on the device (main.cpp:178-217)
                     wm.embed_verify_host_batch(sl, hin, hin, hout, npx, npx, npx, nb, mask, a_e[k2][o:o + nb], c_e[k2][o:o + nb])

@@ -90,7 +90,7 @@ def main():
             traffic.setdefault(kn, []).append(b / frames)
             instr.setdefault(kn, []).append(fnum(r[ix["smsp__inst_executed.sum"]]) / frames)
     # instr/px needs the pixel count: filled by the caller's knowledge of the workload
-    px = {"image1080p": 1080 * 1920, "video4k": 2160 * 3840, "image4k": 2160 * 3840, "image512": 512 * 512}.get(wl)
+    px = {"image1080p": 1080 * 1920, "single1080p": 1080 * 1920, "video4k": 2160 * 3840, "image4k": 2160 * 3840, "image512": 512 * 512}.get(wl)
     if px:
         out = []
         for ln in lines:

@@ -1088,6 +1088,12 @@ static cudaError_t copy_planes(void* dev, void* host, const HostGeo& g, bool to_
     for (int c = 0; c < g.ch; c++) {
         char* d = (char*)dev + (size_t)c * (size_t)(g.L * g.P) * g.es;
         char* h = (char*)host + (size_t)c * (size_t)g.ps * g.es;
+        if (g.ld == g.P) {  // dense rows: one linear copy (a 2-D copy is programmed row by row)
+            const size_t n = (size_t)(g.L * g.P) * g.es;
+            const cudaError_t e1 = to_device ? cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st) : cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st);
+            if (e1 != cudaSuccess) return e1;
+            continue;
+        }
         const cudaError_t e = to_device ? cudaMemcpy2DAsync(d, (size_t)g.P * g.es, h, (size_t)g.ld * g.es, (size_t)g.P * g.es, (size_t)g.L, cudaMemcpyHostToDevice, st)
                                         : cudaMemcpy2DAsync(h, (size_t)g.ld * g.es, d, (size_t)g.P * g.es, (size_t)g.P * g.es, (size_t)g.L, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return e;
@@ -1105,6 +1111,10 @@ static wm_image dense_desc(const wm_image* im, void* dev)
 static cudaError_t copy_batch(void* dev, void* host, const HostGeo& g, int64_t host_stride, int batch, bool to_device, cudaStream_t st)
 {
     const int64_t hs = host_stride > 0 ? host_stride : g.ps * g.ch;
+    if (g.ld == g.P && g.ps == g.L * g.P && hs == g.ps * g.ch) {  // the whole batch is dense on the host too: one copy
+        const size_t n = dense_bytes(g) * (size_t)batch;
+        return to_device ? cudaMemcpyAsync(dev, host, n, cudaMemcpyHostToDevice, st) : cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, st);
+    }
     for (int b = 0; b < batch; b++) {
         const cudaError_t e = copy_planes((char*)dev + (size_t)b * dense_bytes(g), (char*)host + (size_t)b * (size_t)hs * g.es, g, to_device, st);
         if (e != cudaSuccess) return e;
