@@ -687,6 +687,7 @@ def check_sharding(pkg, torch, dist, dev, wm, vctx, base_t, dtype, kind, layout,
             f_r, _ = pkg.shard_frames(total, r, world)
             fr = device_frames(torch, dev, base_t, f_r, 2, dtype)
             out = torch.empty_like(fr)
+            torch.cuda.synchronize(dev)  # the frames are generated on torch's stream, the library runs on its own (non-blocking) streams
             a2, c2 = np.zeros(2, np.float32), np.zeros(2, np.float32)
             if vctx is not None:
                 pkg.process_frames(vctx, pkg.VIDEO_EMBED, fr.data_ptr(), out.data_ptr(), f_r, 2, a2)

@@ -1403,9 +1403,11 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
         } else {
             if (fbytes * nb > (int64_t)s.stage_in_cap && !s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
             if ((rc = ensure_stage(ctx, &s.stage_in, &s.stage_in_cap, (size_t)(fbytes * B)))) return rc;
-            for (int j = 0; j < nb; j++)  // H2D, dropping the row padding on the fly (main.cpp:348-353)
-                CU(cudaMemcpy2DAsync((uint8_t*)s.stage_in + j * fbytes, Wd, frames + (i + j * K) * fstride, linesize, Wd, H,
-                                     cudaMemcpyHostToDevice, s.stream));
+            for (int j = 0; j < nb; j++) {  // H2D, dropping the row padding on the fly (main.cpp:348-353); unpadded frames go as one linear copy
+                if (linesize == Wd) CU(cudaMemcpyAsync((uint8_t*)s.stage_in + j * fbytes, frames + (i + j * K) * fstride, (size_t)fbytes, cudaMemcpyHostToDevice, s.stream));
+                else CU(cudaMemcpy2DAsync((uint8_t*)s.stage_in + j * fbytes, Wd, frames + (i + j * K) * fstride, linesize, Wd, H,
+                                          cudaMemcpyHostToDevice, s.stream));
+            }
             fin.data = s.stage_in; fin.ld = Wd;
             in_stride = fbytes;
         }
