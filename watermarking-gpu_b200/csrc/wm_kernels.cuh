@@ -841,7 +841,7 @@ static __device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* s
     // pivot itself (no shuffle reduction), the pivot row and row k are exchanged through shared memory, and every lane computes its row's
     // multiplier — one division per step on the critical path instead of a division plus 3 x 3 double-word shuffles plus nine dependent
     // multiply-subtracts per lane (the old lane = row layout: 6.4 us of every sweep's tail).  Same operations on the same operands in the
-    // oracle's order, so the result is bit-equal to the plain C LU (oracle/wm_oracle.c: wmo_solve8).
+    // order of a plain C LU with partial pivoting, so the result is bit-equal to it (the parity tests compare exactly that).
     const int ri = lane >> 2, cg = lane & 3;
     T e0 = (T)M[ri * 9 + cg], e1 = (T)M[ri * 9 + cg + 4], e2 = (T)M[ri * 9 + 8];
     double amax = fmax(fabs(M[ri * 9 + cg]), fabs(M[ri * 9 + cg + 4]));
@@ -857,7 +857,7 @@ static __device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* s
     for (int k = 0; k < 8; k++) {
         if (cg == (k & 3)) colbuf[ri] = k < 4 ? e0 : e1;
         __syncwarp();
-        // first maximal |A[i][k]|, i >= k (ascending i, strict >: the oracle's pivot)
+        // first maximal |A[i][k]|, i >= k (ascending i, strict >: the pivot a plain C loop picks)
         int piv = k;
         T pv = colbuf[k], pa = (T)fabs(pv);
 #pragma unroll
@@ -875,7 +875,7 @@ static __device__ void solve_system(const double* tot /* smem [NTOT] */, Scal* s
         const T p0 = pivrow[cg], p1 = pivrow[cg + 4], p2 = pivrow[8];
         if (ri == k) { e0 = p0; e1 = p1; e2 = p2; }
         else if (ri == piv) { e0 = krow[cg]; e1 = krow[cg + 4]; e2 = krow[8]; }
-        if (ri > k) {  // columns <= k of the rows below are never read again (the oracle stores a value there that nothing uses)
+        if (ri > k) {  // columns <= k of the rows below are never read again (a plain C LU stores a value there that nothing uses)
             if (cg > k) e0 = Ops::mulsub(e0, f, p0);
             if (cg + 4 > k) e1 = Ops::mulsub(e1, f, p1);
             e2 = Ops::mulsub(e2, f, p2);
