@@ -517,9 +517,9 @@ __device__ __forceinline__ void block_sum_f32(const float (&v)[NV], double* red)
 __device__ __forceinline__ bool last_block(unsigned* counter, unsigned nblocks)
 {
     __shared__ int s_last;
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();  // cumulative: orders the partials every thread of this CTA wrote before the barrier ahead of the count
         const unsigned prev = atomicInc(counter, nblocks - 1);
         s_last = (prev == nblocks - 1);
     }
