@@ -244,3 +244,22 @@ def test_common_random_matrix_reproduces_committed_file(wmb, tmp_path):
     assert subprocess.run([exe, "64"], capture_output=True).returncode != 0
     # the file loads through the library's own size check (Watermark.cpp:70-71) when a GPU is present
     assert abs(float(a.mean())) < 0.01 and abs(float(a.std()) - 1.0) < 0.01
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference: the reference's path on the host cores (the CPU restatement; no GPU, no product code), one JSON line
+    with the keys the driver compares against the GPU arm's."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["config"]["workload"] == "video4k" and d["config"]["rows"] == 2160 and d["config"]["cols"] == 3840
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
