@@ -78,6 +78,9 @@ enum {
                                  whose tiles fit the resident CTAs' shared memory (e.g. 1080p) runs as ONE cooperative kernel (k_detect1) that keeps its tiles in
                                  shared memory across sweep -> solve -> detector.  Same results; measured 3 us SLOWER per op at 1080p (profiles/r2_latency.md:
                                  the grid-wide hand-over costs more than the second launch it saves), kept as an experiment */
+    WM_OPT_PADDED_UPLOAD = 13, /* 1 (default): wm_process_frames uploads a HOST frame whose row padding is small (<= width / 8) and whose linesize is a multiple
+                                 of 16 together with its padding, as one linear copy, and reads it in place with ld = linesize; 0: the padding is always dropped on
+                                 the way up by a 2-D copy (the reference's row-by-row repack, main.cpp:348-353) */
     WM_OPT_HOST_RUN_FRAMES = 9, /* frames per run (one batched launch sequence + its copies) of wm_process_frames when frames are in HOST memory; default 4 */
     WM_OPT_F32_SOLVE = 8      /* 0 (default): the 8x8 system is summed and solved in f64 (pivot cut 1e-12 max|Rx|); 1: Rx / rx are rounded to f32
                                  and solved by an f32 LU (pivot cut 1e-6 max|Rx|) like af::solve on the reference's f32 arrays

@@ -497,3 +497,42 @@ def test_fused_single_image_ops_equal_multi_kernel_path(wmb, oracle, rows, cols,
         assert abs(c1 - o["corr"]) <= 1e-3 * abs(o["corr"])
         report("fused single-image ops %dx%d layout=%d mask=%d: corr %.7f (multi-kernel %.7f, oracle %.7f), launches embed %d detect %d" % (
             rows, cols, layout, mask, c1, c0, o["corr"], ne1, nd1))
+
+
+# ---------------------------------------------------------------------------------------------------
+# host video frames: uploaded with their row padding (one linear copy, read in place) == repacked on the way up (2-D copy)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("interval", [1, 2])
+@pytest.mark.parametrize("ls_extra,frame_extra", [(64, 0), (64, 4096), (16, 0), (0, 0), (48 + 640, 0)])
+def test_host_frames_padded_upload_equals_repack(wmb, oracle, interval, ls_extra, frame_extra):
+    """main.cpp:348-353 repacks every decoded frame row by row to drop ffmpeg's padding.  wm_process_frames either drops it with a 2-D copy
+    (WM_OPT_PADDED_UPLOAD = 0) or — small paddings, 16-byte aligned rows — uploads the frame with it and reads it in place.  Same frames, same
+    scalars, bit for bit; frame strides with trailing chroma planes (frame_extra) and a padding too large to keep (last case) included."""
+    rows, cols, n, first = 136, 640, 7, 5
+    ls = cols + ls_extra
+    fstride = rows * ls + frame_extra
+    W = util.normal_w(rows, cols)
+    buf = np.full(n * fstride, 201, np.uint8)  # padding and chroma bytes hold junk that must never be read as pixels
+    for i in range(n):
+        fr = buf[i * fstride:i * fstride + rows * ls].reshape(rows, ls)
+        fr[:, :cols] = util.natural_image(rows, cols, seed=900 + i, integer=True)
+    res = []
+    for padded in (0, 1):
+        wm = _mk(wmb, rows, cols, W)
+        wm.set_option(wmb.OPT_PADDED_UPLOAD, padded)
+        out = np.zeros((n, rows, cols), np.uint8)
+        sc = np.zeros(2 * n, np.float32)
+        ctx = wmb.VideoProcessingContext(wm, rows, cols, interval, linesize=ls, frame_stride=fstride, frames_on_device=False)
+        wmb.process_frames(ctx, wmb.VIDEO_EMBED_VERIFY, buf.ctypes.data, out.ctypes.data, first, n, sc)
+        res.append((out, sc))
+        wm.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1], equal_nan=True)
+    out, sc = res[1]
+    for i in range(n):
+        src = buf[i * fstride:i * fstride + rows * ls].reshape(rows, ls)[:, :cols]
+        if (first + i) % interval:
+            assert np.array_equal(out[i], src) and np.isnan(sc[i]) and np.isnan(sc[n + i])
+            continue
+        st, o, a = oracle.embed_frame_u8(src, W, 40.0, oracle.ME)
+        assert st == 0 and abs(sc[i] - a) <= 1e-3 * a
+        assert int(np.abs(out[i].astype(np.int32) - o.astype(np.int32)).max()) <= 1

@@ -78,6 +78,7 @@ struct wm_ctx {
     Slot slots[NSLOTS];
     int opt_fp16 = 1, opt_timing = 0, opt_tma = 1, opt_serial = 0, opt_mma = 1, opt_f32_solve = 0;
     int opt_pdl = 1;         // WM_OPT_PDL: 2nd / 3rd kernel of an op launched with programmatic stream serialization
+    int opt_padded_upload = 1;  // WM_OPT_PADDED_UPLOAD: host video frames with a small row padding are uploaded with it (one linear copy per frame)
     int opt_fused = 0;       // WM_OPT_FUSED_SINGLE: synchronous single-image detect as one cooperative kernel where the image fits (measured slower: off)
     int fused_failures = 0;  // cooperative launches that were refused (the op then takes the multi-kernel path)
     int opt_tma_store = 1;   // WM_OPT_TMA_STORE: apply kernel output through TMA stores where the shape allows (+8..10 % on the apply kernel)
@@ -948,7 +949,7 @@ int wm_clone(const wm_ctx* src, wm_ctx** out)
     ctx->p = src->p; ctx->psnr = src->psnr; ctx->strength = src->strength;
     ctx->w = src->w;
     ctx->opt_fp16 = src->opt_fp16; ctx->opt_mma = src->opt_mma; ctx->opt_split_cost = src->opt_split_cost; ctx->opt_timing = src->opt_timing; ctx->opt_tma = src->opt_tma;
-    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run; ctx->opt_tma_store = src->opt_tma_store; ctx->opt_pdl = src->opt_pdl; ctx->opt_fused = src->opt_fused;
+    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run; ctx->opt_tma_store = src->opt_tma_store; ctx->opt_pdl = src->opt_pdl; ctx->opt_fused = src->opt_fused; ctx->opt_padded_upload = src->opt_padded_upload;
     const int rc = init_slots(ctx, nullptr);
     if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
     *out = ctx;
@@ -1000,6 +1001,7 @@ int wm_set_option(wm_ctx* ctx, int option, int value)
     case WM_OPT_TMA_STORE: ctx->opt_tma_store = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_PDL: ctx->opt_pdl = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_FUSED_SINGLE: ctx->opt_fused = value != 0; clear_graphs(ctx); return WM_OK;
+    case WM_OPT_PADDED_UPLOAD: ctx->opt_padded_upload = value != 0; return WM_OK;
     case WM_OPT_F32_SOLVE: ctx->opt_f32_solve = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_SPLIT_COST: ctx->opt_split_cost = value < 0 ? 1 << 28 : value; return WM_OK;
     default: return fail(ctx, WM_ERR_ARG, "unknown option");
@@ -1401,15 +1403,23 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
             fin.data = (void*)(frames + i * fstride); fin.ld = linesize;  // strided reads: no repack pass needed
             in_stride = K * fstride;
         } else {
-            if (fbytes * nb > (int64_t)s.stage_in_cap && !s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
-            if ((rc = ensure_stage(ctx, &s.stage_in, &s.stage_in_cap, (size_t)(fbytes * B)))) return rc;
-            for (int j = 0; j < nb; j++) {  // H2D, dropping the row padding on the fly (main.cpp:348-353); unpadded frames go as one linear copy
-                if (linesize == Wd) CU(cudaMemcpyAsync((uint8_t*)s.stage_in + j * fbytes, frames + (i + j * K) * fstride, (size_t)fbytes, cudaMemcpyHostToDevice, s.stream));
-                else CU(cudaMemcpy2DAsync((uint8_t*)s.stage_in + j * fbytes, Wd, frames + (i + j * K) * fstride, linesize, Wd, H,
-                                          cudaMemcpyHostToDevice, s.stream));
+            // H2D.  The reference repacks a decoded frame row by row to drop ffmpeg's row padding (main.cpp:348-353).  Here a frame whose
+            // padding is small and whose linesize keeps the rows 16-byte aligned goes up WITH its padding as one linear copy (a 2-D copy is
+            // programmed row by row) and the kernels read it in place with ld = linesize, as they do for frames that are already on the
+            // device; other paddings are dropped by a 2-D copy.
+            const bool keep_pad = ctx->opt_padded_upload && linesize != Wd && linesize % 16 == 0 && (linesize - Wd) * 8 <= Wd;
+            const int64_t sbytes = keep_pad ? H * linesize : fbytes;  // bytes of one staged frame
+            if (sbytes * nb > (int64_t)s.stage_in_cap && !s.queue.empty()) { const int r = finish_slot(ctx, s); if (r < 0) return r; }
+            if ((rc = ensure_stage(ctx, &s.stage_in, &s.stage_in_cap, (size_t)(sbytes * B)))) return rc;
+            if ((linesize == Wd || keep_pad) && K * fstride == sbytes)  // the frames of the run are contiguous on the host too: one copy
+                CU(cudaMemcpyAsync(s.stage_in, frames + i * fstride, (size_t)(sbytes * nb), cudaMemcpyHostToDevice, s.stream));
+            else for (int j = 0; j < nb; j++) {
+                const uint8_t* src = frames + (i + j * K) * fstride;
+                if (linesize == Wd || keep_pad) CU(cudaMemcpyAsync((uint8_t*)s.stage_in + j * sbytes, src, (size_t)sbytes, cudaMemcpyHostToDevice, s.stream));
+                else CU(cudaMemcpy2DAsync((uint8_t*)s.stage_in + j * sbytes, Wd, src, linesize, Wd, H, cudaMemcpyHostToDevice, s.stream));
             }
-            fin.data = s.stage_in; fin.ld = Wd;
-            in_stride = fbytes;
+            fin.data = s.stage_in; fin.ld = keep_pad ? linesize : Wd;
+            in_stride = sbytes;
         }
         if (embed_mode) {
             wm_image fout = fin;
@@ -1425,10 +1435,12 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
             if (rc) return rc;
             s.queue.back().scalar = scalars ? scalars + i : nullptr;
             s.queue.back().sstride = K;
-            if (!v->frames_on_device)
-                for (int j = 0; j < nb; j++)
+            if (!v->frames_on_device) {
+                if (K == 1) CU(cudaMemcpyAsync(out + i * ostride, s.stage_out, (size_t)(fbytes * nb), cudaMemcpyDeviceToHost, s.stream));
+                else for (int j = 0; j < nb; j++)
                     CU(cudaMemcpyAsync(out + (i + j * K) * ostride, (uint8_t*)s.stage_out + j * fbytes, (size_t)fbytes,
                                        cudaMemcpyDeviceToHost, s.stream));
+            }
             if (mode == WM_VIDEO_EMBED_VERIFY) {  // detect on the frame just written, where it lies on the device
                 rc = do_detect(ctx, si, &fout, out_stride, nb, WM_MASK_ME);
                 if (rc) return rc;
