@@ -536,3 +536,40 @@ def test_host_frames_padded_upload_equals_repack(wmb, oracle, interval, ls_extra
         st, o, a = oracle.embed_frame_u8(src, W, 40.0, oracle.ME)
         assert st == 0 and abs(sc[i] - a) <= 1e-3 * a
         assert int(np.abs(out[i].astype(np.int32) - o.astype(np.int32)).max()) <= 1
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_singular_and_zero_mask_through_the_replayed_sync_path(wmb, oracle, fused):
+    """The error behaviour of Watermark.cpp:164-165,246-247 on the path the reference's loops_for_test protocol takes: repeated synchronous
+    calls (captured / replayed graph, result delivered by the op's last CTA into mapped pinned memory), then a solvable image on the same
+    context, then the constant one again — no stale scalar may leak from one op into the next."""
+    rows, cols = 96, 160
+    const = np.full((rows, cols), 100.0, np.float32)
+    nat = util.natural_image(rows, cols, seed=21)
+    W = util.normal_w(rows, cols)
+    wm = _mk(wmb, rows, cols, W)
+    wm.set_option(wmb.OPT_FUSED_SINGLE, fused)
+    dc = wmb.DeviceArray.from_numpy(wm, const, wmb.COL_MAJOR)
+    dn = wmb.DeviceArray.from_numpy(wm, nat, wmb.COL_MAJOR)
+    out = wmb.DeviceArray(wm, rows, cols, wmb.COL_MAJOR, wmb.F32)
+    on = oracle.embed(nat, W, 40.0, wmb.ME)
+    for rep in range(2):
+        for _ in range(4):
+            _, a, st = wm.makeWatermark(dc, dc, wmb.ME, out=out)
+            assert st == wmb.SINGULAR and np.isnan(a) and np.array_equal(out.numpy(), const)
+        for _ in range(4):
+            _, a, st = wm.makeWatermark(dc, dc, wmb.NVF, out=out)
+            assert st == wmb.ZERO_MASK and np.isinf(a) and np.array_equal(out.numpy(), const)
+        for mask in (wmb.ME, wmb.NVF):
+            for _ in range(4):
+                corr, st = wm.detectWatermark(dc, mask)
+                assert st == wmb.SINGULAR and corr == 0.0
+        for _ in range(4):
+            _, a, st = wm.makeWatermark(dn, dn, wmb.ME, out=out)
+            assert st == 0 and abs(a - on["a"]) <= 1e-3 * on["a"]
+        z = out.numpy().copy()
+        od = oracle.detect(z, W, wmb.ME)
+        for _ in range(4):
+            corr, st = wm.detectWatermark(out, wmb.ME)
+            assert st == 0 and abs(corr - od["corr"]) <= 1e-3 * abs(od["corr"])
+    wm.close()
