@@ -250,6 +250,7 @@ def main():
     ap.add_argument("--split-cost", type=int, default=None, help="WM_OPT_SPLIT_COST (A/B: -1 = never partition an unbalanced batch)")
     ap.add_argument("--fhadd", action="store_true", help="sum the rounded Rx/rx products with the FHADD chain instead of HMMA (A/B)")
     ap.add_argument("--no-tma-store", action="store_true", help="WM_OPT_TMA_STORE = 0: apply kernel output through per-thread vector stores (A/B)")
+    ap.add_argument("--no-narrow", action="store_true", help="WM_OPT_NARROW_U8 = 0: u8 stats / apply on 256-thread CTAs (A/B)")
     ap.add_argument("--host-run", type=int, default=0, help="WM_OPT_HOST_RUN_FRAMES for the e2e video path (A/B)")
     ap.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e pass (0 = 128 for video, 96 for images)")
     args = ap.parse_args()
@@ -357,6 +358,8 @@ def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, secondary=
         wm.set_option(pkg.OPT_HOST_RUN_FRAMES, args.host_run)
     if args.no_tma_store:
         wm.set_option(pkg.OPT_TMA_STORE, 0)
+    if args.no_narrow:
+        wm.set_option(pkg.OPT_NARROW_U8, 0)
     dt_code = pkg.U8 if dtype == "u8" else pkg.F32
     esz = 1 if dtype == "u8" else 4
     # image workloads: ArrayFire layout (column-major); video: row-major Y planes

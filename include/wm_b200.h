@@ -81,6 +81,8 @@ enum {
     WM_OPT_PADDED_UPLOAD = 13, /* 1 (default): wm_process_frames uploads a HOST frame whose row padding is small (<= width / 8) and whose linesize is a multiple
                                  of 16 together with its padding, as one linear copy, and reads it in place with ld = linesize; 0: the padding is always dropped on
                                  the way up by a 2-D copy (the reference's row-by-row repack, main.cpp:348-353) */
+    WM_OPT_NARROW_U8 = 14,    /* 1 (default): the stats / apply kernels of u8 frames (TMA path) run on 128-thread CTAs, 4 warps x 8 lines of a tile, four CTAs per SM,
+                                 like the sweep; 0: 256-thread CTAs, 8 warps x 4 lines, three per SM.  Same bits */
     WM_OPT_HOST_RUN_FRAMES = 9, /* frames per run (one batched launch sequence + its copies) of wm_process_frames when frames are in HOST memory; default 4 */
     WM_OPT_F32_SOLVE = 8      /* 0 (default): the 8x8 system is summed and solved in f64 (pivot cut 1e-12 max|Rx|); 1: Rx / rx are rounded to f32
                                  and solved by an f32 LU (pivot cut 1e-6 max|Rx|) like af::solve on the reference's f32 arrays

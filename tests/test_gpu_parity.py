@@ -540,10 +540,13 @@ def test_mma_and_fhadd_accumulation_agree(wmb, oracle, rows, cols):
 
 @pytest.mark.parametrize("rows,cols,ls", [(64, 64, 64), (96, 160, 192), (270, 480, 480), (130, 264, 272)])
 def test_u8_tma_and_plain_paths_agree(wmb, oracle, rows, cols, ls):
-    """u8 frames resident on the device: TMA byte tiles + conversion pass vs the register-prefetched plain loader."""
+    """u8 frames resident on the device: TMA byte tiles + conversion pass vs the register-prefetched plain loader, on the same CTA shape
+    (WM_OPT_NARROW_U8 = 0: the 128-thread stats / apply kernels of the TMA path group the f32 partial sums of a tile differently, which
+    moves `a` in its last bit — that pair is compared in test_narrow_u8_kernels_equal_wide_ones)."""
     n = 5
     W = util.normal_w(rows, cols)
     wm = _mk(wmb, rows, cols, W)
+    wm.set_option(wmb.OPT_NARROW_U8, 0)
     frames = np.zeros((n, rows, ls), np.uint8)
     for i in range(n):
         frames[i, :, :cols] = util.natural_image(rows, cols, seed=500 + i, integer=True)

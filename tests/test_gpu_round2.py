@@ -573,3 +573,46 @@ def test_singular_and_zero_mask_through_the_replayed_sync_path(wmb, oracle, fuse
             corr, st = wm.detectWatermark(out, wmb.ME)
             assert st == 0 and abs(corr - od["corr"]) <= 1e-3 * abs(od["corr"])
     wm.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# u8 frames: stats / apply on 128-thread CTAs (8 lines per thread, the default) == on 256-thread CTAs
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,cols,ls", [(64, 64, 64), (96, 160, 192), (270, 480, 480), (130, 264, 272), (1080, 1920, 1920)])
+def test_narrow_u8_kernels_equal_wide_ones(wmb, oracle, rows, cols, ls):
+    """WM_OPT_NARROW_U8: same arithmetic per pixel; a thread's f32 partial of sum (|e| W)^2 now covers 32 pixels of a tile instead of 16, so
+    the strength may move in its last bits (<= 1e-6 relative) — the watermarked bytes must still agree to 1 LSB (observed: identical) and the
+    frames must match the oracle like the wide kernels do."""
+    n = 5
+    W = util.normal_w(rows, cols)
+    frames = np.zeros((n, rows, ls), np.uint8)
+    for i in range(n):
+        frames[i, :, :cols] = util.natural_image(rows, cols, seed=700 + i, integer=True)
+        frames[i, :, cols:] = 9
+    frames[3, :, :cols] = 77  # unsolvable system: frame copied through by the apply kernel
+    res = {}
+    for narrow in (1, 0):
+        wm = _mk(wmb, rows, cols, W)
+        wm.set_option(wmb.OPT_NARROW_U8, narrow)
+        L = wmb.lib()
+        dfr = L.wm_dev_alloc(wm._h, frames.nbytes)
+        dout = L.wm_dev_alloc(wm._h, n * rows * cols)
+        L.wm_dev_upload(wm._h, dfr, frames.ctypes.data, frames.nbytes)
+        ctx = wmb.VideoProcessingContext(wm, rows, cols, 1, linesize=ls, frames_on_device=True)
+        a = np.zeros(n, np.float32)
+        wmb.process_frames(ctx, wmb.VIDEO_EMBED, dfr, dout, 0, n, a)
+        out = np.zeros((n, rows, cols), np.uint8)
+        L.wm_dev_download(wm._h, out.ctypes.data, dout, out.nbytes)
+        res[narrow] = (a, out)
+        L.wm_dev_free(wm._h, dfr)
+        L.wm_dev_free(wm._h, dout)
+        wm.close()
+    (a1, o1), (a0, o0) = res[1], res[0]
+    assert np.isnan(a1[3]) and np.isnan(a0[3]) and np.array_equal(o1[3], frames[3, :, :cols])
+    ok = ~np.isnan(a0)
+    assert np.max(np.abs(a1[ok] - a0[ok]) / a0[ok]) <= 1e-6
+    assert int(np.abs(o1.astype(np.int32) - o0.astype(np.int32)).max()) <= 1
+    st, oo, oa = oracle.embed_frame_u8(frames[2], W, 40.0, oracle.ME, width=cols)
+    assert abs(a1[2] - oa) <= 1e-3 * oa and int(np.abs(o1[2].astype(np.int32) - oo.astype(np.int32)).max()) <= 1
+    report("narrow vs wide u8 kernels %dx%d ls=%d: a rel diff %.2g, differing bytes %d" % (
+        rows, cols, ls, float(np.max(np.abs(a1[ok] - a0[ok]) / a0[ok])), int(np.count_nonzero(o1 != o0))))

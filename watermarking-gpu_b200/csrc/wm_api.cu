@@ -78,6 +78,7 @@ struct wm_ctx {
     Slot slots[NSLOTS];
     int opt_fp16 = 1, opt_timing = 0, opt_tma = 1, opt_serial = 0, opt_mma = 1, opt_f32_solve = 0;
     int opt_pdl = 1;         // WM_OPT_PDL: 2nd / 3rd kernel of an op launched with programmatic stream serialization
+    int opt_narrow_u8 = 1;      // WM_OPT_NARROW_U8: stats / apply of u8 TMA frames on 128-thread CTAs (8 lines per thread), four per SM
     int opt_padded_upload = 1;  // WM_OPT_PADDED_UPLOAD: host video frames with a small row padding are uploaded with it (one linear copy per frame)
     int opt_fused = 0;       // WM_OPT_FUSED_SINGLE: synchronous single-image detect as one cooperative kernel where the image fits (measured slower: off)
     int fused_failures = 0;  // cooperative launches that were refused (the op then takes the multi-kernel path)
@@ -311,11 +312,12 @@ int max_rows(const std::vector<SubBatch>& v)
     for (const SubBatch& sb : v) m = std::max(m, sb.base + (sb.extra > 0 ? 1 : 0));
     return m;
 }
-Plan plan(const wm_ctx* ctx, const Geo& g, int batch, int dtype)
+// narrow: stats / apply of u8 TMA frames run on 128-thread CTAs, four per SM (WM_OPT_NARROW_U8)
+Plan plan(const wm_ctx* ctx, const Geo& g, int batch, int dtype, bool narrow = false)
 {
     Plan p;
     p.detect = partition(detect_ctas_per_sm(dtype == WM_U8) * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
-    p.embed = partition(EMBED_CTAS_PER_SM * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
+    p.embed = partition((narrow ? EMBED_CTAS_PER_SM_U8 : EMBED_CTAS_PER_SM) * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
     p.sweep = partition(SWEEP_CTAS_PER_SM * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
     p.nframe = 0;  // the frame ring is shared by the sweep blocks
     p.nsweep = max_rows(p.sweep);
@@ -547,7 +549,8 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
     CU(cudaSetDevice(ctx->device));
     Slot& s = ctx->slots[slot];
     const Geo g = geo(vi.L, vi.P);
-    const Plan pl = plan(ctx, g, batch, vi.dtype);
+    const bool narrow = ctx->opt_narrow_u8 && vi.dtype == WM_U8 && tma_ok(ctx, vi, in_stride, batch);
+    const Plan pl = plan(ctx, g, batch, vi.dtype, narrow);
     if ((rc = ensure_slot(ctx, s, batch, std::max(pl.gx_stats, pl.gx_detect), pl.nsweep, pl.nframe))) return rc;
     const float* W = w_for(ctx, vi.transposed, s.stream, &rc);
     if (rc) return rc;
@@ -591,7 +594,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
         PdlScope pdl(ctx->opt_pdl && mask == WM_MASK_ME && !ctx->opt_timing && !ctx->inject_coef);  // the Rx sweep of this op precedes
         for (const SubBatch& sb : pl.embed) {
             ea.b0 = sb.b0; ea.nblk_base = sb.base; ea.nblk_extra = sb.extra;
-            launch_stats(vi.dtype, kmask, vi.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmI, tmW, ea);
+            launch_stats(vi.dtype, kmask, vi.transposed, tma, narrow, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmI, tmW, ea);
         }
     }
     CU(cudaGetLastError());
@@ -606,7 +609,7 @@ int do_embed(wm_ctx* ctx, int slot, const wm_image* in, const wm_image* base, wm
         for (const SubBatch& sb : pl.embed) {
             ea.b0 = sb.b0; ea.nblk_base = sb.base; ea.nblk_extra = sb.extra;
             const dim3 grid(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb);
-            if (ts) launch_apply_ts(vi.dtype, kmask, vi.transposed, grid, s.stream, tmI, tmW, tmO, ea);
+            if (ts) launch_apply_ts(vi.dtype, kmask, vi.transposed, narrow, grid, s.stream, tmI, tmW, tmO, ea);
             else launch_apply(vi.dtype, vo.dtype, kmask, vi.transposed, tma, grid, s.stream, tmI, tmW, ea);
         }
     }
@@ -949,7 +952,7 @@ int wm_clone(const wm_ctx* src, wm_ctx** out)
     ctx->p = src->p; ctx->psnr = src->psnr; ctx->strength = src->strength;
     ctx->w = src->w;
     ctx->opt_fp16 = src->opt_fp16; ctx->opt_mma = src->opt_mma; ctx->opt_split_cost = src->opt_split_cost; ctx->opt_timing = src->opt_timing; ctx->opt_tma = src->opt_tma;
-    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run; ctx->opt_tma_store = src->opt_tma_store; ctx->opt_pdl = src->opt_pdl; ctx->opt_fused = src->opt_fused; ctx->opt_padded_upload = src->opt_padded_upload;
+    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run; ctx->opt_tma_store = src->opt_tma_store; ctx->opt_pdl = src->opt_pdl; ctx->opt_fused = src->opt_fused; ctx->opt_padded_upload = src->opt_padded_upload; ctx->opt_narrow_u8 = src->opt_narrow_u8;
     const int rc = init_slots(ctx, nullptr);
     if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
     *out = ctx;
@@ -1002,6 +1005,7 @@ int wm_set_option(wm_ctx* ctx, int option, int value)
     case WM_OPT_PDL: ctx->opt_pdl = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_FUSED_SINGLE: ctx->opt_fused = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_PADDED_UPLOAD: ctx->opt_padded_upload = value != 0; return WM_OK;
+    case WM_OPT_NARROW_U8: ctx->opt_narrow_u8 = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_F32_SOLVE: ctx->opt_f32_solve = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_SPLIT_COST: ctx->opt_split_cost = value < 0 ? 1 << 28 : value; return WM_OK;
     default: return fail(ctx, WM_ERR_ARG, "unknown option");

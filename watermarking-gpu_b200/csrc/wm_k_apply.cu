@@ -17,8 +17,14 @@ void launch_apply_t(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtenso
     else launch_apply_s<PixT, OutT, TMA, false>(mask, tr, grid, st, tmI, tmW, a);
 }
 // A/B variant with TMA stores (gray, same base, TMA loads, 3x3 masks)
-void launch_apply_ts(int dtype, int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const CUtensorMap& tmO, const EmbedArgs& a)
+void launch_apply_ts(int dtype, int mask, bool tr, bool narrow, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const CUtensorMap& tmO, const EmbedArgs& a)
 {
+    if (narrow && dtype != WM_F32) {  // u8 frames on 128-thread CTAs (8 lines per thread, 4 CTAs per SM)
+        constexpr int SM = embed_smem(true, true, ENT_U8) + 2 * TL * TP;
+        if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH_T((k_apply_ts<uint8_t, 0, true, ENT_U8>), ENT_U8, SM, tmI, tmW, tmO, a); else WM_LAUNCH_T((k_apply_ts<uint8_t, 0, false, ENT_U8>), ENT_U8, SM, tmI, tmW, tmO, a); }
+        else { if (tr) WM_LAUNCH_T((k_apply_ts<uint8_t, 1, true, ENT_U8>), ENT_U8, SM, tmI, tmW, tmO, a); else WM_LAUNCH_T((k_apply_ts<uint8_t, 1, false, ENT_U8>), ENT_U8, SM, tmI, tmW, tmO, a); }
+        return;
+    }
 #define WM_TS(PIX, SM)                                                                                                                 \
     if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_apply_ts<PIX, 0, true>), SM, tmI, tmW, tmO, a); else WM_LAUNCH((k_apply_ts<PIX, 0, false>), SM, tmI, tmW, tmO, a); } \
     else { if (tr) WM_LAUNCH((k_apply_ts<PIX, 1, true>), SM, tmI, tmW, tmO, a); else WM_LAUNCH((k_apply_ts<PIX, 1, false>), SM, tmI, tmW, tmO, a); }

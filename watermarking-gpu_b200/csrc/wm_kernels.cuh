@@ -72,6 +72,12 @@ constexpr int SNT = 128, SLPT = TL / (SNT / 32);
 constexpr int SGRP = 16, SMAXG = 48;  // second stage of the sweep in two levels: groups of 16 partial rows, at most 48 groups (768 CTAs) per image
 constexpr int SWEEP_CTAS_PER_SM = 4;  // measured: 3 and 5 CTAs per SM are both 4-6 % slower (u8 4K: 117.7 / 112-115 / 121.9 us per run; f32 1080p: 452 / 424-431 / 453 us per 148 frames)
 constexpr int EMBED_CTAS_PER_SM = 3;  // stats / apply: 2 stages of 35 KB -> three CTAs (24 warps) per SM
+// u8 TMA frames: stats / apply on 128-thread CTAs, 4 warps x 8 lines like the sweep (the per-tile costs — tile walk, TMA issue, frame tests,
+// barriers — are paid once per 32 pixels of a thread instead of once per 16, and a thread's rolling window loads 10 lines per 8 instead of
+// 6 per 4); 2 stages of 21 KB (+ the apply kernel's two byte tiles) -> four CTAs (16 warps) per SM
+constexpr int ENT_U8 = 128, EMBED_CTAS_PER_SM_U8 = 4, EMBED_NST_U8N = 2;
+__host__ __device__ constexpr int embed_nst(bool tma, bool u8, int nth) { return tma ? (u8 ? (nth == ENT_U8 ? EMBED_NST_U8N : EMBED_NST_U8) : EMBED_NST) : 1; }
+__host__ __device__ constexpr int embed_ctas_per_sm(int nth) { return nth == ENT_U8 ? EMBED_CTAS_PER_SM_U8 : EMBED_CTAS_PER_SM; }
 // dynamic shared memory per kernel: [NST stages][work tiles]; with f32 TMA the stage IS the work tile
 __host__ __device__ constexpr int sweep_stage(bool u8) { return u8 ? U8_I34 : SZ_I34; }
 __host__ __device__ constexpr int embed_stage(bool u8) { return (u8 ? U8_I34 : SZ_I34) + SZ_WT; }
@@ -81,7 +87,7 @@ __host__ __device__ constexpr int sweep_smem(bool tma, bool u8)
 {
     return tma ? (u8 ? SWEEP_NST_U8 * sweep_stage(true) + SZ_I34 : SWEEP_NST * sweep_stage(false)) : (SZ_I34 > align128(NFRM * SNT * 4) ? SZ_I34 : align128(NFRM * SNT * 4));
 }
-constexpr int embed_smem(bool tma, bool u8) { return tma ? (u8 ? EMBED_NST_U8 : EMBED_NST) * embed_stage(u8) : SZ_I34 + SZ_WT; }
+constexpr int embed_smem(bool tma, bool u8, int nth = NT) { return tma ? embed_nst(tma, u8, nth) * embed_stage(u8) : SZ_I34 + SZ_WT; }
 constexpr int detect_smem(bool tma, bool u8)  // + u tile
 {
     return (tma ? DETECT_NST * detect_stage(u8) : SZ_I36 + SZ_I34) + SZ_I34;
@@ -1481,12 +1487,13 @@ struct EmbedArgs {
 // persistent tile loop shared by k_stats and k_apply: calls body(tile, wtile, l0, p0) once per tile
 // `ready()` runs once, after the barriers are initialised and the first tile loads are in flight: it executes griddepcontrol.wait and reads
 // what the previous kernel produced (coefficients, strength); when it returns false the CTA drains its loads and leaves.
-template <typename PixT, bool TMA, typename Ready, typename Body>
+template <typename PixT, bool TMA, int NTH = NT, typename Ready, typename Body>
 __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CUtensorMap* tmW, const EmbedArgs& a,
                                                 unsigned char* dsm, uint64_t* bars, Ready ready, Body body)
 {
     constexpr bool U8T = TMA && sizeof(PixT) == 1;
-    constexpr int NST = TMA ? (U8T ? EMBED_NST_U8 : EMBED_NST) : 1;
+    constexpr int NST = embed_nst(TMA, U8T, NTH);
+    static_assert(NTH == NT || U8T, "the 128-thread form exists for u8 TMA frames only (the plain loaders assume NT threads)");
     constexpr int STG = embed_stage(U8T), IPART = U8T ? U8_I34 : SZ_I34;
     using TileT = typename std::conditional<U8T, unsigned char, float>::type;  // u8 TMA stages are read where they landed
     const int b = blockIdx.y + a.b0, step = blocks_of_image(a.nblk_base, a.nblk_extra, blockIdx.y);
@@ -1543,7 +1550,7 @@ __device__ __forceinline__ void embed_tile_loop(const CUtensorMap* tmI, const CU
             tile = reinterpret_cast<TileT*>(stage(pos.s));
             pos.next();
             patched = tile_on_frame<TL + 2>(l0 - 1, p0 - HP, a.L, a.P);
-            if (patched) { fix_border<TL + 2>(tile, l0 - 1, p0 - HP, a.L, a.P); __syncthreads(); }
+            if (patched) { fix_border<TL + 2, NTH>(tile, l0 - 1, p0 - HP, a.L, a.P); __syncthreads(); }
         } else {
             tile = reinterpret_cast<TileT*>(dsm);
             wtile = reinterpret_cast<float*>(dsm) + SZ_I34 / 4;
@@ -1576,21 +1583,22 @@ __device__ __forceinline__ void mask_from_plane(float (&m)[4], const MaskSrc& ms
         for (int j = 0; j < 4; j++) m[j] = (r < ms.nl && j < ms.np) ? __ldg(row + j) : 0.0f;
     }
 }
-template <int MASK, bool TR, typename T, typename F>
+// LPT lines per thread: warp w takes the tile's lines LPT * w .. (4 with 8 warps, 8 with 4 warps)
+template <int MASK, bool TR, int LPT = 4, typename T, typename F>
 __device__ __forceinline__ void mask_lines(const T* __restrict__ tile, const float* __restrict__ wt, const float (&c)[8], F f,
                                            const MaskSrc ms = MaskSrc{nullptr, 0, 0, 0}, const float kb = -1024.0f)
 {
     constexpr int ST = TileGeo<T>::STRIDE;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const T* tb = tile + (4 * w) * ST;  // smem line of image line l-1 for r = 0
+    const T* tb = tile + (LPT * w) * ST;  // smem line of image line l-1 for r = 0
     const int scol = 4 * lane + HP;
     float r0[6], r1[6], r2[6];
     load_win6(r0, tb, scol, kb);
     load_win6(r1, tb + ST, scol, kb);
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
+    for (int r = 0; r < LPT; r++) {
         load_win6(r2, tb + (r + 2) * ST, scol, kb);
-        const float4 wv = *reinterpret_cast<const float4*>(wt + (4 * w + r) * TP + 4 * lane);
+        const float4 wv = *reinterpret_cast<const float4*>(wt + (LPT * w + r) * TP + 4 * lane);
         const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
         float m[4];
         if constexpr (MASK == 2) mask_from_plane(m, ms, r);
@@ -1611,10 +1619,11 @@ template <bool V> struct BoolTag { static constexpr bool value = V; };
 
 // ---- k_stats: MASK = ME: sum (|e| W)^2 and max|e| (the max cancels out of a.mask.W — SURVEY.md §0 — so no
 // separate max pass); MASK = NVF: sum (nvf W)^2.  Last block: a = strength / (||mask.W|| / sqrt(N)) (Watermark.cpp:170)
-template <typename PixT, int MASK, bool TR, bool TMA>
-__global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
+template <typename PixT, int MASK, bool TR, bool TMA, int NTH = NT>
+__global__ void __launch_bounds__(NTH, embed_ctas_per_sm(NTH)) k_stats(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
                                                  const EmbedArgs a)
 {
+    constexpr int NT = NTH, LPT = TL / (NTH / 32);  // every NT below is this kernel's own CTA size
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * 2];
     __shared__ __align__(8) uint64_t bars[EMBED_NST_U8];
@@ -1632,7 +1641,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
     __shared__ float s_kb;
     float kb = -1024.0f;
     u8_bias_init(&s_kb);
-    embed_tile_loop<PixT, TMA>(&tmI, &tmW, a, dsm, bars, [&]() {
+    embed_tile_loop<PixT, TMA, NTH>(&tmI, &tmW, a, dsm, bars, [&]() {
         if constexpr (TMA && sizeof(PixT) == 1) kb = u8_bias_get(&s_kb);  // after the loop's first __syncthreads
         pdl_wait();  // the sweep's coefficients (ME) are valid from here on
         if (MASK == 0 && sc->status != 0) { skip = true; return false; }  // singular: a untouched, apply copies base through
@@ -1644,8 +1653,8 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
         float fs = 0.0f;
         auto run = [&](auto tag) {
             constexpr bool FULL = decltype(tag)::value;
-            mask_lines<MASK, TR>(tile, wt, c, [&](int r, const float (&m)[4], const float (&wq)[4], const float (&)[6]) {
-                const bool lok = FULL || (l0 + 4 * w + r < L);
+            mask_lines<MASK, TR, LPT>(tile, wt, c, [&](int r, const float (&m)[4], const float (&wq)[4], const float (&)[6]) {
+                const bool lok = FULL || (l0 + LPT * w + r < L);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const bool ok = FULL || (lok && pb + j < P);
@@ -1654,7 +1663,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
                     const float u = __fmul_rn(mj, wq[j]);
                     fs = __fmaf_rn(u, u, fs);
                 }
-            }, MASK == 2 ? MaskSrc{a.maskp + (long long)b * a.mask_bstride + (long long)(l0 + 4 * w) * P + pb, P, L - (l0 + 4 * w), P - pb}
+            }, MASK == 2 ? MaskSrc{a.maskp + (long long)b * a.mask_bstride + (long long)(l0 + LPT * w) * P + pb, P, L - (l0 + LPT * w), P - pb}
                          : MaskSrc{nullptr, 0, 0, 0}, kb);
         };
         if (l0 + TL <= L && p0 + TP <= P) run(BoolTag<true>{}); else run(BoolTag<false>{});
@@ -1675,7 +1684,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_stats(const __grid_co
     }
     if (!last_block(a.counter + b, nblk)) return;
     __shared__ double tot2[2];
-    block_column_reduce<2, 2, 1>(a.part + (size_t)b * a.pstride * 2, nblk, tot2, reinterpret_cast<double*>(dsm));
+    block_column_reduce<2, 2, 1, NTH>(a.part + (size_t)b * a.pstride * 2, nblk, tot2, reinterpret_cast<double*>(dsm));
     if (w == 0) {
         const double S2 = tot2[0];
         const float mx = (float)tot2[1];
@@ -1699,9 +1708,10 @@ template <typename T> __device__ __forceinline__ T to_out(float v);
 template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ uint8_t to_out<uint8_t>(float v) { return (uint8_t)v; }  // truncation
 
-template <typename PixT, typename OutT>
+template <typename PixT, typename OutT, int NTH = NT>
 __device__ __forceinline__ void copy_base_through(const EmbedArgs& a)
 {
+    constexpr int NT = NTH;
     const int b = blockIdx.y + a.b0;
     const PixT* bas = reinterpret_cast<const PixT*>(a.base) + (long long)b * a.base_bstride;
     OutT* out = reinterpret_cast<OutT*>(a.out) + (long long)b * a.out_bstride;
@@ -1820,14 +1830,16 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply(const __grid_co
 // smem tile and leaves through a TMA store (cp.async.bulk.tensor smem -> global) instead of per-thread STG.  f32: the output overwrites
 // the W tile's own cells in place (each thread reads its W values, then owns those cells), so no extra smem; u8: two 4 KB byte tiles.
 // Same bits as k_apply, 8-10 % faster (profiles/r2_tma_store_ab.md): the per-line 64-bit store addressing leaves the instruction stream.
-template <typename PixT, int MASK, bool TR>
-__global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply_ts(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
+template <typename PixT, int MASK, bool TR, int NTH = NT>
+__global__ void __launch_bounds__(NTH, embed_ctas_per_sm(NTH)) k_apply_ts(const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmW,
                                                                     const __grid_constant__ CUtensorMap tmO, const EmbedArgs a)
 {
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ __align__(8) uint64_t bars[EMBED_NST_U8];
     constexpr bool U8T = sizeof(PixT) == 1;
-    constexpr int NST = U8T ? EMBED_NST_U8 : EMBED_NST;
+    constexpr int NT = NTH, LPT = TL / (NTH / 32);  // every NT below is this kernel's own CTA size
+    static_assert(NTH == wm::NT || U8T, "the 128-thread form exists for u8 frames only");
+    constexpr int NST = embed_nst(true, U8T, NTH);
     constexpr int STG = embed_stage(U8T), IPART = U8T ? U8_I34 : SZ_I34;
     using TileT = typename std::conditional<U8T, unsigned char, float>::type;
     pdl_launch_dependents();
@@ -1870,7 +1882,7 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply_ts(const __grid
     if (sc->status != 0) {  // unsolvable system / zero mask: out = base; the loads in flight must land before the CTA may leave
         for (int s = 0; s < NST - 1; s++)
             if ((int)blockIdx.x + s * step < a.ntiles) mbar_wait(&bars[s], 0);
-        copy_base_through<PixT, PixT>(a);
+        copy_base_through<PixT, PixT, NTH>(a);
         publish();
         return;
     }
@@ -1894,9 +1906,9 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply_ts(const __grid
         float* wtile = reinterpret_cast<float*>(stage(pos.s) + IPART);
         TileT* tile = reinterpret_cast<TileT*>(stage(pos.s));
         pos.next();
-        if (tile_on_frame<TL + 2>(l0 - 1, p0 - HP, L, P)) { fix_border<TL + 2>(tile, l0 - 1, p0 - HP, L, P); __syncthreads(); }
+        if (tile_on_frame<TL + 2>(l0 - 1, p0 - HP, L, P)) { fix_border<TL + 2, NTH>(tile, l0 - 1, p0 - HP, L, P); __syncthreads(); }
         unsigned char* const ot = otiles + (size_t)(k & 1) * (TL * TP);
-        mask_lines<MASK, TR>(tile, wtile, c, [&](int r, const float (&m)[4], const float (&wq)[4], const float (&r1)[6]) {
+        mask_lines<MASK, TR, LPT>(tile, wtile, c, [&](int r, const float (&m)[4], const float (&wq)[4], const float (&r1)[6]) {
             float ov[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -1906,9 +1918,9 @@ __global__ void __launch_bounds__(NT, EMBED_CTAS_PER_SM) k_apply_ts(const __grid
             if constexpr (U8T) {
                 const unsigned u0 = __float_as_uint(__fadd_rz(ov[0], 8388608.0f)), u1 = __float_as_uint(__fadd_rz(ov[1], 8388608.0f));
                 const unsigned u2 = __float_as_uint(__fadd_rz(ov[2], 8388608.0f)), u3 = __float_as_uint(__fadd_rz(ov[3], 8388608.0f));
-                *reinterpret_cast<unsigned*>(ot + (4 * w + r) * TP + 4 * lane) = __byte_perm(__byte_perm(u0, u1, 0x0040), __byte_perm(u2, u3, 0x0040), 0x5410);
+                *reinterpret_cast<unsigned*>(ot + (LPT * w + r) * TP + 4 * lane) = __byte_perm(__byte_perm(u0, u1, 0x0040), __byte_perm(u2, u3, 0x0040), 0x5410);
             } else {
-                *reinterpret_cast<float4*>(wtile + (4 * w + r) * TP + 4 * lane) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                *reinterpret_cast<float4*>(wtile + (LPT * w + r) * TP + 4 * lane) = make_float4(ov[0], ov[1], ov[2], ov[3]);
             }
         }, MaskSrc{nullptr, 0, 0, 0}, kb);
         fence_proxy_async();  // every writer: generic-proxy smem writes -> visible to the TMA store
