@@ -580,8 +580,8 @@ def test_singular_and_zero_mask_through_the_replayed_sync_path(wmb, oracle, fuse
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("rows,cols,ls", [(64, 64, 64), (96, 160, 192), (270, 480, 480), (130, 264, 272), (1080, 1920, 1920)])
 def test_narrow_u8_kernels_equal_wide_ones(wmb, oracle, rows, cols, ls):
-    """WM_OPT_NARROW_U8: same arithmetic per pixel; a thread's f32 partial of sum (|e| W)^2 now covers 32 pixels of a tile instead of 16, so
-    the strength may move in its last bits (<= 1e-6 relative) — the watermarked bytes must still agree to 1 LSB (observed: identical) and the
+    """WM_OPT_NARROW_U8 (stats, apply, detector): same arithmetic per pixel; a thread's f32 partials of a tile now cover 32 pixels instead of
+    16, so the strength and the correlation may move in their last bits (<= 1e-6 relative) — the watermarked bytes must still agree to 1 LSB (observed: identical) and the
     frames must match the oracle like the wide kernels do."""
     n = 5
     W = util.normal_w(rows, cols)
@@ -603,16 +603,26 @@ def test_narrow_u8_kernels_equal_wide_ones(wmb, oracle, rows, cols, ls):
         wmb.process_frames(ctx, wmb.VIDEO_EMBED, dfr, dout, 0, n, a)
         out = np.zeros((n, rows, cols), np.uint8)
         L.wm_dev_download(wm._h, out.ctypes.data, dout, out.nbytes)
-        res[narrow] = (a, out)
+        # the detector on the watermarked frames (identical bytes for both variants, asserted below)
+        cdet = np.zeros(n, np.float32)
+        ctx_o = wmb.VideoProcessingContext(wm, rows, cols, 1, linesize=cols, frames_on_device=True)
+        wmb.process_frames(ctx_o, wmb.VIDEO_DETECT, dout, None, 0, n, cdet)
+        res[narrow] = (a, out, cdet)
         L.wm_dev_free(wm._h, dfr)
         L.wm_dev_free(wm._h, dout)
         wm.close()
-    (a1, o1), (a0, o0) = res[1], res[0]
+    (a1, o1, c1), (a0, o0, c0) = res[1], res[0]
+    assert c1[3] == 0.0 and c0[3] == 0.0  # unsolvable frame: correlation 0 (Watermark.cpp:246-247)
+    okc = c0 != 0.0
+    assert np.max(np.abs(c1[okc] - c0[okc]) / np.abs(c0[okc])) <= 2e-6
+    st2, oc = oracle.detect_frame_u8(o1[2], W, oracle.ME)
+    assert abs(c1[2] - oc) <= 1e-3 * abs(oc)
     assert np.isnan(a1[3]) and np.isnan(a0[3]) and np.array_equal(o1[3], frames[3, :, :cols])
     ok = ~np.isnan(a0)
     assert np.max(np.abs(a1[ok] - a0[ok]) / a0[ok]) <= 1e-6
     assert int(np.abs(o1.astype(np.int32) - o0.astype(np.int32)).max()) <= 1
     st, oo, oa = oracle.embed_frame_u8(frames[2], W, 40.0, oracle.ME, width=cols)
     assert abs(a1[2] - oa) <= 1e-3 * oa and int(np.abs(o1[2].astype(np.int32) - oo.astype(np.int32)).max()) <= 1
-    report("narrow vs wide u8 kernels %dx%d ls=%d: a rel diff %.2g, differing bytes %d" % (
-        rows, cols, ls, float(np.max(np.abs(a1[ok] - a0[ok]) / a0[ok])), int(np.count_nonzero(o1 != o0))))
+    report("narrow vs wide u8 kernels %dx%d ls=%d: a rel diff %.2g, differing bytes %d, corr rel diff %.2g" % (
+        rows, cols, ls, float(np.max(np.abs(a1[ok] - a0[ok]) / a0[ok])), int(np.count_nonzero(o1 != o0)),
+        float(np.max(np.abs(c1[okc] - c0[okc]) / np.abs(c0[okc])))))

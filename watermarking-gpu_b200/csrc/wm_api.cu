@@ -316,7 +316,7 @@ int max_rows(const std::vector<SubBatch>& v)
 Plan plan(const wm_ctx* ctx, const Geo& g, int batch, int dtype, bool narrow = false)
 {
     Plan p;
-    p.detect = partition(detect_ctas_per_sm(dtype == WM_U8) * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
+    p.detect = partition((narrow ? DETECT_CTAS_PER_SM_U8N : detect_ctas_per_sm(dtype == WM_U8)) * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
     p.embed = partition((narrow ? EMBED_CTAS_PER_SM_U8 : EMBED_CTAS_PER_SM) * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
     p.sweep = partition(SWEEP_CTAS_PER_SM * ctx->sms, batch, g.ntiles, ctx->opt_split_cost);
     p.nframe = 0;  // the frame ring is shared by the sweep blocks
@@ -632,12 +632,13 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
     CU(cudaSetDevice(ctx->device));
     Slot& s = ctx->slots[slot];
     const Geo g = geo(v.L, v.P);
-    const Plan pl = plan(ctx, g, batch, v.dtype);
+    bool tma = tma_ok(ctx, v, img_stride, batch);
+    const bool narrow = ctx->opt_narrow_u8 && v.dtype == WM_U8 && tma && !dbg_u;
+    const Plan pl = plan(ctx, g, batch, v.dtype, narrow);
     if ((rc = ensure_slot(ctx, s, batch, std::max(pl.gx_stats, pl.gx_detect), pl.nsweep, pl.nframe))) return rc;
     const float* W = w_for(ctx, v.transposed, s.stream, &rc);
     if (rc) return rc;
     const bool planes = mask == WM_MASK_NVF && ctx->p != 3;
-    bool tma = tma_ok(ctx, v, img_stride, batch);
     // synchronous single image: sweep + solve + detector as ONE cooperative kernel with the tiles kept in shared memory
     const int fgrid = std::min(g.ntiles, detect_ctas_per_sm(false) * ctx->sms);
     const bool fuse = direct && batch == 1 && ctx->opt_fused && tma && v.dtype == WM_F32 && !planes && ctx->opt_fp16 && ctx->opt_mma &&
@@ -681,7 +682,7 @@ int do_detect(wm_ctx* ctx, int slot, const wm_image* img, int64_t img_stride, in
         PdlScope pdl(ctx->opt_pdl && !ctx->opt_timing && !planes && !ctx->inject_coef);  // the Rx sweep of this op precedes
         for (const SubBatch& sb : pl.detect) {
             da.b0 = sb.b0; da.nblk_base = sb.base; da.nblk_extra = sb.extra;
-            launch_detect(v.dtype, planes ? 2 : mask, v.transposed, tma, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmZ, tmW, da);
+            launch_detect(v.dtype, planes ? 2 : mask, v.transposed, tma, narrow, dim3(sb.base + (sb.extra > 0 ? 1 : 0), sb.nb), s.stream, tmZ, tmW, da);
         }
     }
     CU(cudaGetLastError());

@@ -17,8 +17,17 @@ static void launch_detect_dbg(int mask, bool tr, dim3 grid, cudaStream_t st, con
     if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH((k_detect<float, 0, true, TMA, true>), detect_smem(TMA, false), tmZ, tmW, a); else WM_LAUNCH((k_detect<float, 0, false, TMA, true>), detect_smem(TMA, false), tmZ, tmW, a); }
     else { if (tr) WM_LAUNCH((k_detect<float, 1, true, TMA, true>), detect_smem(TMA, false), tmZ, tmW, a); else WM_LAUNCH((k_detect<float, 1, false, TMA, true>), detect_smem(TMA, false), tmZ, tmW, a); }
 }
-void launch_detect(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
+// u8 TMA frames on 128-thread CTAs (8 lines per thread, u in place over the W tile, 4 CTAs per SM)
+static void launch_detect_u8n(int mask, bool tr, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
 {
+    constexpr int SM = detect_smem_u8n();
+    if (mask == 2) { if (tr) WM_LAUNCH_T((k_detect<uint8_t, 2, true, true, false, ENT_U8>), ENT_U8, SM, tmZ, tmW, a); else WM_LAUNCH_T((k_detect<uint8_t, 2, false, true, false, ENT_U8>), ENT_U8, SM, tmZ, tmW, a); }
+    else if (mask == WM_MASK_ME) { if (tr) WM_LAUNCH_T((k_detect<uint8_t, 0, true, true, false, ENT_U8>), ENT_U8, SM, tmZ, tmW, a); else WM_LAUNCH_T((k_detect<uint8_t, 0, false, true, false, ENT_U8>), ENT_U8, SM, tmZ, tmW, a); }
+    else { if (tr) WM_LAUNCH_T((k_detect<uint8_t, 1, true, true, false, ENT_U8>), ENT_U8, SM, tmZ, tmW, a); else WM_LAUNCH_T((k_detect<uint8_t, 1, false, true, false, ENT_U8>), ENT_U8, SM, tmZ, tmW, a); }
+}
+void launch_detect(int dtype, int mask, bool tr, bool tma, bool narrow, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a)
+{
+    if (narrow && tma && dtype != WM_F32 && !a.dbg_u) { launch_detect_u8n(mask, tr, grid, st, tmZ, tmW, a); return; }
     if (a.dbg_u) { if (tma) launch_detect_dbg<true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_dbg<false>(mask, tr, grid, st, tmZ, tmW, a); return; }
     if (dtype == WM_F32) { if (tma) launch_detect_t<float, true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_t<float, false>(mask, tr, grid, st, tmZ, tmW, a); }
     else { if (tma) launch_detect_t<uint8_t, true>(mask, tr, grid, st, tmZ, tmW, a); else launch_detect_t<uint8_t, false>(mask, tr, grid, st, tmZ, tmW, a); }

@@ -1962,10 +1962,16 @@ struct DetectArgs {
 };
 // CTAs per SM of the detector (2 x 38 KB of f32 stages + the u tile allow two; three for u8 frames fit but were measured slower)
 __host__ __device__ constexpr int detect_ctas_per_sm(bool) { return 2; }
+// u8 TMA frames (WM_OPT_NARROW_U8): 128-thread CTAs, 4 warps x 8 lines, u = mask.W written IN PLACE over the W tile (no separate u tile):
+// 2 stages of 24 KB -> four CTAs (16 warps, as before) per SM
+constexpr int DETECT_CTAS_PER_SM_U8N = 4;
+__host__ __device__ constexpr int detect_smem_u8n() { return DETECT_NST * detect_stage(true); }
 
 // one tile of the detector; FULL = the tile lies completely inside the image (its 1-pixel ring may not)
-template <int MASK, bool TR, bool FULL, bool DBG, typename ZT>
-__device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* __restrict__ wt, float* __restrict__ ut,
+// NTH threads: warp w takes the tile's lines LPT * w .. (LPT = 4 with 8 warps, 8 with 4 warps).  ut may be the W tile itself (wt): every cell
+// of u = mask.W is written by the one thread that read that cell of W (the narrow u8 kernel has no separate u tile).
+template <int MASK, bool TR, bool FULL, bool DBG, typename ZT, int NTH = NT>
+__device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* wt, float* ut,
                                             const float (&c)[8], int l0, int p0,
                                             int L, int P, float& fd, float& fz, float& fu, const float* __restrict__ mplane = nullptr,
                                             float* __restrict__ dbg_u = nullptr, float* __restrict__ dbg_eu = nullptr, const float kb = -1024.0f)
@@ -1976,18 +1982,19 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* __
     const int pb = p0 + 4 * lane;
     const int scol = 4 * lane + HP;
     constexpr int ZS = TileGeo<ZT>::STRIDE, ZO = TileGeo<ZT>::OFF;
-    float ez[4][4];
+    constexpr int LPT = TL / (NTH / 32);
+    float ez[LPT][4];
     // ---- phase 1a: my 4 x 4 pixels.  (Parking e_z in the W tile's dead cells instead of 16 registers, with three CTAs per SM for
     // u8 frames, was measured 3-6 % SLOWER: the detector is short of issue slots, not of registers.) ----
     {
-        const ZT* zb = zt + (4 * w + 1) * ZS;  // smem line of image line l-1 for r = 0
+        const ZT* zb = zt + (LPT * w + 1) * ZS;  // smem line of image line l-1 for r = 0
         float r0[6], r1[6], r2[6];
         load_win6(r0, zb, scol, kb);
         load_win6(r1, zb + ZS, scol, kb);
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < LPT; r++) {
             load_win6(r2, zb + (r + 2) * ZS, scol, kb);
-            const float4 wv = *reinterpret_cast<const float4*>(wt + (4 * w + r + 1) * SW + scol);
+            const float4 wv = *reinterpret_cast<const float4*>(wt + (LPT * w + r + 1) * SW + scol);
             const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
             float uu[4];
 #pragma unroll
@@ -1997,12 +2004,12 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* __
                 float m;
                 if constexpr (MASK == 0) m = fabsf(e);
                 else if constexpr (MASK == 1) m = nvf_mask<TR>(r0, r1, r2, j);
-                else m = plane_at(l0 + 4 * w + r, pb + j);
+                else m = plane_at(l0 + LPT * w + r, pb + j);
                 uu[j] = __fmul_rn(m, wq[j]);
             }
-            *reinterpret_cast<float4*>(ut + (4 * w + r + 1) * SW + scol) = make_float4(uu[0], uu[1], uu[2], uu[3]);
+            *reinterpret_cast<float4*>(ut + (LPT * w + r + 1) * SW + scol) = make_float4(uu[0], uu[1], uu[2], uu[3]);
             if constexpr (DBG) {
-                const int l = l0 + 4 * w + r;
+                const int l = l0 + LPT * w + r;
 #pragma unroll
                 for (int j = 0; j < 4; j++) if (l < L && pb + j < P) dbg_u[(long long)l * P + pb + j] = uu[j];
             }
@@ -2035,8 +2042,7 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* __
             }
             *reinterpret_cast<float4*>(ut + (rl + 1) * SW + scol) = make_float4(uu[0], uu[1], uu[2], uu[3]);
         }
-    } else if ((int)threadIdx.x < 64 + 2 * (TL + 2)) {
-        const int idx = threadIdx.x - 64;
+    } else for (int idx = threadIdx.x - 64; idx < 2 * (TL + 2); idx += NTH - 64) {
         const int rp = idx < TL + 2 ? -1 : TP;
         const int rl = (idx < TL + 2 ? idx : idx - (TL + 2)) - 1;  // -1 .. TL
         const int l = l0 + rl, p = p0 + rp;
@@ -2059,7 +2065,7 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* __
         const int rl_lo = max(l0, 0) - l0, rl_hi = min(l0 + TL, L) - l0;  // in-image tile lines [rl_lo, rl_hi) (rel.)
         const int rp_lo = 0, rp_hi = min(p0 + TP, P) - p0;
         (void)rl_lo; (void)rp_lo;
-        for (int idx = threadIdx.x; idx < 2 * (TP + 2) + 2 * (TL + 2); idx += NT) {
+        for (int idx = threadIdx.x; idx < 2 * (TP + 2) + 2 * (TL + 2); idx += NTH) {
             int rl, rp;
             if (idx < TP + 2) { rl = -1; rp = idx - 1; }                       // line above the tile
             else if (idx < 2 * (TP + 2)) { rl = rl_hi; rp = idx - (TP + 2) - 1; }  // first line below the in-image part
@@ -2075,14 +2081,14 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* __
     }
     // ---- phase 2: e_u and the correlation sums ----
     {
-        const float* ub = ut + (4 * w) * SW;
+        const float* ub = ut + (LPT * w) * SW;
         float r0[6], r1[6], r2[6];
         load_win6(r0, ub, scol);
         load_win6(r1, ub + SW, scol);
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < LPT; r++) {
             load_win6(r2, ub + (r + 2) * SW, scol);
-            const bool lok = FULL || (l0 + 4 * w + r < L);
+            const bool lok = FULL || (l0 + LPT * w + r < L);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const bool ok = FULL || (lok && pb + j < P);
@@ -2091,7 +2097,7 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* __
                 fd = __fmaf_rn(eu, e, fd);
                 fz = __fmaf_rn(e, e, fz);
                 fu = __fmaf_rn(eu, eu, fu);
-                if constexpr (DBG) { if (ok) dbg_eu[(long long)(l0 + 4 * w + r) * P + pb + j] = eu; }
+                if constexpr (DBG) { if (ok) dbg_eu[(long long)(l0 + LPT * w + r) * P + pb + j] = eu; }
             }
 #pragma unroll
             for (int i = 0; i < 6; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
@@ -2099,10 +2105,13 @@ __device__ __forceinline__ void detect_tile(const ZT* __restrict__ zt, float* __
     }
 }
 
-template <typename PixT, int MASK, bool TR, bool TMA, bool DBG = false>
-__global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_detect(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW,
+template <typename PixT, int MASK, bool TR, bool TMA, bool DBG = false, int NTH = NT>
+__global__ void __launch_bounds__(NTH, NTH == NT ? detect_ctas_per_sm(sizeof(PixT) == 1) : DETECT_CTAS_PER_SM_U8N) k_detect(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW,
                                                   const DetectArgs a)
 {
+    constexpr bool NARROW = NTH != wm::NT;  // u8 TMA frames: 4 warps x 8 lines, u in place over the W tile
+    constexpr int NT = NTH;                 // every NT below is this kernel's own CTA size
+    static_assert(!NARROW || (TMA && sizeof(PixT) == 1 && !DBG), "the 128-thread detector exists for u8 TMA frames only");
     extern __shared__ __align__(128) unsigned char dsm[];
     __shared__ double red[8 * 3];
     __shared__ __align__(8) uint64_t bars[DETECT_NST];
@@ -2110,7 +2119,7 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
     constexpr bool U8T = TMA && sizeof(PixT) == 1;
     constexpr int STG = TMA ? detect_stage(U8T) : SZ_I36 + SZ_I34, ZPART = U8T ? U8_I36 : SZ_I36;
     using ZT = typename std::conditional<U8T, unsigned char, float>::type;  // u8 TMA stages are read where they landed
-    float* const ut = reinterpret_cast<float*>(dsm + (size_t)NST * STG);      // (TL+2) x SW, lines l0-1 .. l0+TL
+    float* const ut_sep = reinterpret_cast<float*>(dsm + (size_t)NST * STG);  // (TL+2) x SW, lines l0-1 .. l0+TL (not NARROW)
     pdl_launch_dependents();
     const int b = blockIdx.y + a.b0;
     Scal* sc = a.scal + b;
@@ -2176,8 +2185,8 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
             wt = reinterpret_cast<float*>(stage(pos.s) + ZPART);
             zt = reinterpret_cast<ZT*>(stage(pos.s));
             pos.next();
-            patched = tile_on_frame<TL + 4>(l0 - 2, p0 - HP, L, P);
-            if (patched) { fix_border<TL + 4>(zt, l0 - 2, p0 - HP, L, P); __syncthreads(); }
+            patched = NARROW || tile_on_frame<TL + 4>(l0 - 2, p0 - HP, L, P);  // NARROW: the W tile of every stage is overwritten with u
+            if (tile_on_frame<TL + 4>(l0 - 2, p0 - HP, L, P)) { fix_border<TL + 4, NTH>(zt, l0 - 2, p0 - HP, L, P); __syncthreads(); }
         } else {
             zt = reinterpret_cast<ZT*>(dsm);
             wt = reinterpret_cast<float*>(dsm) + SZ_I36 / 4;
@@ -2190,18 +2199,19 @@ __global__ void __launch_bounds__(NT, detect_ctas_per_sm(sizeof(PixT) == 1)) k_d
                 wpre.issue(a.W, P, L, P, pf.tl * TL - 1, pf.tp * TP - HP, a.w_vec_ok != 0);
             }
         }
+        float* const ut = NARROW ? wt : ut_sep;
         float fd = 0.0f, fz = 0.0f, fu = 0.0f;
-        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true, DBG>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr, a.dbg_u, a.dbg_eu, kb);
-        else detect_tile<MASK, TR, false, DBG>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr, a.dbg_u, a.dbg_eu, kb);
+        if (l0 + TL <= L && p0 + TP <= P) detect_tile<MASK, TR, true, DBG, ZT, NTH>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr, a.dbg_u, a.dbg_eu, kb);
+        else detect_tile<MASK, TR, false, DBG, ZT, NTH>(zt, wt, ut, c, l0, p0, L, P, fd, fz, fu, MASK == 2 ? a.maskp + (long long)b * a.mask_bstride : nullptr, a.dbg_u, a.dbg_eu, kb);
         ddot += (double)fd; dnz += (double)fz; dnu += (double)fu;
         if constexpr (TMA) __syncthreads();  // ut and the stage are rewritten from the next iteration on
     }
     __syncthreads();
     const double v3[3] = {ddot, dnz, dnu};
-    block_sum<3>(v3, red);
+    block_sum<3, NTH>(v3, red);
     if (threadIdx.x < 3) a.part[((size_t)b * a.pstride + blockIdx.x) * 3 + threadIdx.x] = red[threadIdx.x];
     if (!last_block(a.counter + b, step)) return;
-    block_column_reduce<3, 4, 3>(a.part + (size_t)b * a.pstride * 3, step, red, reinterpret_cast<double*>(dsm));
+    block_column_reduce<3, 4, 3, NTH>(a.part + (size_t)b * a.pstride * 3, step, red, reinterpret_cast<double*>(dsm));
     if (threadIdx.x == 0) {
         a.dbg[b].dot = red[0]; a.dbg[b].nz = red[1]; a.dbg[b].nu = red[2];
         const float dotf = (float)red[0];

@@ -9,7 +9,7 @@ void launch_apply(int in_dtype, int out_dtype, int mask, bool tr, bool tma, dim3
                   const CUtensorMap& tmW, const EmbedArgs& a);
 void launch_apply_ts(int dtype, int mask, bool tr, bool narrow, dim3 grid, cudaStream_t st, const CUtensorMap& tmI, const CUtensorMap& tmW, const CUtensorMap& tmO,
                      const EmbedArgs& a);
-void launch_detect(int dtype, int mask, bool tr, bool tma, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a);
+void launch_detect(int dtype, int mask, bool tr, bool tma, bool narrow, dim3 grid, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const DetectArgs& a);
 // single-image fused detect (cooperative launch): false when the grid cannot be co-resident or the launch fails (the caller falls back)
 bool launch_detect1(int mask, bool tr, int grid_x, cudaStream_t st, const CUtensorMap& tmZ, const CUtensorMap& tmW, const SweepArgs& sa,
                     const DetectArgs& a, unsigned* gen, int sms);
