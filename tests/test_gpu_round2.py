@@ -626,3 +626,40 @@ def test_narrow_u8_kernels_equal_wide_ones(wmb, oracle, rows, cols, ls):
     report("narrow vs wide u8 kernels %dx%d ls=%d: a rel diff %.2g, differing bytes %d, corr rel diff %.2g" % (
         rows, cols, ls, float(np.max(np.abs(a1[ok] - a0[ok]) / a0[ok])), int(np.count_nonzero(o1 != o0)),
         float(np.max(np.abs(c1[okc] - c0[okc]) / np.abs(c0[okc])))))
+
+
+@pytest.mark.parametrize("p", [3, 5])
+@pytest.mark.parametrize("rows,cols", [(96, 160), (270, 480)])
+def test_u8_images_both_masks_narrow_kernels(wmb, oracle, rows, cols, p):
+    """u8 images through the batch API with BOTH masks (the video driver only ever uses ME): the 128-thread u8 kernels with the fused 3 x 3
+    NVF mask (p = 3) and with the precomputed mask planes of a larger window (p = 5: stats / detector in the 128-thread form, apply in the
+    256-thread one on the same grid), against the oracle's u8 frame path."""
+    B = 3
+    W = util.normal_w(rows, cols)
+    o = oracle.opts(p=p)
+    ys = np.stack([util.natural_image(rows, cols, seed=950 + b, integer=True) for b in range(B)])
+    for narrow in (1, 0):
+        wm = wmb.Watermark(rows, cols, W, p, 40.0)
+        wm.set_option(wmb.OPT_NARROW_U8, narrow)
+        L = wmb.lib()
+        din = L.wm_dev_alloc(wm._h, ys.nbytes)
+        dout = L.wm_dev_alloc(wm._h, ys.nbytes)
+        L.wm_dev_upload(wm._h, din, ys.ctypes.data, ys.nbytes)
+        di = wmb.image_desc(din, rows, cols, wmb.ROW_MAJOR, wmb.U8)
+        do = wmb.image_desc(dout, rows, cols, wmb.ROW_MAJOR, wmb.U8)
+        for mask in (wmb.NVF, wmb.ME):
+            ab, cb = np.zeros(B, np.float32), np.zeros(B, np.float32)
+            wm.embed_batch(0, di, di, do, rows * cols, rows * cols, rows * cols, B, mask, ab)
+            wm.detect_batch(0, do, rows * cols, B, mask, cb)
+            wm.sync(0)
+            out = np.zeros_like(ys)
+            L.wm_dev_download(wm._h, out.ctypes.data, dout, out.nbytes)
+            for b in range(B):
+                st, oo, oa = oracle.embed_frame_u8(ys[b], W, 40.0, mask, o=o)
+                st2, oc = oracle.detect_frame_u8(oo, W, mask, o=o)
+                assert st == 0 and abs(ab[b] - oa) <= 1e-3 * oa, (narrow, mask, b, ab[b], oa)
+                assert int(np.abs(out[b].astype(np.int32) - oo.astype(np.int32)).max()) <= 1
+                assert abs(cb[b] - oc) <= 1e-3 * abs(oc), (narrow, mask, b, cb[b], oc)
+        L.wm_dev_free(wm._h, din)
+        L.wm_dev_free(wm._h, dout)
+        wm.close()
