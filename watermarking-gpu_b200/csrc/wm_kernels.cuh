@@ -29,6 +29,11 @@
 // products are packed-half multiplies.  With TMA = false (odd strides / sizes) a register-prefetched cooperative
 // clamped loader fills a single stage.  Every reduction ends in a last-block second stage run by the whole CTA
 // (block_column_reduce), so results are bit-reproducible for a given grid.
+//
+// CTA shapes.  256 threads = 8 warps x 4 lines of a tile (stats / apply / detect, f32 images and the plain loaders), or 128 threads =
+// 4 warps x 8 lines (the sweep, and stats / apply / detect of u8 TMA frames, four CTAs per SM): what a thread spends per TILE — tile walk,
+// TMA issue, frame tests, barriers — is then paid once per 32 pixels instead of 16 and its rolling 3-line window loads 10 lines per 8.
+// The u8 detector writes u = mask.W in place over the W tile, so it needs no separate u tile.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
