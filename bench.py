@@ -41,8 +41,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOADS = {
     # name: (rows, cols, frames per API call, calls per step, kind, dtype).  Frames per call divide the resident CTA counts of a launch
-    # (3 x 148 for sweep / stats / apply, 2 x 148 for the detector); calls per step make the timed region of a default run >= 1 s.
-    "video4k": (2160, 3840, 1184, 1, "video", "u8"),      # one wm_process_frames call over the rank's whole chunk (runs of 10-11 frames inside)
+    # (4 x 148 for the sweep and the u8 kernels, 3 x 148 / 2 x 148 for f32 stats / apply / detector); frames and calls per step make the timed
+    # region of a default run (20 steps) >= 1 s.
+    "video4k": (2160, 3840, 1332, 1, "video", "u8"),      # one wm_process_frames call over the rank's whole chunk (111 runs of 12 frames inside)
     "image1080p": (1080, 1920, 148, 12, "image", "f32"),
     "image4k": (2160, 3840, 37, 12, "image", "f32"),
     "image8k": (4320, 7680, 4, 28, "image", "f32"),
