@@ -376,6 +376,7 @@ template <int NROWS, int NTH = NT>
 __device__ __forceinline__ void convert_u8_tile(const unsigned char* __restrict__ src, float* __restrict__ dst)
 {
     constexpr int NT = NTH;  // shadows the CTA-wide default inside this function
+    __builtin_assume(threadIdx.x < (unsigned)NT);
     constexpr int NIT = (NROWS + NT / 32 - 1) / (NT / 32);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned char* s0 = src + w * U8_ROW + U8_OFF + 4 * lane;
@@ -414,6 +415,7 @@ template <int NROWS, int NTH = NT>
 __device__ __forceinline__ void convert_u8_tile_h(const unsigned char* __restrict__ src, __half* __restrict__ dst)
 {
     constexpr int NT = NTH;
+    __builtin_assume(threadIdx.x < (unsigned)NT);  // lets the row tests below fold for all but the last step
     constexpr int NIT = (NROWS + NT / 32 - 1) / (NT / 32);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned char* s0 = src + w * U8_ROW + U8_OFF + 4 * lane;
