@@ -43,7 +43,7 @@ WORKLOADS = {
     # name: (rows, cols, frames per API call, calls per step, kind, dtype).  Frames per call divide the resident CTA counts of a launch
     # (4 x 148 for the sweep and the u8 kernels, 3 x 148 / 2 x 148 for f32 stats / apply / detector); frames and calls per step make the timed
     # region of a default run (20 steps) >= 1 s.
-    "video4k": (2160, 3840, 1332, 1, "video", "u8"),      # one wm_process_frames call over the rank's whole chunk (111 runs of 12 frames inside)
+    "video4k": (2160, 3840, 1332, 1, "video", "u8"),      # one wm_process_frames call over the rank's whole chunk (79 runs of 16-17 frames inside)
     "image1080p": (1080, 1920, 148, 12, "image", "f32"),
     "image4k": (2160, 3840, 37, 12, "image", "f32"),
     "image8k": (4320, 7680, 4, 28, "image", "f32"),
@@ -252,6 +252,7 @@ def main():
     ap.add_argument("--fhadd", action="store_true", help="sum the rounded Rx/rx products with the FHADD chain instead of HMMA (A/B)")
     ap.add_argument("--no-tma-store", action="store_true", help="WM_OPT_TMA_STORE = 0: apply kernel output through per-thread vector stores (A/B)")
     ap.add_argument("--no-narrow", action="store_true", help="WM_OPT_NARROW_U8 = 0: u8 stats / apply on 256-thread CTAs (A/B)")
+    ap.add_argument("--run-mb", type=int, default=0, help="WM_OPT_RUN_MB: MB of device frames per run of the video driver (A/B)")
     ap.add_argument("--host-run", type=int, default=0, help="WM_OPT_HOST_RUN_FRAMES for the e2e video path (A/B)")
     ap.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e pass (0 = 128 for video, 96 for images)")
     args = ap.parse_args()
@@ -361,6 +362,8 @@ def run_workload(args, wl, torch, dist, dev, rank, local_rank, world, secondary=
         wm.set_option(pkg.OPT_TMA_STORE, 0)
     if args.no_narrow:
         wm.set_option(pkg.OPT_NARROW_U8, 0)
+    if args.run_mb:
+        wm.set_option(pkg.OPT_RUN_MB, args.run_mb)
     dt_code = pkg.U8 if dtype == "u8" else pkg.F32
     esz = 1 if dtype == "u8" else 4
     # image workloads: ArrayFire layout (column-major); video: row-major Y planes

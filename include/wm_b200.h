@@ -83,6 +83,9 @@ enum {
                                  the way up by a 2-D copy (the reference's row-by-row repack, main.cpp:348-353) */
     WM_OPT_NARROW_U8 = 14,    /* 1 (default): the stats / apply kernels of u8 frames (TMA path) run on 128-thread CTAs, 4 warps x 8 lines of a tile, four CTAs per SM,
                                  like the sweep; 0: 256-thread CTAs, 8 warps x 4 lines, three per SM.  Same bits */
+    WM_OPT_RUN_MB = 15,       /* frames of one run (one batched launch sequence) of wm_process_frames on DEVICE frames fill at most this many MB (default 136, at most
+                                 32 frames): large enough to amortise a launch's ramp and tail, small enough that a run's watermarked frames are still in L2 when
+                                 the detector's kernels read them back */
     WM_OPT_HOST_RUN_FRAMES = 9, /* frames per run (one batched launch sequence + its copies) of wm_process_frames when frames are in HOST memory; default 4 */
     WM_OPT_F32_SOLVE = 8      /* 0 (default): the 8x8 system is summed and solved in f64 (pivot cut 1e-12 max|Rx|); 1: Rx / rx are rounded to f32
                                  and solved by an f32 LU (pivot cut 1e-6 max|Rx|) like af::solve on the reference's f32 arrays

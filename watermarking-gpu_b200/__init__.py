@@ -22,7 +22,7 @@ COL_MAJOR, ROW_MAJOR = 0, 1
 F32, U8 = 0, 1
 OK, SINGULAR, ZERO_MASK = 0, 1, 2
 OPT_FP16_PRODUCTS, OPT_KERNEL_TIMING, OPT_USE_TMA, OPT_SERIAL_SLOTS, OPT_CUDA_GRAPHS, OPT_MMA_ACCUM, OPT_SPLIT_COST = 1, 2, 3, 4, 5, 6, 7
-OPT_F32_SOLVE, OPT_HOST_RUN_FRAMES, OPT_TMA_STORE, OPT_PDL, OPT_FUSED_SINGLE, OPT_PADDED_UPLOAD, OPT_NARROW_U8 = 8, 9, 10, 11, 12, 13, 14
+OPT_F32_SOLVE, OPT_HOST_RUN_FRAMES, OPT_TMA_STORE, OPT_PDL, OPT_FUSED_SINGLE, OPT_PADDED_UPLOAD, OPT_NARROW_U8, OPT_RUN_MB = 8, 9, 10, 11, 12, 13, 14, 15
 DBG_RX, DBG_RXVEC, DBG_COEFFS, DBG_SCALARS, DBG_ERRSEQ, DBG_MASK_NVF, DBG_PHASES, DBG_MASK_ME = range(8)
 KERNEL_NAMES = ["rx_sweep", "me_stats", "nvf_stats", "me_apply", "me_detect", "nvf_apply", "nvf_detect"]
 VIDEO_EMBED, VIDEO_DETECT, VIDEO_EMBED_VERIFY = 0, 1, 2

@@ -78,6 +78,7 @@ struct wm_ctx {
     Slot slots[NSLOTS];
     int opt_fp16 = 1, opt_timing = 0, opt_tma = 1, opt_serial = 0, opt_mma = 1, opt_f32_solve = 0;
     int opt_pdl = 1;         // WM_OPT_PDL: 2nd / 3rd kernel of an op launched with programmatic stream serialization
+    int opt_run_mb = 136;       // WM_OPT_RUN_MB: frames of a run of the video driver (device frames) fill at most this many MB (4K u8: 17 frames)
     int opt_narrow_u8 = 1;      // WM_OPT_NARROW_U8: stats / apply of u8 TMA frames on 128-thread CTAs (8 lines per thread), four per SM
     int opt_padded_upload = 1;  // WM_OPT_PADDED_UPLOAD: host video frames with a small row padding are uploaded with it (one linear copy per frame)
     int opt_fused = 0;       // WM_OPT_FUSED_SINGLE: synchronous single-image detect as one cooperative kernel where the image fits (measured slower: off)
@@ -953,7 +954,7 @@ int wm_clone(const wm_ctx* src, wm_ctx** out)
     ctx->p = src->p; ctx->psnr = src->psnr; ctx->strength = src->strength;
     ctx->w = src->w;
     ctx->opt_fp16 = src->opt_fp16; ctx->opt_mma = src->opt_mma; ctx->opt_split_cost = src->opt_split_cost; ctx->opt_timing = src->opt_timing; ctx->opt_tma = src->opt_tma;
-    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run; ctx->opt_tma_store = src->opt_tma_store; ctx->opt_pdl = src->opt_pdl; ctx->opt_fused = src->opt_fused; ctx->opt_padded_upload = src->opt_padded_upload; ctx->opt_narrow_u8 = src->opt_narrow_u8;
+    ctx->opt_serial = src->opt_serial; ctx->opt_graphs = src->opt_graphs; ctx->opt_f32_solve = src->opt_f32_solve; ctx->opt_host_run = src->opt_host_run; ctx->opt_tma_store = src->opt_tma_store; ctx->opt_pdl = src->opt_pdl; ctx->opt_fused = src->opt_fused; ctx->opt_padded_upload = src->opt_padded_upload; ctx->opt_narrow_u8 = src->opt_narrow_u8; ctx->opt_run_mb = src->opt_run_mb;
     const int rc = init_slots(ctx, nullptr);
     if (rc) { g_create_error = ctx->err; wm_destroy(ctx); return rc; }
     *out = ctx;
@@ -1007,6 +1008,7 @@ int wm_set_option(wm_ctx* ctx, int option, int value)
     case WM_OPT_FUSED_SINGLE: ctx->opt_fused = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_PADDED_UPLOAD: ctx->opt_padded_upload = value != 0; return WM_OK;
     case WM_OPT_NARROW_U8: ctx->opt_narrow_u8 = value != 0; clear_graphs(ctx); return WM_OK;
+    case WM_OPT_RUN_MB: ctx->opt_run_mb = std::max(1, std::min(value, 4096)); return WM_OK;
     case WM_OPT_F32_SOLVE: ctx->opt_f32_solve = value != 0; clear_graphs(ctx); return WM_OK;
     case WM_OPT_SPLIT_COST: ctx->opt_split_cost = value < 0 ? 1 << 28 : value; return WM_OK;
     default: return fail(ctx, WM_ERR_ARG, "unknown option");
@@ -1388,8 +1390,9 @@ int64_t wm_process_frames(const wm_video_ctx* v, int mode, const uint8_t* frames
     // blockIdx.y); runs go round-robin over the slots so copies, kernels and the per-frame solves of different runs overlap
     const int64_t fbytes = H * Wd;
     // frames per run: big enough to amortise a launch's ramp and second-stage tail, small enough that several runs are in
-    // flight on different slots (4K u8: 4 / 7 / 10 / 19 / 37 frames per run gave 17.1k / 18.2k / 19.0k / 18.5k / 18.2k frames/s)
-    int64_t B = v->frames_on_device ? std::max<int64_t>(1, std::min<int64_t>(32, (96LL << 20) / fbytes)) : ctx->opt_host_run;
+    // flight on different slots (round 1, 4K u8: 4 / 7 / 10 / 19 / 37 frames per run gave 17.1k / 18.2k / 19.0k / 18.5k / 18.2k frames/s; with the
+    // round-2 kernels 7 / 9 / 11 / 13 / 16 / 24 / 32 frames per run give 25.2k / 25.2k / 25.5k / 25.6k / 25.8k / 25.8k / 25.8k: WM_OPT_RUN_MB = 136)
+    int64_t B = v->frames_on_device ? std::max<int64_t>(1, std::min<int64_t>(32, ((int64_t)ctx->opt_run_mb << 20) / fbytes)) : ctx->opt_host_run;
     // even runs (37 frames at 7 per run: 7,6,6,6,6,6 rather than 7,7,7,7,7,2)
     const int64_t nruns = ngated > 0 ? (ngated + B - 1) / B : 0;
     const int64_t run_base = nruns ? ngated / nruns : 0, run_extra = nruns ? ngated % nruns : 0;
